@@ -1,0 +1,154 @@
+/* b2t_b200 -- C ABI of the B200-native GRU -> CTC -> n-gram decode hot path.
+ *
+ * Every entry point takes plain pointers and sizes (device pointers where noted); no torch or
+ * C++ types cross the boundary.  `stream` is a cudaStream_t passed as void*.
+ * Functions return 0 (or a non-negative value) on success and a negative code on failure;
+ * b2t_last_error() returns a human-readable message for the calling thread's last failure.
+ *
+ * Reference interfaces replaced (file:line under the upstream repository):
+ *   b2t_forward ............ GRUDecoder.forward            model_training/rnn_model.py:88-134
+ *                            + transform_data/gauss_smooth  model_training/rnn_trainer.py:436-484,
+ *                                                           model_training/data_augmentations.py:6-37
+ *                            + runSingleDecodingStep        model_training/evaluate_model_helpers.py:87-115
+ *   b2t_ctc_loss ........... log_softmax + torch.nn.CTCLoss model_training/rnn_trainer.py:242,538-545
+ *   b2t_backward ........... loss.backward()                model_training/rnn_trainer.py:547
+ *   b2t_optimizer_step ..... clip_grad_norm_ + AdamW.step   model_training/rnn_trainer.py:550-558,259-292
+ *   b2t_greedy_edit ........ greedy decode + edit distance  model_training/rnn_trainer.py:724-736
+ *   b2t_decoder_* .......... lm_decoder pybind module       language_model/runtime/server/x86/python/lm_decoder.cc:14-75
+ *                            BrainSpeechDecoder             language_model/runtime/core/decoder/brain_speech_decoder.h:22-148
+ */
+#ifndef B2T_B200_H_
+#define B2T_B200_H_
+
+#if defined(B2T_EXPORTS)
+#define B2T_API __attribute__((visibility("default")))
+#else
+#define B2T_API
+#endif
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2T_OK 0
+#define B2T_ERR_ARG (-1)
+#define B2T_ERR_CUDA (-2)
+#define B2T_ERR_WORKSPACE (-3)
+#define B2T_ERR_UNSUPPORTED (-4)
+#define B2T_ERR_STATE (-5)
+
+const char* b2t_last_error(void);
+int b2t_version(void);
+
+/* ------------------------------------------------------------------ model / engine */
+
+typedef struct b2t_config {
+  int neural_dim;    /* input channels (512) */
+  int n_units;       /* GRU hidden size (768); multiple of 64, <= 768 */
+  int n_layers;      /* stacked GRU layers (5) */
+  int n_days;        /* number of day-specific input layers (45) */
+  int n_classes;     /* CTC classes incl. blank (41); <= 64 */
+  int patch_size;    /* 14 (0 disables patching) */
+  int patch_stride;  /* 4 */
+  float rnn_dropout;   /* between GRU layers, training only (0.4) */
+  float input_dropout; /* after the day layer, training only (0.2) */
+} b2t_config;
+
+/* Flat parameter layout.  Parameters live in ONE fp32 buffer owned by the caller; segment i has the
+ * reference state_dict name (day_weights.{d}, day_biases.{d}, gru.weight_ih_l{k}, gru.weight_hh_l{k},
+ * gru.bias_ih_l{k}, gru.bias_hh_l{k}, out.weight, out.bias, h0), an element offset (multiple of 64)
+ * and a [rows, cols] shape.  Returns the number of segments; with index >= 0 fills the outputs. */
+int b2t_param_segments(const b2t_config* cfg);
+int b2t_param_segment(const b2t_config* cfg, int index, char* name, int name_cap, long long* offset, long long* rows,
+                      long long* cols);
+/* Elements of the flat parameter buffer, and of the gradient buffer (= parameters + n_days "touched"
+ * flags at the tail, so that ONE all-reduce carries both). */
+long long b2t_param_elems(const b2t_config* cfg);
+long long b2t_grad_elems(const b2t_config* cfg);
+long long b2t_workspace_bytes(const b2t_config* cfg, int max_batch, int max_T, int max_label_len, int training);
+
+typedef struct b2t_engine b2t_engine;
+
+/* All buffers are device memory owned by the caller and must outlive the engine.
+ * grads / exp_avg / exp_avg_sq may be NULL for an inference-only engine (training == 0). */
+b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, int max_T, int max_label_len, int training,
+                              float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* workspace,
+                              long long workspace_bytes);
+void b2t_engine_destroy(b2t_engine* e);
+
+/* Re-derive the bf16 operand copies (and W_hh^T) from the fp32 parameters, e.g. after load_state_dict. */
+int b2t_refresh_weights(b2t_engine* e, void* stream);
+
+typedef struct b2t_forward_args {
+  const float* x;           /* device [B][T][neural_dim] fp32 */
+  int B, T;
+  const int* day_idx;       /* device int32 [B] */
+  int training;             /* 1: dropout active and activations saved for b2t_backward */
+  int smooth_mode;          /* 0 none, 1 'same' (trainer), 2 'valid' (evaluate_model) */
+  float smooth_std;         /* 2.0 */
+  int smooth_size;          /* 100 */
+  int cut;                  /* random_cut draw: frames dropped from the front */
+  float white_noise_std;    /* 0 disables */
+  float offset_noise_std;   /* 0 disables */
+  const float* white_noise; /* optional explicit N(0,1) draws, device [B][T][neural_dim] */
+  const float* offset_noise;/* optional explicit N(0,1) draws, device [B][neural_dim] */
+  unsigned long long seed;  /* device RNG stream for noise (when no explicit draws) and dropout */
+  const float* states;      /* optional device [n_layers][B][n_units] initial state; NULL => h0 */
+  float* logits_out;        /* optional device [B][T'][n_classes] fp32 */
+  float* hidden_out;        /* optional device [n_layers][B][n_units] fp32 */
+} b2t_forward_args;
+
+/* Returns T' (number of output frames) or a negative error code. */
+int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* stream);
+/* T' for an input of T frames under the given smoothing mode and cut. */
+int b2t_output_frames(const b2t_config* cfg, int T, int smooth_mode, int smooth_std_taps, int cut);
+
+/* CTC on the logits of the last b2t_forward.  labels: device int32 [B][Smax]; in_len/tgt_len: device
+ * int32 [B]; loss_out: device fp32 [B] (per-trial, reduction 'none').  With want_grad, the gradient of
+ * grad_scale * sum_b loss_b (grad_scale = 1/global_batch reproduces torch.mean) is kept inside the
+ * engine for b2t_backward. */
+int b2t_ctc_loss(b2t_engine* e, const int* labels, int Smax, const int* in_len, const int* tgt_len, float grad_scale,
+                 float* loss_out, int want_grad, void* stream);
+/* Stand-alone CTC on caller logits (device [T][B][C] fp32, the nn.CTCLoss layout).  dlogits may be NULL. */
+int b2t_ctc_loss_tbc(const float* logits_tbc, int T, int B, int C, const int* labels, int Smax, const int* in_len,
+                     const int* tgt_len, float grad_scale, float* loss_out, float* dlogits_tbc, void* workspace,
+                     long long workspace_bytes, void* stream);
+long long b2t_ctc_workspace_bytes(int T, int B, int Smax);
+
+/* Provide d(loss)/d(logits) computed elsewhere (device [B][T'][n_classes]) instead of b2t_ctc_loss. */
+int b2t_set_dlogits(b2t_engine* e, const float* dlogits, void* stream);
+/* Back-propagate through head, GRU stack, patching and day layers into the flat gradient buffer.
+ * Gradients of day layers absent from the batch are left untouched (their "touched" flag stays 0). */
+int b2t_backward(b2t_engine* e, void* stream);
+
+typedef struct b2t_adamw_args {
+  float lr[3];            /* per group: 0 biases, 1 day layers, 2 everything else */
+  float weight_decay[3];
+  float beta1, beta2, eps;
+  float max_grad_norm;    /* <= 0 disables clipping */
+} b2t_adamw_args;
+/* stats_out: optional device fp32 [2] = {total gradient norm, clip coefficient}. */
+int b2t_optimizer_step(b2t_engine* e, const b2t_adamw_args* a, float* stats_out, void* stream);
+/* Per-segment AdamW step counters (device int32 [n_segments]) for checkpointing. */
+int* b2t_step_counters(b2t_engine* e);
+
+/* Greedy CTC decode + edit distance on the logits of the last forward (integer outputs). */
+int b2t_greedy_edit(b2t_engine* e, const int* labels, int Smax, const int* in_len, const int* tgt_len, int* decoded,
+                    int* dec_len, int* edit, void* stream);
+
+/* Number of kernels this library has launched on behalf of the calling process (bench accounting). */
+long long b2t_launch_count(void);
+
+/* ------------------------------------------------------------------ test hooks (also used by tests/) */
+/* C[M,N] = A[M,K] * B^T with B given as [N,K] (b_mn == 0) or as [K,N] (b_mn == 1), A as [M,K]
+ * (a_mn == 0) or [K,M] (a_mn == 1); bf16 inputs, fp32 or bf16 output, optional fp32 bias[N]. */
+int b2t_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int a_mn, int b_mn, int out_bf16,
+                  const float* bias, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2T_B200_H_ */

@@ -1,0 +1,181 @@
+// Fused log-softmax + CTC loss + gradient wrt logits (fp32 log-space), one CTA per trial.
+//
+// Reference: rnn_trainer.py:538-545 -- torch.nn.CTCLoss(blank=0, reduction='none',
+// zero_infinity=False) applied to logits.log_softmax(2), then torch.mean over the batch.
+// alpha/beta follow Graves et al. 2006 with both including the emission at t, so that
+//   dL/dlogit[t,c] = softmax[t,c] - exp(logsumexp_{s: l'_s = c}(alpha_t(s)+beta_t(s)) - lp[t,c] - ll)
+// (the form ATen's ctc_loss backward uses).  Label expansion, lengths and the skip rule are integer
+// logic and must match exactly; the floating-point part is compared at 1e-5 relative.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <cuda_bf16.h>
+
+namespace b2t {
+
+constexpr int CTC_THREADS = 128;
+
+struct CtcParams {
+  const float* logits;      // row (t*Bpad + b), pitch ldl floats
+  int ldl, Bpad, T, C, blank;
+  const int* labels;        // [B][Smax]
+  int Smax;
+  const int* in_len;        // [B]
+  const int* tgt_len;       // [B]
+  float* alpha;             // scratch [B][T][Lmax], Lmax = 2*Smax+1
+  float* loss;              // [B]
+  float* dlogits;           // fp32, same layout as logits (nullable => loss only)
+  __nv_bfloat16* dlogits_bf16;  // bf16 copy for the tensor-core GEMMs (nullable)
+  float* dbias;             // [C] atomicAdd of sum_t,b dlogits (nullable)
+  float grad_scale;         // 1 / global batch (torch.mean)
+};
+
+__device__ __forceinline__ float lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -CUDART_INF_F) return -CUDART_INF_F;
+  return m + log1pf(expf(fminf(a, b) - m));
+}
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, b), c);
+  if (m == -CUDART_INF_F) return -CUDART_INF_F;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+// dynamic smem: lp[T*C] | ext[Lmax] (int) | rowA[Lmax] | rowB[Lmax] | ab[Lmax]
+__global__ void __launch_bounds__(CTC_THREADS)
+ctc_loss_grad_kernel(const CtcParams p) {
+  extern __shared__ float ctc_smem[];
+  const int b = blockIdx.x;
+  const int Lmax = 2 * p.Smax + 1;
+  float* lp = ctc_smem;
+  int* ext = reinterpret_cast<int*>(lp + (size_t)p.T * p.C);
+  float* rowA = reinterpret_cast<float*>(ext + Lmax);
+  float* rowB = rowA + Lmax;
+  float* ab = rowB + Lmax;
+  __shared__ float s_ll;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int Tb = p.in_len[b];
+  Tb = Tb < 0 ? 0 : (Tb > p.T ? p.T : Tb);
+  const int S = p.tgt_len[b];
+  const int L = 2 * S + 1;
+  const float NINF = -CUDART_INF_F;
+
+  // ---- extended label sequence (integer logic)
+  for (int s = tid; s < L; s += CTC_THREADS) ext[s] = (s & 1) ? p.labels[(size_t)b * p.Smax + (s >> 1)] : p.blank;
+
+  // ---- log-softmax per frame: one warp per frame
+  for (int t = warp; t < Tb; t += CTC_THREADS / 32) {
+    const float* row = p.logits + ((size_t)t * p.Bpad + b) * p.ldl;
+    float m = NINF;
+    for (int c = lane; c < p.C; c += 32) m = fmaxf(m, row[c]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int c = lane; c < p.C; c += 32) sum += expf(row[c] - m);
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float lz = m + logf(sum);
+    for (int c = lane; c < p.C; c += 32) lp[t * p.C + c] = row[c] - lz;
+  }
+  __syncthreads();
+
+  float* alpha = p.alpha + (size_t)b * p.T * Lmax;
+  // ---- alpha recursion
+  float* prev = rowA;
+  float* cur = rowB;
+  if (Tb > 0) {
+    for (int s = tid; s < L; s += CTC_THREADS) {
+      float a = NINF;
+      if (s == 0) a = lp[p.blank];
+      else if (s == 1) a = lp[ext[1]];
+      prev[s] = a;
+      alpha[s] = a;
+    }
+  }
+  __syncthreads();
+  for (int t = 1; t < Tb; ++t) {
+    for (int s = tid; s < L; s += CTC_THREADS) {
+      const float a0 = prev[s];
+      const float a1 = s >= 1 ? prev[s - 1] : NINF;
+      const float a2 = (s >= 2 && ext[s] != p.blank && ext[s] != ext[s - 2]) ? prev[s - 2] : NINF;
+      const float a = lse3(a0, a1, a2) + lp[t * p.C + ext[s]];
+      cur[s] = a;
+      alpha[(size_t)t * Lmax + s] = a;
+    }
+    __syncthreads();
+    float* tmp = prev; prev = cur; cur = tmp;
+  }
+  if (tid == 0) {
+    float ll;
+    if (Tb > 0) ll = lse2(prev[L - 1], L > 1 ? prev[L - 2] : NINF);
+    else ll = (S == 0) ? 0.f : NINF;
+    s_ll = ll;
+    p.loss[b] = -ll;
+  }
+  __syncthreads();
+  if (!p.dlogits && !p.dlogits_bf16) return;
+  const float ll = s_ll;
+
+  // ---- beta recursion + gradient, t descending
+  float dbacc = 0.f;   // thread c < C accumulates sum_t dlogits[t][c]
+  float* bprev = rowA;
+  float* bcur = rowB;
+  for (int t = p.T - 1; t >= 0; --t) {
+    float* drow = p.dlogits ? p.dlogits + ((size_t)t * p.Bpad + b) * p.ldl : nullptr;
+    __nv_bfloat16* drow16 = p.dlogits_bf16 ? p.dlogits_bf16 + ((size_t)t * p.Bpad + b) * p.ldl : nullptr;
+    if (t >= Tb) {     // frames beyond the input length get zero gradient
+      for (int c = tid; c < p.ldl; c += CTC_THREADS) {
+        if (drow) drow[c] = 0.f;
+        if (drow16) drow16[c] = __float2bfloat16_rn(0.f);
+      }
+      continue;
+    }
+    for (int s = tid; s < L; s += CTC_THREADS) {
+      float v;
+      if (t == Tb - 1) {
+        v = (s == L - 1 || s == L - 2) ? lp[t * p.C + ext[s]] : NINF;
+      } else {
+        const float b0 = bprev[s];
+        const float b1 = s + 1 < L ? bprev[s + 1] : NINF;
+        const float b2 = (s + 2 < L && ext[s + 2] != p.blank && ext[s + 2] != ext[s]) ? bprev[s + 2] : NINF;
+        v = lse3(b0, b1, b2) + lp[t * p.C + ext[s]];
+      }
+      bcur[s] = v;
+      ab[s] = alpha[(size_t)t * Lmax + s] + v;
+    }
+    __syncthreads();
+    for (int c = tid; c < p.ldl; c += CTC_THREADS) {
+      float g = 0.f;
+      if (c < p.C) {
+        float m = NINF;
+        for (int s = (c == p.blank ? 0 : 1); s < L; s += 2)
+          if (ext[s] == c) m = fmaxf(m, ab[s]);
+        float occ = 0.f;
+        if (m != NINF) {
+          float sum = 0.f;
+          for (int s = (c == p.blank ? 0 : 1); s < L; s += 2)
+            if (ext[s] == c) sum += expf(ab[s] - m);
+          occ = expf(m + logf(sum) - ll - lp[t * p.C + c]);
+        }
+        g = (expf(lp[t * p.C + c]) - occ) * p.grad_scale;
+        dbacc += g;
+      }
+      if (drow) drow[c] = g;
+      if (drow16) drow16[c] = __float2bfloat16_rn(g);
+    }
+    __syncthreads();
+    float* tmp = bprev; bprev = bcur; bcur = tmp;
+  }
+  if (p.dbias) {
+    for (int c = tid; c < p.C; c += CTC_THREADS) {
+      // with C <= CTC_THREADS each thread owns one class; dbacc already holds its sum
+    }
+    if (tid < p.C) atomicAdd(p.dbias + tid, dbacc);
+  }
+}
+
+inline size_t ctc_smem_bytes(int T, int C, int Smax) {
+  const int Lmax = 2 * Smax + 1;
+  return ((size_t)T * C + 4 * (size_t)Lmax) * sizeof(float) + 16;
+}
+
+}  // namespace b2t

@@ -1,0 +1,759 @@
+// Engine: owns the buffer carving, tensor-map plans and kernel sequencing of the GRU -> CTC
+// training / inference step, and exports it through the C ABI in include/b2t_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b2t_b200.h"
+#include "ctc.cuh"
+#include "elementwise.cuh"
+#include "gemm.h"
+#include "gru_rec.cuh"
+#include "optim.cuh"
+#include "tmap.h"
+
+using namespace b2t;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t _e = (call);                                                                              \
+    if (_e != cudaSuccess) return fail(B2T_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+#define LAUNCHED() (++g_launches, cudaGetLastError())
+
+extern "C" const char* b2t_last_error(void) { return g_err; }
+extern "C" int b2t_version(void) { return 100; }
+extern "C" long long b2t_launch_count(void) { return g_launches; }
+
+// ------------------------------------------------------------------------------------ layout
+static inline long long r64(long long x) { return (x + 63) / 64 * 64; }
+static inline int r16(int x) { return (x + 15) / 16 * 16; }
+
+struct SegInfo {
+  std::string name;
+  long long offset, rows, cols;
+  int group, day;
+};
+
+static std::vector<SegInfo> build_layout(const b2t_config& c, long long* total) {
+  std::vector<SegInfo> v;
+  long long off = 0;
+  auto add = [&](const std::string& n, long long r, long long cc, int group, int day) {
+    v.push_back({n, off, r, cc, group, day});
+    off += r64(r * cc);
+  };
+  const int D = c.neural_dim, H = c.n_units;
+  const int K0 = D * (c.patch_size > 0 ? c.patch_size : 1);
+  for (int d = 0; d < c.n_days; ++d) add("day_weights." + std::to_string(d), D, D, 1, d);
+  for (int d = 0; d < c.n_days; ++d) add("day_biases." + std::to_string(d), 1, D, 1, d);
+  for (int l = 0; l < c.n_layers; ++l) {
+    const std::string s = std::to_string(l);
+    add("gru.weight_ih_l" + s, 3 * H, l == 0 ? K0 : H, 2, -1);
+    add("gru.weight_hh_l" + s, 3 * H, H, 2, -1);
+    add("gru.bias_ih_l" + s, 1, 3 * H, 0, -1);
+    add("gru.bias_hh_l" + s, 1, 3 * H, 0, -1);
+  }
+  add("out.weight", c.n_classes, H, 2, -1);
+  add("out.bias", 1, c.n_classes, 0, -1);
+  add("h0", 1, H, 2, -1);
+  if (total) *total = off;
+  return v;
+}
+
+static int check_cfg(const b2t_config* c) {
+  if (!c) return fail(B2T_ERR_ARG, "null config");
+  if (c->n_units % 64 != 0 || c->n_units < 64 || c->n_units > 768)
+    return fail(B2T_ERR_UNSUPPORTED, "n_units=%d: must be a multiple of 64 in [64,768] (W_hh slice must fit in shared memory)", c->n_units);
+  if (c->neural_dim % 8 != 0 || c->neural_dim < 8 || c->neural_dim > 1024) return fail(B2T_ERR_UNSUPPORTED, "neural_dim=%d: must be a multiple of 8, <= 1024", c->neural_dim);
+  if (c->n_classes < 2 || c->n_classes > 64) return fail(B2T_ERR_UNSUPPORTED, "n_classes=%d: must be in [2,64]", c->n_classes);
+  if (c->n_layers < 1 || c->n_layers > 16 || c->n_days < 1) return fail(B2T_ERR_ARG, "bad n_layers/n_days");
+  if (c->patch_size < 0 || (c->patch_size > 0 && c->patch_stride < 1)) return fail(B2T_ERR_ARG, "bad patch config");
+  return 0;
+}
+
+extern "C" int b2t_param_segments(const b2t_config* cfg) {
+  if (check_cfg(cfg)) return B2T_ERR_ARG;
+  return (int)build_layout(*cfg, nullptr).size();
+}
+extern "C" int b2t_param_segment(const b2t_config* cfg, int index, char* name, int name_cap, long long* offset, long long* rows, long long* cols) {
+  if (check_cfg(cfg)) return B2T_ERR_ARG;
+  auto v = build_layout(*cfg, nullptr);
+  if (index < 0 || index >= (int)v.size()) return fail(B2T_ERR_ARG, "segment index out of range");
+  if (name && name_cap > 0) snprintf(name, name_cap, "%s", v[index].name.c_str());
+  if (offset) *offset = v[index].offset;
+  if (rows) *rows = v[index].rows;
+  if (cols) *cols = v[index].cols;
+  return 0;
+}
+extern "C" long long b2t_param_elems(const b2t_config* cfg) {
+  if (check_cfg(cfg)) return B2T_ERR_ARG;
+  long long t = 0;
+  build_layout(*cfg, &t);
+  return t;
+}
+extern "C" long long b2t_grad_elems(const b2t_config* cfg) {
+  const long long t = b2t_param_elems(cfg);
+  return t < 0 ? t : t + r64(cfg->n_days);
+}
+
+// ------------------------------------------------------------------------------------ engine
+struct Carver {
+  uint8_t* base;
+  size_t off, cap;
+  bool dry;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) & ~size_t(1023);
+    T* p = dry ? nullptr : reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+constexpr int LDL = 64;   // pitch (elements) of logits / dlogits rows: 128 B in bf16, TMA friendly
+
+struct LayerBuf {
+  __nv_bfloat16 *hseq, *hdrop, *R, *Z, *Nn, *HN;
+};
+
+struct b2t_engine {
+  b2t_config cfg;
+  int maxB, maxT, maxS, training;
+  int D, H, L, C, K0, patch, stride;
+  std::vector<SegInfo> segs;
+  long long n_params;
+  float *params, *grads, *m1, *m2;
+  // carved buffers
+  __nv_bfloat16* shadow;
+  __nv_bfloat16* whhT;        // [L][H][3H]
+  __nv_bfloat16 *xs, *xd, *xu, *dxu, *dpre, *dGx, *dGh, *dlog16;
+  float *gx, *logits, *dlog32, *alpha, *dY[2], *dh0, *h_init, *h_final;
+  std::vector<LayerBuf> lay;
+  int *done, *day_pad, *steps, *greedy_scratch;
+  float *sumsq, *stats;
+  Segment* d_segs;
+  ChunkRef* d_chunks;
+  int n_chunks;
+  float* touched;             // tail of the gradient buffer: [n_days]
+  // current shape + plans
+  int B = 0, Bpad = 0, T_in = 0, T_out = 0, Tp = 0, M = 0;
+  bool plans_ok = false, use_unfold_copy = false;
+  GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw;
+  std::vector<GemmPlan> p_in, p_dwih, p_dwhh, p_dx;
+  std::vector<CUtensorMap> tm_w, tm_h, tm_wt;
+  CUtensorMap tm_g;
+  // state of the last forward
+  bool have_fwd = false, have_dlogits = false, fwd_training = false;
+  unsigned long long seed = 0;
+  const int* day_idx = nullptr;
+  bool states_given = false;
+};
+
+static long long seg_off(const b2t_engine* e, const std::string& n) {
+  for (auto& s : e->segs)
+    if (s.name == n) return s.offset;
+  return -1;
+}
+
+static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
+  Carver c{reinterpret_cast<uint8_t*>(ws), 0, cap, dry};
+  const int Bp = r16(e->maxB), T = e->maxT, D = e->D, H = e->H, L = e->L;
+  const int Tp = e->cfg.patch_size > 0 ? (T - e->patch) / e->stride + 1 : T;
+  const size_t M = (size_t)(Tp > 0 ? Tp : 1) * Bp;
+  const bool tr = e->training != 0;
+  e->shadow = c.take<__nv_bfloat16>(e->n_params);
+  e->whhT = c.take<__nv_bfloat16>((size_t)L * H * 3 * H);
+  e->xs = c.take<__nv_bfloat16>((size_t)Bp * T * D);
+  e->xd = c.take<__nv_bfloat16>((size_t)Bp * T * D);
+  e->xu = c.take<__nv_bfloat16>(M * e->K0);
+  e->gx = c.take<float>(M * 3 * H);
+  e->lay.resize(L);
+  for (int l = 0; l < L; ++l) {
+    e->lay[l].hseq = c.take<__nv_bfloat16>((M + Bp) * H);
+    e->lay[l].hdrop = (tr && l < L - 1) ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    e->lay[l].R = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    e->lay[l].Z = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    e->lay[l].Nn = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    e->lay[l].HN = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
+  }
+  e->h_init = c.take<float>((size_t)L * Bp * H);
+  e->h_final = c.take<float>((size_t)L * Bp * H);
+  e->logits = c.take<float>(M * LDL);
+  e->dlog32 = c.take<float>(M * LDL);
+  e->dlog16 = c.take<__nv_bfloat16>(M * LDL);
+  e->alpha = c.take<float>((size_t)e->maxB * (Tp > 0 ? Tp : 1) * (2 * e->maxS + 1));
+  e->done = c.take<int>((size_t)(Bp / 16) * (Tp > 0 ? Tp : 1) + 16);
+  e->day_pad = c.take<int>(Bp);
+  e->greedy_scratch = c.take<int>((size_t)e->maxB * 2 * (e->maxS + 1));
+  if (tr) {
+    e->dY[0] = c.take<float>(M * H);
+    e->dY[1] = c.take<float>(M * H);
+    e->dGx = c.take<__nv_bfloat16>(M * 3 * H);
+    e->dGh = c.take<__nv_bfloat16>(M * 3 * H);
+    e->dxu = c.take<__nv_bfloat16>(M * e->K0);
+    e->dpre = c.take<__nv_bfloat16>((size_t)Bp * T * D);
+    e->dh0 = c.take<float>((size_t)L * Bp * H);
+    e->sumsq = c.take<float>(4);
+    e->stats = e->sumsq ? e->sumsq + 1 : nullptr;
+    e->steps = c.take<int>(e->segs.size());
+    e->d_segs = c.take<Segment>(e->segs.size());
+    size_t nch = 0;
+    for (auto& s : e->segs) nch += (size_t)((s.rows * s.cols + OPT_CHUNK - 1) / OPT_CHUNK);
+    e->n_chunks = (int)nch;
+    e->d_chunks = c.take<ChunkRef>(nch);
+  }
+  return c.off + 1024;
+}
+
+extern "C" long long b2t_workspace_bytes(const b2t_config* cfg, int max_batch, int max_T, int max_label_len, int training) {
+  if (check_cfg(cfg)) return B2T_ERR_ARG;
+  b2t_engine e;
+  e.cfg = *cfg; e.maxB = max_batch; e.maxT = max_T; e.maxS = max_label_len > 0 ? max_label_len : 1; e.training = training;
+  e.D = cfg->neural_dim; e.H = cfg->n_units; e.L = cfg->n_layers; e.C = cfg->n_classes;
+  e.patch = cfg->patch_size > 0 ? cfg->patch_size : 1; e.stride = cfg->patch_size > 0 ? cfg->patch_stride : 1;
+  e.K0 = e.D * e.patch;
+  e.segs = build_layout(*cfg, &e.n_params);
+  return (long long)carve(&e, nullptr, 0, true);
+}
+
+extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, int max_T, int max_label_len, int training, float* params,
+                                         float* grads, float* exp_avg, float* exp_avg_sq, void* workspace, long long workspace_bytes) {
+  if (check_cfg(cfg)) return nullptr;
+  if (!params || !workspace || max_batch < 1 || max_T < 1) { fail(B2T_ERR_ARG, "null buffer or bad sizes"); return nullptr; }
+  if (training && (!grads || !exp_avg || !exp_avg_sq)) { fail(B2T_ERR_ARG, "training engine needs grads/exp_avg/exp_avg_sq"); return nullptr; }
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    fail(B2T_ERR_CUDA, "no CUDA device"); return nullptr;
+  }
+  if (major != 10) { fail(B2T_ERR_UNSUPPORTED, "this library contains sm_100a code only (device is sm_%d*)", major); return nullptr; }
+  const long long need = b2t_workspace_bytes(cfg, max_batch, max_T, max_label_len, training);
+  if (workspace_bytes < need) { fail(B2T_ERR_WORKSPACE, "workspace too small: %lld < %lld", workspace_bytes, need); return nullptr; }
+  b2t_engine* e = new b2t_engine();
+  e->cfg = *cfg; e->maxB = max_batch; e->maxT = max_T; e->maxS = max_label_len > 0 ? max_label_len : 1; e->training = training;
+  e->D = cfg->neural_dim; e->H = cfg->n_units; e->L = cfg->n_layers; e->C = cfg->n_classes;
+  e->patch = cfg->patch_size > 0 ? cfg->patch_size : 1; e->stride = cfg->patch_size > 0 ? cfg->patch_stride : 1;
+  e->K0 = e->D * e->patch;
+  e->segs = build_layout(*cfg, &e->n_params);
+  e->params = params; e->grads = grads; e->m1 = exp_avg; e->m2 = exp_avg_sq;
+  carve(e, workspace, (size_t)workspace_bytes, false);
+  e->touched = grads ? grads + e->n_params : nullptr;
+  if (training) {
+    std::vector<Segment> hs;
+    std::vector<ChunkRef> hc;
+    for (size_t i = 0; i < e->segs.size(); ++i) {
+      auto& s = e->segs[i];
+      hs.push_back({s.offset, s.rows * s.cols, s.group, s.day});
+      for (long long f = 0; f < s.rows * s.cols; f += OPT_CHUNK) hc.push_back({(int)i, (int)f});
+    }
+    if (cudaMemcpy(e->d_segs, hs.data(), hs.size() * sizeof(Segment), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(e->d_chunks, hc.data(), hc.size() * sizeof(ChunkRef), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(e->steps, 0, e->segs.size() * sizeof(int)) != cudaSuccess) {
+      fail(B2T_ERR_CUDA, "engine setup copies failed");
+      delete e;
+      return nullptr;
+    }
+  }
+  return e;
+}
+extern "C" void b2t_engine_destroy(b2t_engine* e) { delete e; }
+extern "C" int* b2t_step_counters(b2t_engine* e) { return e ? e->steps : nullptr; }
+
+extern "C" int b2t_refresh_weights(b2t_engine* e, void* stream) {
+  if (!e) return fail(B2T_ERR_ARG, "null engine");
+  cudaStream_t st = (cudaStream_t)stream;
+  cast_bf16_kernel<<<num_sms() * 4, 256, 0, st>>>(e->params, e->shadow, (size_t)e->n_params);
+  CK(LAUNCHED());
+  for (int l = 0; l < e->L; ++l) {
+    const long long off = seg_off(e, "gru.weight_hh_l" + std::to_string(l));
+    dim3 grid((e->H + 31) / 32, (3 * e->H + 31) / 32), blk(32, 8);
+    transpose_bf16_kernel<<<grid, blk, 0, st>>>(e->shadow + off, e->whhT + (size_t)l * e->H * 3 * e->H, 3 * e->H, e->H);
+    CK(LAUNCHED());
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ plans
+static int make_2d(CUtensorMap* tm, const void* p, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+  const uint64_t dims[4] = {inner, rows, 1, 1};
+  const uint64_t str[3] = {ld, ld * rows > 8 ? 8 : 8, 8};
+  const uint32_t box[4] = {64, box_rows, 1, 1};
+  (void)str;
+  const uint64_t s2[3] = {ld, 8, 8};
+  return make_tmap_bf16_4d(tm, p, dims, s2, box);
+}
+
+static int build_plans(b2t_engine* e) {
+  const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp, M = e->M, K0 = e->K0, T = e->T_in;
+  const bool tr = e->training != 0;
+  e->p_in.assign(L, GemmPlan());
+  e->p_dwih.assign(L, GemmPlan());
+  e->p_dwhh.assign(L, GemmPlan());
+  e->p_dx.assign(L, GemmPlan());
+  e->tm_w.assign(L, CUtensorMap());
+  e->tm_h.assign(L, CUtensorMap());
+  e->tm_wt.assign(L, CUtensorMap());
+  int rc;
+  {  // day layer: xd[b] = softsign(xs[b] @ W_day[day_b] + b_day[day_b]) (+dropout)      rnn_model.py:95-103
+    GemmSpec s;
+    s.a_mn = 0; s.b_mn = 1; s.epi = EPI_DAY; s.out_bf16 = 1;
+    s.M = e->T_out; s.N = D; s.K = D;
+    s.A = e->xs; s.lda = D; s.a_zstride = (long long)T * D; s.nz = e->B;
+    s.B = e->shadow + seg_off(e, "day_weights.0"); s.ldb = D; s.b_zstride = (long long)D * D; s.nzb = e->cfg.n_days;
+    s.z_map = e->day_idx; s.zmap_b = 1;
+    s.C = e->xd; s.ldc = D; s.c_zstride = (long long)T * D;
+    s.bias = e->params + seg_off(e, "day_biases.0"); s.bias_zstride = r64(D);
+    s.keep = 1.0f;
+    if ((rc = gemm_plan_build(&e->p_day, s))) return fail(B2T_ERR_CUDA, "day-layer plan failed (%d)", rc);
+  }
+  for (int l = 0; l < L; ++l) {
+    const std::string sl = std::to_string(l);
+    GemmSpec s;
+    s.a_mn = 0; s.b_mn = 0; s.epi = EPI_STORE; s.out_bf16 = 0;
+    s.N = 3 * H;
+    s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
+    s.C = e->gx; s.ldc = 3 * H;
+    s.bias = e->params + seg_off(e, "gru.bias_ih_l" + sl);
+    if (l == 0) {
+      s.K = K0; s.ldb = K0; s.M = M;
+      if (!e->use_unfold_copy) {   // strided patch view of xd (rnn_model.py:106-119), never materialised
+        s.A = e->xd; s.a_rin = Bp; s.a_rout = Tp; s.a_rin_stride = (long long)T * D; s.a_rout_stride = (long long)e->stride * D;
+        rc = gemm_plan_build(&e->p_in[0], s);
+        if (rc) {
+          fprintf(stderr, "b2t: strided patch tensor map rejected (%d); falling back to a materialised unfold\n", rc);
+          e->use_unfold_copy = true;
+        }
+      }
+      if (e->use_unfold_copy) {
+        s.a_rin = 0; s.A = e->xu; s.lda = K0;
+        if ((rc = gemm_plan_build(&e->p_in[0], s))) return fail(B2T_ERR_CUDA, "L0 input plan failed (%d)", rc);
+      }
+    } else {
+      s.K = H; s.ldb = H; s.M = M; s.lda = H;
+      s.A = e->lay[l - 1].hdrop ? e->lay[l - 1].hdrop : e->lay[l - 1].hseq + (size_t)Bp * H;
+      if ((rc = gemm_plan_build(&e->p_in[l], s))) return fail(B2T_ERR_CUDA, "input plan %d failed (%d)", l, rc);
+    }
+    if (make_2d(&e->tm_w[l], e->shadow + seg_off(e, "gru.weight_hh_l" + sl), H, 3 * H, H, 32)) return fail(B2T_ERR_CUDA, "W_hh map failed");
+    if (make_2d(&e->tm_h[l], e->lay[l].hseq, H, (uint64_t)(Tp + 1) * Bp, H, 16)) return fail(B2T_ERR_CUDA, "hseq map failed");
+    if (tr && make_2d(&e->tm_wt[l], e->whhT + (size_t)l * H * 3 * H, 3 * H, H, 3 * H, 32)) return fail(B2T_ERR_CUDA, "W_hh^T map failed");
+  }
+  {  // head: logits = top @ W_out^T + b_out                                       rnn_model.py:129
+    GemmSpec s;
+    s.a_mn = 0; s.b_mn = 0; s.epi = EPI_STORE; s.out_bf16 = 0;
+    s.M = M; s.N = e->C; s.K = H;
+    s.A = e->lay[L - 1].hseq + (size_t)Bp * H; s.lda = H;
+    s.B = e->shadow + seg_off(e, "out.weight"); s.ldb = H;
+    s.C = e->logits; s.ldc = LDL;
+    s.bias = e->params + seg_off(e, "out.bias");
+    if ((rc = gemm_plan_build(&e->p_head, s))) return fail(B2T_ERR_CUDA, "head plan failed (%d)", rc);
+  }
+  if (!tr) return 0;
+  if (make_2d(&e->tm_g, e->dGh, 3 * H, (uint64_t)Tp * Bp, 3 * H, 16)) return fail(B2T_ERR_CUDA, "dGh map failed");
+  {  // dW_out[C][H] = dlogits^T top
+    GemmSpec s;
+    s.a_mn = 1; s.b_mn = 1; s.epi = EPI_STORE;
+    s.M = e->C; s.N = H; s.K = M;
+    s.A = e->dlog16; s.lda = LDL; s.B = e->lay[L - 1].hseq + (size_t)Bp * H; s.ldb = H;
+    s.C = e->grads + seg_off(e, "out.weight"); s.ldc = H;
+    if ((rc = gemm_plan_build(&e->p_dwout, s))) return fail(B2T_ERR_CUDA, "dW_out plan failed (%d)", rc);
+  }
+  {  // dY_top[M][H] = dlogits W_out
+    GemmSpec s;
+    s.a_mn = 0; s.b_mn = 1; s.epi = EPI_STORE;
+    s.M = M; s.N = H; s.K = e->C;
+    s.A = e->dlog16; s.lda = LDL; s.B = e->shadow + seg_off(e, "out.weight"); s.ldb = H;
+    s.C = e->dY[0]; s.ldc = H;
+    if ((rc = gemm_plan_build(&e->p_dytop, s))) return fail(B2T_ERR_CUDA, "dY_top plan failed (%d)", rc);
+  }
+  for (int l = 0; l < L; ++l) {
+    const std::string sl = std::to_string(l);
+    {  // dW_ih = dGx^T X
+      GemmSpec s;
+      s.a_mn = 1; s.b_mn = 1; s.epi = EPI_STORE;
+      s.M = 3 * H; s.K = M;
+      s.A = e->dGx; s.lda = 3 * H;
+      s.C = e->grads + seg_off(e, "gru.weight_ih_l" + sl);
+      if (l == 0) {
+        s.N = K0; s.ldc = K0;
+        if (!e->use_unfold_copy) {
+          s.k_rin = Bp; s.k_rout = Tp;
+          s.a_rin_stride = 3 * H; s.a_rout_stride = (long long)Bp * 3 * H;
+          s.B = e->xd; s.b_rin_stride = (long long)T * D; s.b_rout_stride = (long long)e->stride * D;
+        } else {
+          s.B = e->xu; s.ldb = K0;
+        }
+      } else {
+        s.N = H; s.ldc = H; s.ldb = H;
+        s.B = e->lay[l - 1].hdrop ? e->lay[l - 1].hdrop : e->lay[l - 1].hseq + (size_t)Bp * H;
+      }
+      if ((rc = gemm_plan_build(&e->p_dwih[l], s))) return fail(B2T_ERR_CUDA, "dW_ih plan %d failed (%d)", l, rc);
+    }
+    {  // dW_hh = dGh^T H_prev   (H_prev = hseq slots 0..T-1)
+      GemmSpec s;
+      s.a_mn = 1; s.b_mn = 1; s.epi = EPI_STORE;
+      s.M = 3 * H; s.N = H; s.K = M;
+      s.A = e->dGh; s.lda = 3 * H; s.B = e->lay[l].hseq; s.ldb = H;
+      s.C = e->grads + seg_off(e, "gru.weight_hh_l" + sl); s.ldc = H;
+      if ((rc = gemm_plan_build(&e->p_dwhh[l], s))) return fail(B2T_ERR_CUDA, "dW_hh plan %d failed (%d)", l, rc);
+    }
+    {  // dX = dGx W_ih
+      GemmSpec s;
+      s.a_mn = 0; s.b_mn = 1; s.epi = EPI_STORE;
+      s.M = M; s.K = 3 * H;
+      s.A = e->dGx; s.lda = 3 * H;
+      s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
+      if (l == 0) { s.N = K0; s.ldb = K0; s.out_bf16 = 1; s.C = e->dxu; s.ldc = K0; }
+      else { s.N = H; s.ldb = H; s.out_bf16 = 0; s.C = e->dY[(L - l) & 1]; s.ldc = H; }
+      if ((rc = gemm_plan_build(&e->p_dx[l], s))) return fail(B2T_ERR_CUDA, "dX plan %d failed (%d)", l, rc);
+    }
+  }
+  {  // dW_day[day_b] += xs[b]^T dpre[b]
+    GemmSpec s;
+    s.a_mn = 1; s.b_mn = 1; s.epi = EPI_ATOMIC;
+    s.M = D; s.N = D; s.K = e->T_out;
+    s.A = e->xs; s.lda = D; s.a_zstride = (long long)T * D; s.nz = e->B;
+    s.B = e->dpre; s.ldb = D; s.b_zstride = (long long)T * D; s.nzb = e->B;
+    s.z_map = e->day_idx; s.zmap_b = 0;
+    s.C = e->grads + seg_off(e, "day_weights.0"); s.ldc = D; s.c_zstride = (long long)D * D;
+    if ((rc = gemm_plan_build(&e->p_daydw, s))) return fail(B2T_ERR_CUDA, "dW_day plan failed (%d)", rc);
+  }
+  return 0;
+}
+
+static int gauss_taps(float std, int size, float* taps16, int* ntaps) {
+  // data_augmentations.py:19-24 -- impulse response of scipy gaussian_filter1d(sigma=std), > 0.01, renormalised
+  const int radius = (int)(4.0 * std + 0.5);
+  std::vector<double> w(2 * radius + 1);
+  double sum = 0;
+  for (int i = -radius; i <= radius; ++i) { w[i + radius] = exp(-0.5 / ((double)std * std) * i * i); sum += w[i + radius]; }
+  std::vector<float> imp(size, 0.f);
+  const int c = size / 2;
+  for (int i = 0; i < 2 * radius + 1; ++i) {
+    const int j = c - radius + i;
+    if (j >= 0 && j < size) imp[j] += (float)(w[i] / sum);
+  }
+  std::vector<float> k;
+  for (float v : imp) if (v > 0.01f) k.push_back(v);
+  if (k.empty() || k.size() > 16) return -1;
+  float s = 0;
+  for (float v : k) s += v;
+  for (int i = 0; i < 16; ++i) taps16[i] = 0.f;
+  for (size_t i = 0; i < k.size(); ++i) taps16[16 - k.size() + i] = k[i] / s;
+  *ntaps = (int)k.size();
+  return 0;
+}
+
+extern "C" int b2t_output_frames(const b2t_config* cfg, int T, int smooth_mode, int ntaps, int cut) {
+  int To = T - cut;
+  if (smooth_mode == 2) To -= ntaps - 1;
+  if (cfg->patch_size > 0) return To < cfg->patch_size ? 0 : (To - cfg->patch_size) / cfg->patch_stride + 1;
+  return To;
+}
+
+template <typename P>
+static cudaError_t launch_rec(void (*kern)(const CUtensorMap, const CUtensorMap, const P), const CUtensorMap& a, const CUtensorMap& b, const P& p,
+                              int grid, size_t smem, cudaStream_t st) {
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  void* args[3] = {(void*)&a, (void*)&b, (void*)&p};
+  // cooperative launch: guarantees that every CTA of the grid is co-resident (they spin on each other's flags)
+  err = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, st);
+  ++g_launches;
+  return err;
+}
+
+static size_t rec_fwd_smem(int H) {
+  const int KC = H / 64;
+  return 1024 + (size_t)KC * 12288 + (size_t)(KC * 2048 > 4096 ? KC * 2048 : 4096) + 3 * 32 * REC_XPAD * 4 + 18 * 8 + 16;
+}
+static size_t rec_bwd_smem(int H) {
+  const int KC = 3 * H / 64;
+  return 1024 + (size_t)KC * 4096 + (size_t)(KC * 2048 > 12288 ? KC * 2048 : 12288) + 32 * REC_XPAD * 4 + 50 * 8 + 16;
+}
+
+// ------------------------------------------------------------------------------------ forward
+extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* stream) {
+  if (!e || !a || !a->x || !a->day_idx) return fail(B2T_ERR_ARG, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = e->D, H = e->H, L = e->L;
+  if (a->B < 1 || a->B > e->maxB || a->T < 1 || a->T > e->maxT) return fail(B2T_ERR_ARG, "B=%d T=%d exceed engine limits (%d, %d)", a->B, a->T, e->maxB, e->maxT);
+  if (a->training && !e->training) return fail(B2T_ERR_STATE, "engine was created for inference only");
+  PreParams pp;
+  memset(&pp, 0, sizeof(pp));
+  int ntaps = 0;
+  for (int i = 0; i < 16; ++i) pp.taps[i] = 0.f;
+  pp.taps[15] = 1.f;
+  if (a->smooth_mode != 0) {
+    if (gauss_taps(a->smooth_std, a->smooth_size, pp.taps, &ntaps)) return fail(B2T_ERR_UNSUPPORTED, "smoothing kernel has more than 16 taps");
+  }
+  const int cut = a->training ? a->cut : 0;
+  const int T_out = a->T - cut - (a->smooth_mode == 2 ? ntaps - 1 : 0);
+  const int Tp = b2t_output_frames(&e->cfg, a->T, a->smooth_mode, ntaps, cut);
+  if (Tp < 1) return fail(B2T_ERR_ARG, "input too short: T=%d gives no output frame", a->T);
+  const int Bp = r16(a->B);
+  if ((H / 32) * (Bp / 16) > num_sms()) return fail(B2T_ERR_UNSUPPORTED, "batch %d needs %d co-resident CTAs (> %d SMs); split the batch", a->B, (H / 32) * (Bp / 16), num_sms());
+  if (!e->plans_ok || e->B != a->B || e->T_in != a->T || e->Tp != Tp || e->T_out != T_out || e->day_idx != a->day_idx) {
+    e->B = a->B; e->Bpad = Bp; e->T_in = a->T; e->T_out = T_out; e->Tp = Tp; e->M = Tp * Bp; e->day_idx = a->day_idx;
+    e->plans_ok = false;
+    CK(cudaMemsetAsync(e->xd, 0, (size_t)Bp * a->T * D * sizeof(__nv_bfloat16), st));   // pad trials must stay finite
+    if (build_plans(e)) return B2T_ERR_CUDA;
+    e->plans_ok = true;
+  }
+  e->have_fwd = false; e->have_dlogits = false;
+  e->fwd_training = a->training != 0;
+  e->seed = a->seed;
+  e->states_given = a->states != nullptr;
+  const float keep_in = (a->training && e->cfg.input_dropout > 0.f) ? 1.0f - e->cfg.input_dropout : 1.0f;
+  const float keep_rnn = (a->training && e->cfg.rnn_dropout > 0.f) ? 1.0f - e->cfg.rnn_dropout : 1.0f;
+
+  // 1. augmentation + smoothing -> xs (bf16)
+  pp.x = a->x; pp.out = e->xs; pp.B = a->B; pp.Bpad = Bp; pp.T_in = a->T; pp.T_alloc = a->T; pp.D = D;
+  pp.cut = cut; pp.ntaps = ntaps; pp.valid = a->smooth_mode == 2;
+  pp.white_std = a->training ? a->white_noise_std : 0.f;
+  pp.offset_std = a->training ? a->offset_noise_std : 0.f;
+  pp.white = a->white_noise; pp.offset = a->offset_noise; pp.use_philox = 1;
+  pp.seed = a->seed; pp.rng_offset = 0;
+  {
+    dim3 grid((a->T + PRE_TT - 1) / PRE_TT, Bp);
+    pre_smooth_kernel<<<grid, D / 4, 0, st>>>(pp);
+    CK(LAUNCHED());
+  }
+  // 2. day layer
+  e->p_day.p.keep = keep_in; e->p_day.p.seed = a->seed; e->p_day.p.rng_offset = 0;
+  CK(gemm_run(e->p_day, st)); ++g_launches;
+  // 3. GRU stack
+  const int n_groups = Bp / 16, grid = (H / 32) * n_groups;
+  for (int l = 0; l < L; ++l) {
+    if (l == 0 && e->use_unfold_copy) {
+      unfold_kernel<<<num_sms() * 4, 256, 0, st>>>(e->xd, e->xu, Bp, a->T, D, Tp, e->patch, e->stride);
+      CK(LAUNCHED());
+    }
+    CK(gemm_run(e->p_in[l], st)); ++g_launches;
+    float* hin = e->h_init + (size_t)l * Bp * H;
+    init_state_kernel<<<(Bp * H + 255) / 256, 256, 0, st>>>(e->params + seg_off(e, "h0"), a->states ? a->states + (size_t)l * a->B * H : nullptr,
+                                                             a->B, Bp, H, e->lay[l].hseq, hin);
+    CK(LAUNCHED());
+    CK(cudaMemsetAsync(e->done, 0, (size_t)n_groups * Tp * sizeof(int), st));
+    RecFwdParams rp;
+    rp.H = H; rp.T = Tp; rp.Bpad = Bp; rp.n_slices = H / 32;
+    rp.gx = e->gx; rp.bhh = e->params + seg_off(e, "gru.bias_hh_l" + std::to_string(l));
+    rp.hseq = e->lay[l].hseq; rp.h_init = hin; rp.h_final = e->h_final + (size_t)l * Bp * H;
+    const bool save = a->training != 0;
+    rp.hdrop = save ? e->lay[l].hdrop : nullptr;
+    rp.R = save ? e->lay[l].R : nullptr; rp.Z = save ? e->lay[l].Z : nullptr;
+    rp.Nn = save ? e->lay[l].Nn : nullptr; rp.HN = save ? e->lay[l].HN : nullptr;
+    rp.done = e->done; rp.keep = keep_rnn; rp.seed = a->seed; rp.rng_offset = (unsigned long long)(l + 1) << 40;
+    // eval-mode forward through a training engine: the next layer reads hdrop if it exists, so keep it in sync
+    if (!save && e->lay[l].hdrop) { rp.hdrop = e->lay[l].hdrop; rp.keep = 1.0f; }
+    CK(launch_rec(gru_rec_fwd_kernel, e->tm_w[l], e->tm_h[l], rp, grid, rec_fwd_smem(H), st));
+  }
+  // 4. head
+  CK(gemm_run(e->p_head, st)); ++g_launches;
+  if (a->logits_out) {
+    gather_logits_kernel<<<num_sms() * 2, 256, 0, st>>>(e->logits, Tp, a->B, Bp, LDL, e->C, a->logits_out);
+    CK(LAUNCHED());
+  }
+  if (a->hidden_out) {
+    for (int l = 0; l < L; ++l)
+      CK(cudaMemcpyAsync(a->hidden_out + (size_t)l * a->B * H, e->h_final + (size_t)l * Bp * H, (size_t)a->B * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  e->have_fwd = true;
+  return Tp;
+}
+
+// ------------------------------------------------------------------------------------ CTC
+static int run_ctc(const CtcParams& cp, int B, cudaStream_t st) {
+  const size_t smem = ctc_smem_bytes(cp.T, cp.C, cp.Smax);
+  if (smem > 200 * 1024) return fail(B2T_ERR_UNSUPPORTED, "CTC problem too large for shared memory (T=%d, S=%d)", cp.T, cp.Smax);
+  if (cp.C > CTC_THREADS || cp.ldl > CTC_THREADS) return fail(B2T_ERR_UNSUPPORTED, "too many classes");
+  CK(cudaFuncSetAttribute(ctc_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_loss_grad_kernel<<<B, CTC_THREADS, smem, st>>>(cp);
+  CK(LAUNCHED());
+  return 0;
+}
+
+extern "C" int b2t_ctc_loss(b2t_engine* e, const int* labels, int Smax, const int* in_len, const int* tgt_len, float grad_scale,
+                            float* loss_out, int want_grad, void* stream) {
+  if (!e || !labels || !in_len || !tgt_len || !loss_out) return fail(B2T_ERR_ARG, "null argument");
+  if (!e->have_fwd) return fail(B2T_ERR_STATE, "b2t_ctc_loss needs a preceding b2t_forward");
+  if (Smax < 1 || Smax > e->maxS) return fail(B2T_ERR_ARG, "Smax=%d exceeds engine limit %d", Smax, e->maxS);
+  cudaStream_t st = (cudaStream_t)stream;
+  CtcParams cp;
+  cp.logits = e->logits; cp.ldl = LDL; cp.Bpad = e->Bpad; cp.T = e->Tp; cp.C = e->C; cp.blank = 0;
+  cp.labels = labels; cp.Smax = Smax; cp.in_len = in_len; cp.tgt_len = tgt_len;
+  cp.alpha = e->alpha; cp.loss = loss_out;
+  cp.dlogits = want_grad ? e->dlog32 : nullptr;
+  cp.dlogits_bf16 = want_grad ? e->dlog16 : nullptr;
+  cp.dbias = nullptr;
+  cp.grad_scale = grad_scale;
+  if (want_grad) {
+    if (!e->training) return fail(B2T_ERR_STATE, "inference engine cannot keep gradients");
+    // pad trials (b >= B) are never visited by the kernel: clear them once
+    CK(cudaMemsetAsync(e->dlog16, 0, (size_t)e->M * LDL * sizeof(__nv_bfloat16), st));
+    CK(cudaMemsetAsync(e->dlog32, 0, (size_t)e->M * LDL * sizeof(float), st));
+  }
+  int rc = run_ctc(cp, e->B, st);
+  if (rc) return rc;
+  if (want_grad) e->have_dlogits = true;
+  return 0;
+}
+
+extern "C" long long b2t_ctc_workspace_bytes(int T, int B, int Smax) { return (long long)T * B * (2 * Smax + 1) * 4 + 1024; }
+
+extern "C" int b2t_ctc_loss_tbc(const float* logits_tbc, int T, int B, int C, const int* labels, int Smax, const int* in_len, const int* tgt_len,
+                                float grad_scale, float* loss_out, float* dlogits_tbc, void* workspace, long long workspace_bytes, void* stream) {
+  if (!logits_tbc || !labels || !in_len || !tgt_len || !loss_out || !workspace) return fail(B2T_ERR_ARG, "null argument");
+  if (workspace_bytes < b2t_ctc_workspace_bytes(T, B, Smax)) return fail(B2T_ERR_WORKSPACE, "CTC workspace too small");
+  CtcParams cp;
+  cp.logits = logits_tbc; cp.ldl = C; cp.Bpad = B; cp.T = T; cp.C = C; cp.blank = 0;
+  cp.labels = labels; cp.Smax = Smax; cp.in_len = in_len; cp.tgt_len = tgt_len;
+  cp.alpha = reinterpret_cast<float*>(workspace); cp.loss = loss_out; cp.dlogits = dlogits_tbc; cp.dlogits_bf16 = nullptr; cp.dbias = nullptr;
+  cp.grad_scale = grad_scale;
+  return run_ctc(cp, B, (cudaStream_t)stream);
+}
+
+extern "C" int b2t_set_dlogits(b2t_engine* e, const float* dlogits, void* stream) {
+  if (!e || !dlogits) return fail(B2T_ERR_ARG, "null argument");
+  if (!e->have_fwd || !e->training) return fail(B2T_ERR_STATE, "no training forward to attach gradients to");
+  cudaStream_t st = (cudaStream_t)stream;
+  scatter_dlogits_kernel<<<num_sms() * 2, 256, 0, st>>>(dlogits, e->Tp, e->B, e->Bpad, LDL, e->C, e->dlog32, e->dlog16);
+  CK(LAUNCHED());
+  e->have_dlogits = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ backward
+extern "C" int b2t_backward(b2t_engine* e, void* stream) {
+  if (!e) return fail(B2T_ERR_ARG, "null engine");
+  if (!e->training || !e->have_fwd || !e->fwd_training) return fail(B2T_ERR_STATE, "b2t_backward needs a training-mode b2t_forward");
+  if (!e->have_dlogits) return fail(B2T_ERR_STATE, "no dlogits: call b2t_ctc_loss(want_grad) or b2t_set_dlogits first");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp;
+  const float keep_in = e->cfg.input_dropout > 0.f ? 1.0f - e->cfg.input_dropout : 1.0f;
+  const float keep_rnn = e->cfg.rnn_dropout > 0.f ? 1.0f - e->cfg.rnn_dropout : 1.0f;
+  // zero what is accumulated with atomics: biases, h0, day params of the touched days, touched flags
+  CK(cudaMemsetAsync(e->touched, 0, r64(e->cfg.n_days) * sizeof(float), st));
+  mark_days_kernel<<<(e->B + 127) / 128, 128, 0, st>>>(e->day_idx, e->B, e->touched);
+  CK(LAUNCHED());
+  // (GEMM-stored gradients are fully overwritten; day-weight / bias / h0 regions are cleared here.  Untouched
+  //  day segments are cleared too -- cheap, and keeps the gradient-norm reduction free of stale values.)
+  CK(cudaMemsetAsync(e->grads + seg_off(e, "day_weights.0"), 0, (size_t)(seg_off(e, "gru.weight_ih_l0") - seg_off(e, "day_weights.0")) * sizeof(float), st));
+  for (int l = 0; l < L; ++l)
+    CK(cudaMemsetAsync(e->grads + seg_off(e, "gru.bias_ih_l" + std::to_string(l)), 0, (size_t)2 * r64(3 * H) * sizeof(float), st));
+  CK(cudaMemsetAsync(e->grads + seg_off(e, "out.bias"), 0, (size_t)(r64(e->C) + r64(H)) * sizeof(float), st));
+
+  // head
+  colsum_kernel<<<64, 64, 0, st>>>(e->dlog32, (size_t)e->M, LDL, e->C, e->grads + seg_off(e, "out.bias"));
+  CK(LAUNCHED());
+  CK(gemm_run(e->p_dwout, st)); ++g_launches;
+  CK(gemm_run(e->p_dytop, st)); ++g_launches;
+  const int n_groups = Bp / 16, grid = (H / 32) * n_groups;
+  for (int l = L - 1; l >= 0; --l) {
+    const std::string sl = std::to_string(l);
+    CK(cudaMemsetAsync(e->done, 0, (size_t)n_groups * Tp * sizeof(int), st));
+    RecBwdParams bp;
+    bp.H = H; bp.T = Tp; bp.Bpad = Bp; bp.n_slices = H / 32;
+    bp.dY = e->dY[(L - 1 - l) & 1];
+    bp.hseq = e->lay[l].hseq; bp.R = e->lay[l].R; bp.Z = e->lay[l].Z; bp.Nn = e->lay[l].Nn; bp.HN = e->lay[l].HN;
+    bp.dGx = e->dGx; bp.dGh = e->dGh;
+    bp.dbih = e->grads + seg_off(e, "gru.bias_ih_l" + sl); bp.dbhh = e->grads + seg_off(e, "gru.bias_hh_l" + sl);
+    bp.dh0 = e->dh0 + (size_t)l * Bp * H;
+    bp.done = e->done; bp.n_valid = e->B;
+    bp.keep = (l < L - 1) ? keep_rnn : 1.0f;
+    bp.seed = e->seed; bp.rng_offset = (unsigned long long)(l + 1) << 40;
+    CK(launch_rec(gru_rec_bwd_kernel, e->tm_wt[l], e->tm_g, bp, grid, rec_bwd_smem(H), st));
+    CK(gemm_run(e->p_dwih[l], st)); ++g_launches;
+    CK(gemm_run(e->p_dwhh[l], st)); ++g_launches;
+    CK(gemm_run(e->p_dx[l], st)); ++g_launches;
+    if (!e->states_given) {
+      reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, st>>>(e->dh0 + (size_t)l * Bp * H, e->B, H, e->grads + seg_off(e, "h0"));
+      CK(LAUNCHED());
+    }
+  }
+  // patch fold + day layer
+  FoldParams fp;
+  fp.dxu = e->dxu; fp.xd = e->xd; fp.dpre = e->dpre; fp.dbias_day = e->grads + seg_off(e, "day_biases.0");
+  fp.day_idx = e->day_idx; fp.B = e->B; fp.Bpad = Bp; fp.T_alloc = e->T_in; fp.T_valid = e->T_out; fp.D = D; fp.Tp = Tp;
+  fp.patch = e->patch; fp.stride = e->stride; fp.keep = keep_in; fp.seed = e->seed; fp.rng_offset = 0;
+  {
+    dim3 g((e->T_in + FOLD_TT - 1) / FOLD_TT, Bp);
+    fold_dpre_kernel<<<g, D / 4, 0, st>>>(fp);
+    CK(LAUNCHED());
+  }
+  CK(gemm_run(e->p_daydw, st)); ++g_launches;
+  e->have_dlogits = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ optimizer
+extern "C" int b2t_optimizer_step(b2t_engine* e, const b2t_adamw_args* a, float* stats_out, void* stream) {
+  if (!e || !a) return fail(B2T_ERR_ARG, "null argument");
+  if (!e->training) return fail(B2T_ERR_STATE, "inference engine has no optimizer state");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(e->sumsq, 0, sizeof(float), st));
+  sumsq_kernel<<<num_sms() * 4, 256, 0, st>>>(e->grads, (size_t)e->n_params, e->sumsq);
+  CK(LAUNCHED());
+  AdamParams ap;
+  ap.p = e->params; ap.g = e->grads; ap.m = e->m1; ap.v = e->m2; ap.shadow = e->shadow;
+  ap.segs = e->d_segs; ap.chunks = e->d_chunks; ap.step = e->steps; ap.day_touched = e->touched;
+  ap.sumsq = e->sumsq; ap.stats = e->stats; ap.max_norm = a->max_grad_norm;
+  for (int i = 0; i < 3; ++i) { ap.lr[i] = a->lr[i]; ap.wd[i] = a->weight_decay[i]; }
+  ap.beta1 = a->beta1; ap.beta2 = a->beta2; ap.eps = a->eps;
+  clip_adamw_kernel<<<e->n_chunks, 256, 0, st>>>(ap);
+  CK(LAUNCHED());
+  bump_steps_kernel<<<((int)e->segs.size() + 127) / 128, 128, 0, st>>>(e->d_segs, (int)e->segs.size(), e->touched, e->steps);
+  CK(LAUNCHED());
+  for (int l = 0; l < e->L; ++l) {
+    const long long off = seg_off(e, "gru.weight_hh_l" + std::to_string(l));
+    dim3 grid((e->H + 31) / 32, (3 * e->H + 31) / 32), blk(32, 8);
+    transpose_bf16_kernel<<<grid, blk, 0, st>>>(e->shadow + off, e->whhT + (size_t)l * e->H * 3 * e->H, 3 * e->H, e->H);
+    CK(LAUNCHED());
+  }
+  if (stats_out) CK(cudaMemcpyAsync(stats_out, e->stats, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ greedy decode
+extern "C" int b2t_greedy_edit(b2t_engine* e, const int* labels, int Smax, const int* in_len, const int* tgt_len, int* decoded, int* dec_len,
+                               int* edit, void* stream) {
+  if (!e || !labels || !in_len || !tgt_len || !decoded || !dec_len || !edit) return fail(B2T_ERR_ARG, "null argument");
+  if (!e->have_fwd) return fail(B2T_ERR_STATE, "needs a preceding b2t_forward");
+  if (Smax < 1 || Smax > e->maxS) return fail(B2T_ERR_ARG, "Smax out of range");
+  GreedyParams gp;
+  gp.logits = e->logits; gp.T = e->Tp; gp.Bpad = e->Bpad; gp.ldl = LDL; gp.C = e->C;
+  gp.in_len = in_len; gp.labels = labels; gp.tgt_len = tgt_len; gp.Smax = Smax;
+  gp.decoded = decoded; gp.dec_len = dec_len; gp.edit = edit; gp.scratch = e->greedy_scratch;
+  greedy_edit_kernel<<<e->B, 128, e->Tp * sizeof(int), (cudaStream_t)stream>>>(gp);
+  CK(LAUNCHED());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ GEMM test hook
+extern "C" int b2t_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int a_mn, int b_mn, int out_bf16, const float* bias,
+                             void* stream) {
+  GemmSpec s;
+  s.a_mn = a_mn; s.b_mn = b_mn; s.epi = EPI_STORE; s.out_bf16 = out_bf16;
+  s.M = M; s.N = N; s.K = K;
+  s.A = A; s.lda = a_mn ? M : K;
+  s.B = B; s.ldb = b_mn ? N : K;
+  s.C = C; s.ldc = N; s.bias = bias;
+  GemmPlan pl;
+  int rc = gemm_plan_build(&pl, s);
+  if (rc) return fail(B2T_ERR_CUDA, "gemm plan failed (%d)", rc);
+  CK(gemm_run(pl, (cudaStream_t)stream));
+  ++g_launches;
+  return 0;
+}

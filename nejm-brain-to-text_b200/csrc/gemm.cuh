@@ -1,0 +1,264 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  C[m,n] = sum_k A[m,k] * B[n,k]  (fp32 accumulate)
+//
+//   warp 0      : TMA producer (one elected lane)   global -> 6-stage smem ring (SWIZZLE_128B)
+//   warp 1      : tcgen05.mma issuer (one lane); also owns the TMEM allocation (2 x 128 fp32 columns)
+//   warps 2..5  : epilogue; warp w reads TMEM lanes 32*(w%4).. with tcgen05.ld and writes C
+//
+// Operands are described by 4-D tensor maps so that the same kernel serves
+//   * plain row-major matrices (K-major operand: rows x K, K contiguous),
+//   * the overlapping sliding-window "patch" view of the day-layer output (rows (t',b) of the
+//     unfolded [B*T', 14*512] matrix are addressed with strides, never materialised; reference
+//     rnn_model.py:106-119),
+//   * transposed use of a row-major matrix (MN-major operand: the contraction index is the row index
+//     of the stored array) for the weight-gradient and data-gradient GEMMs,
+//   * batched problems with a per-problem index map (the 45 day-specific 512x512 layers,
+//     rnn_model.py:95-98).
+//
+// Tile 128 x 128 x 64; one tcgen05.mma is 128 x 128 x 16.
+#pragma once
+#include "sm100.cuh"
+#include "gemm_params.h"
+
+namespace b2t {
+
+
+constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64, GEMM_STAGES = 6;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2, GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;
+constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_THREADS = 192;
+
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store_row32(OutT* dst, const float (&f)[32], int ncols, bool vec_ok);
+
+template <>
+__device__ __forceinline__ void store_row32<float>(float* dst, const float (&f)[32], int ncols, bool vec_ok) {
+  if (ncols >= 32 && vec_ok) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols) dst[i] = f[i];
+  }
+}
+template <>
+__device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, const float (&f)[32], int ncols, bool vec_ok) {
+  if (ncols >= 32 && vec_ok) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * i], f[8 * i + 1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(f[8 * i + 2], f[8 * i + 3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * i + 4], f[8 * i + 5]);
+      __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * i + 6], f[8 * i + 7]);
+      u.x = *reinterpret_cast<uint32_t*>(&p0);
+      u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2);
+      u.w = *reinterpret_cast<uint32_t*>(&p3);
+      reinterpret_cast<uint4*>(dst)[i] = u;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols) dst[i] = __float2bfloat16_rn(f[i]);
+  }
+}
+
+template <bool A_MN, bool B_MN, int EPI, typename OutT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  uint64_t* tfull_bar = empty_bar + GEMM_STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.nz;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<2 * GEMM_BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tn = tile % p.tiles_n;
+        const int tm = (tile / p.tiles_n) % p.tiles_m;
+        const int z = tile / (p.tiles_n * p.tiles_m);
+        const int zb = (p.z_map && p.zmap_b) ? p.z_map[z] : z;
+        for (int kc = 0; kc < p.k_iters; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * GEMM_STAGE_BYTES;
+          uint8_t* sb = sa + GEMM_A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], GEMM_STAGE_BYTES);
+          const int kb = kc % p.k_rin_blocks, ko = kc / p.k_rin_blocks;
+          if (A_MN) {
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], tm * GEMM_BM, kb * p.k_bin, ko * (64 / p.k_bin), z);
+            tma_load_4d(sa + 8192, &tmap_a, &full_bar[stage], tm * GEMM_BM + 64, kb * p.k_bin, ko * (64 / p.k_bin), z);
+          } else {
+            const int rb = tm % p.a_rin_blocks, ro = tm / p.a_rin_blocks;
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * GEMM_BK, rb * p.a_bin, ro * (GEMM_BM / p.a_bin), z);
+          }
+          if (B_MN) {
+            tma_load_4d(sb, &tmap_b, &full_bar[stage], tn * GEMM_BN, kb * p.k_bin, ko * (64 / p.k_bin), zb);
+            tma_load_4d(sb + 8192, &tmap_b, &full_bar[stage], tn * GEMM_BN + 64, kb * p.k_bin, ko * (64 / p.k_bin), zb);
+          } else {
+            tma_load_4d(sb, &tmap_b, &full_bar[stage], kc * GEMM_BK, 0, tn * GEMM_BN, zb);
+          }
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, GEMM_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * GEMM_BN;
+        for (int kc = 0; kc < p.k_iters; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * GEMM_STAGE_BYTES);
+          const uint32_t sb = sa + GEMM_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = A_MN ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);        // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;             // row inside the 128-row tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tn = tile % p.tiles_n;
+      const int tm = (tile / p.tiles_n) % p.tiles_m;
+      const int z = tile / (p.tiles_n * p.tiles_m);
+      const int zb = p.z_map ? p.z_map[z] : z;
+      long long m;
+      bool row_ok;
+      if (A_MN) {
+        m = (long long)tm * GEMM_BM + r;
+        row_ok = m < p.M;
+      } else {
+        const int rb = tm % p.a_rin_blocks, ro = tm / p.a_rin_blocks;
+        const int rin = rb * p.a_bin + (r % p.a_bin);
+        const int rout = ro * (GEMM_BM / p.a_bin) + (r / p.a_bin);
+        m = (long long)rout * p.a_rin + rin;
+        row_ok = rout < p.a_rout;
+      }
+      const int zc = (EPI == EPI_ATOMIC) ? zb : z;
+      OutT* crow = reinterpret_cast<OutT*>(p.C) + (long long)zc * p.c_zstride + m * p.ldc;
+      const float* bias = p.bias ? p.bias + (long long)zb * p.bias_zstride : nullptr;
+      const bool vec_ok = (p.ldc % (16 / (int)sizeof(OutT))) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(p.C) + (size_t)zc * p.c_zstride * sizeof(OutT)) & 15) == 0;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < GEMM_BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BN + c0, v);
+        tmem_ld_wait();
+        const int n0 = tn * GEMM_BN + c0;
+        const int ncols = p.N - n0;          // columns of this 32-chunk that exist
+        if (row_ok && ncols > 0) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols) f[i] += __ldg(bias + n0 + i);
+          }
+          if (EPI == EPI_DAY) {
+            // softsign (rnn_model.py:99) then inverted dropout (rnn_model.py:102-103)
+            const float inv_keep = 1.0f / p.keep;
+            const unsigned long long e0 = (unsigned long long)zc * p.c_zstride + (unsigned long long)m * p.ldc + n0;
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+              uint4 rnd = make_uint4(0, 0, 0, 0);
+              if (p.keep < 1.0f) {
+                const unsigned long long c = (e0 >> 2) + i4 + p.rng_offset;
+                rnd = philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x0da1u, 0), make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+              }
+              const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float y = f[4 * i4 + j];
+                y = y / (1.0f + fabsf(y));
+                if (p.keep < 1.0f) y = (u32_to_unit(rr[j]) < p.keep) ? y * inv_keep : 0.0f;
+                f[4 * i4 + j] = y;
+              }
+            }
+          }
+          if (EPI == EPI_ATOMIC) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols) atomicAdd(reinterpret_cast<float*>(crow) + n0 + i, f[i]);
+          } else {
+            store_row32<OutT>(crow + n0, f, ncols, vec_ok);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * GEMM_BN>(tmem_base);
+  }
+}
+
+}  // namespace b2t

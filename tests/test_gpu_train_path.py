@@ -1,0 +1,140 @@
+"""GPU parity tests of the training path (GEMM, forward, CTC, backward, optimizer) through the C ABI.
+
+Checker = oracle/gru_ctc_oracle.py (numpy restatement pinned to the reference by tests/golden) and the
+golden vectors themselves.  Tolerances: integer outputs bit-exact; CTC (fp32) 1e-5 relative; anything
+that passes through bf16 tensor-core GEMMs is compared at bf16 tolerances stated per test.
+"""
+import numpy as np
+import pytest
+import torch
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E(pkg):
+    import b2t_pkg
+    return b2t_pkg.submodule("engine")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 41, 768), (97 * 16, 192, 448), (130, 136, 72)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_gemm_vs_torch(E, M, N, K, a_mn, b_mn):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A.float() @ B.float().t() + bias
+    Ain = A.t().contiguous() if a_mn else A
+    Bin = B.t().contiguous() if b_mn else B
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operands need a 16-byte aligned leading dimension")
+    out = E.gemm_bf16(Ain, Bin, a_mn=a_mn, b_mn=b_mn, bias=bias)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    assert err < 1e-2 * max(1.0, ref.abs().max().item() / 50), err      # fp32 accumulation of exact bf16 products
+    out16 = E.gemm_bf16(Ain, Bin, a_mn=a_mn, b_mn=b_mn, out_bf16=True, bias=bias) if not (a_mn and b_mn) else None
+    if out16 is not None:
+        assert (out16.float() - ref).abs().max().item() < 0.02 * ref.abs().max().item() + 1e-2
+
+
+def _engine_from_golden(E, name, training=True):
+    params, grads, p1, rest = util.load_golden(name)
+    D, H, L, n_days, B, T = [int(v) for v in rest["cfg"]]
+    cfg = E.make_config(D, H, L, n_days, 41, 14, 4, 0.0, 0.0)
+    flat = util.flat_from_params(E, cfg, params, "cuda")
+    eng = E.Engine(cfg, flat, max_batch=B, max_T=T, max_label_len=16, training=training)
+    return eng, cfg, params, grads, p1, rest
+
+
+@pytest.mark.parametrize("name", ["train_small.npz", "train_ragged.npz"])
+def test_forward_logits_vs_golden(E, name):
+    eng, cfg, params, grads, p1, rest = _engine_from_golden(E, name)
+    x = torch.from_numpy(rest["x"]).cuda()
+    logits, hidden = eng.forward(x, torch.from_numpy(rest["days"]), training=False, smooth_mode=1, want_hidden=True)
+    torch.cuda.synchronize()
+    ref = rest["logits"]
+    assert logits.shape == ref.shape
+    err = np.abs(logits.cpu().numpy() - ref).max()
+    assert err < 5e-2, err                               # bf16 operands, fp32 accumulate (SURVEY tolerance table)
+    assert np.abs(hidden.cpu().numpy() - rest["hidden"]).max() < 3e-2
+
+
+@pytest.mark.parametrize("name", ["train_small.npz", "train_ragged.npz"])
+def test_ctc_vs_golden(E, pkg, name):
+    import ctypes as C
+    params, grads, p1, rest = util.load_golden(name)
+    N = pkg._native
+    logits = torch.from_numpy(rest["logits"]).cuda()                     # [B,T,C]
+    B, T, Cc = logits.shape
+    tbc = logits.permute(1, 0, 2).contiguous()
+    labels = torch.from_numpy(rest["labels"]).to(torch.int32).cuda()
+    import gru_ctc_oracle as O
+    in_len = torch.from_numpy(O.adjusted_lens(rest["n_steps"])).to(torch.int32).cuda()
+    tgt = torch.from_numpy(rest["lens"]).to(torch.int32).cuda()
+    ws = torch.empty(N.lib.b2t_ctc_workspace_bytes(T, B, labels.shape[1]), dtype=torch.uint8, device="cuda")
+    loss = torch.empty(B, device="cuda")
+    dl = torch.empty_like(tbc)
+    N.check(N.lib.b2t_ctc_loss_tbc(tbc.data_ptr(), T, B, Cc, labels.data_ptr(), labels.shape[1], in_len.data_ptr(), tgt.data_ptr(),
+                                   1.0 / B, loss.data_ptr(), dl.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   torch.cuda.current_stream().cuda_stream), "ctc")
+    torch.cuda.synchronize()
+    assert util.rel_err(loss.cpu().numpy(), rest["loss_vec"]) < 1e-5
+    got = dl.permute(1, 0, 2).cpu().numpy()
+    assert np.abs(got - rest["dlogits"]).max() < 1e-5 * max(1.0, np.abs(rest["dlogits"]).max() * 10)
+
+
+@pytest.mark.parametrize("name", ["train_small.npz", "train_ragged.npz"])
+def test_train_step_vs_golden(E, name):
+    """forward -> CTC -> backward -> clip+AdamW against the reference's own step (golden)."""
+    import gru_ctc_oracle as O
+    eng, cfg, params, grads, p1, rest = _engine_from_golden(E, name)
+    x = torch.from_numpy(rest["x"]).cuda()
+    B = x.shape[0]
+    logits, _ = eng.forward(x, torch.from_numpy(rest["days"]), training=True, smooth_mode=1)
+    in_len = torch.from_numpy(O.adjusted_lens(rest["n_steps"]))
+    loss = eng.ctc_loss(torch.from_numpy(rest["labels"]), in_len, torch.from_numpy(rest["lens"]), grad_scale=1.0 / B)
+    eng.backward()
+    torch.cuda.synchronize()
+    assert util.rel_err(loss.cpu().numpy(), rest["loss_vec"]) < 2e-2      # logits carry bf16 error
+    got = util.unflatten(E, cfg, eng.grads[:eng.n_params])
+    worst = 0.0
+    for k, g in grads.items():
+        r = util.rel_err(got[k].reshape(g.shape), g)
+        worst = max(worst, r)
+        assert r < 6e-2, (k, r)                                          # bf16 GEMM operands / bf16 activation stash
+    touched = eng.touched_days().cpu().numpy()
+    assert sorted(np.nonzero(touched)[0].tolist()) == sorted(set(int(d) for d in rest["days"]))
+    for k in got:                                                        # untouched day layers: zero grad, skipped by AdamW
+        if k not in grads:
+            assert np.abs(got[k]).max() == 0.0, k
+    lr = float(rest["lr"])
+    stats = eng.optimizer_step([lr] * 3, [0.0, 0.0, 1e-3], 0.9, 0.999, 0.1, 10.0)
+    torch.cuda.synchronize()
+    assert abs(stats[0].item() - float(rest["grad_norm"])) < 3e-2 * float(rest["grad_norm"])
+    newp = util.unflatten(E, cfg, eng.params)
+    for k, v in p1.items():
+        # after one step the update is lr * m_hat/(sqrt(v_hat)+eps); compare the *delta* at bf16-gradient tolerance
+        d_ref = v - params[k]
+        d_got = newp[k].reshape(v.shape) - params[k]
+        assert np.abs(d_got - d_ref).max() < 6e-2 * np.abs(d_ref).max() + 1e-7, k
+    for k in newp:
+        if k not in p1:
+            assert np.array_equal(newp[k].reshape(params[k].shape), params[k].astype(np.float32)), k
+
+
+def test_greedy_edit_bit_exact(E):
+    import gru_ctc_oracle as O
+    eng, cfg, params, grads, p1, rest = _engine_from_golden(E, "train_ragged.npz", training=False)
+    x = torch.from_numpy(rest["x"]).cuda()
+    logits, _ = eng.forward(x, torch.from_numpy(rest["days"]), training=False, smooth_mode=1)
+    in_len = torch.from_numpy(O.adjusted_lens(rest["n_steps"]))
+    dec, dlen, ed = eng.greedy_edit(torch.from_numpy(rest["labels"]), in_len, torch.from_numpy(rest["lens"]))
+    torch.cuda.synchronize()
+    lg = logits.cpu().numpy()
+    for b in range(lg.shape[0]):
+        want = O.greedy_decode(lg[b], int(in_len[b]))                    # same logits -> integer pipeline must be identical
+        assert dec[b, :dlen[b]].cpu().tolist() == want
+        assert int(ed[b]) == O.edit_distance(want, rest["labels"][b][:rest["lens"][b]])

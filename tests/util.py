@@ -1,0 +1,36 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    params = {k[2:]: z[k] for k in z.files if k.startswith("p.")}
+    grads = {k[2:]: z[k] for k in z.files if k.startswith("g.")}
+    p1 = {k[3:]: z[k] for k in z.files if k.startswith("p1.")}
+    rest = {k: z[k] for k in z.files if not (k.startswith("p.") or k.startswith("g.") or k.startswith("p1."))}
+    return params, grads, p1, rest
+
+
+def flat_from_params(E, cfg, params, device):
+    import torch
+    flat = torch.zeros(E.param_elems(cfg), dtype=torch.float32)
+    for name, off, rows, cols in E.param_layout(cfg):
+        flat[off:off + rows * cols] = torch.from_numpy(np.ascontiguousarray(params[name], dtype=np.float32).reshape(-1))
+    return flat.to(device)
+
+
+def unflatten(E, cfg, flat):
+    out = {}
+    f = flat.detach().float().cpu().numpy()
+    for name, off, rows, cols in E.param_layout(cfg):
+        out[name] = f[off:off + rows * cols].reshape(rows, cols)
+    return out
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-12))
