@@ -143,7 +143,8 @@ struct FoldParams {
   const __nv_bfloat16* dxu;   // [Tp][Bpad][patch*D]
   const __nv_bfloat16* xd;    // [Bpad][T_alloc][D] (post-dropout day-layer output)
   __nv_bfloat16* dpre;        // [Bpad][T_alloc][D]
-  float* dbias_day;           // [n_days][D] (atomicAdd)
+  float* dbias_day;           // [n_days][bias_pitch] (atomicAdd)
+  int bias_pitch;
   const int* day_idx;         // [B]
   int B, Bpad, T_alloc, T_valid, D, Tp, patch, stride;
   float keep;
@@ -195,7 +196,7 @@ __global__ void fold_dpre_kernel(const FoldParams p) {
     st_bf16x4(p.dpre + e, g[0], g[1], g[2], g[3]);
   }
   if (b < p.B && p.dbias_day) {
-    float* dst = p.dbias_day + (size_t)p.day_idx[b] * p.D + d;
+    float* dst = p.dbias_day + (size_t)p.day_idx[b] * p.bias_pitch + d;
 #pragma unroll
     for (int k = 0; k < 4; ++k) atomicAdd(dst + k, bsum[k]);
   }

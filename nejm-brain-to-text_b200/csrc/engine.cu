@@ -685,7 +685,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   }
   // patch fold + day layer
   FoldParams fp;
-  fp.dxu = e->dxu; fp.xd = e->xd; fp.dpre = e->dpre; fp.dbias_day = e->grads + seg_off(e, "day_biases.0");
+  fp.dxu = e->dxu; fp.xd = e->xd; fp.dpre = e->dpre; fp.dbias_day = e->grads + seg_off(e, "day_biases.0"); fp.bias_pitch = (int)r64(D);
   fp.day_idx = e->day_idx; fp.B = e->B; fp.Bpad = Bp; fp.T_alloc = e->T_in; fp.T_valid = e->T_out; fp.D = D; fp.Tp = Tp;
   fp.patch = e->patch; fp.stride = e->stride; fp.keep = keep_in; fp.seed = e->seed; fp.rng_offset = 0;
   {

@@ -100,11 +100,9 @@ def test_train_step_vs_golden(E, name):
     torch.cuda.synchronize()
     assert util.rel_err(loss.cpu().numpy(), rest["loss_vec"]) < 2e-2      # logits carry bf16 error
     got = util.unflatten(E, cfg, eng.grads[:eng.n_params])
-    worst = 0.0
-    for k, g in grads.items():
-        r = util.rel_err(got[k].reshape(g.shape), g)
-        worst = max(worst, r)
-        assert r < 6e-2, (k, r)                                          # bf16 GEMM operands / bf16 activation stash
+    errs = {k: util.rel_err(got[k].reshape(g.shape), g) for k, g in grads.items()}
+    bad = {k: round(r, 4) for k, r in errs.items() if r >= 6e-2}           # bf16 GEMM operands / bf16 activation stash
+    assert not bad, bad
     touched = eng.touched_days().cpu().numpy()
     assert sorted(np.nonzero(touched)[0].tolist()) == sorted(set(int(d) for d in rest["days"]))
     for k in got:                                                        # untouched day layers: zero grad, skipped by AdamW
