@@ -40,6 +40,20 @@ def grad_elems(cfg: N.Config) -> int:
     return N.check(N.lib.b2t_grad_elems(C.byref(cfg)), "b2t_grad_elems")
 
 
+def flat_from_state_dict(cfg: N.Config, sd) -> torch.Tensor:
+    """Pack a reference-style state_dict (tensors or arrays) into the flat fp32 layout (CPU tensor)."""
+    flat = torch.zeros(param_elems(cfg), dtype=torch.float32)
+    for name, off, rows, cols in param_layout(cfg):
+        key = name if name in sd else next((k for k in sd if k.endswith(name) and k[:-len(name)] in ("_orig_mod.", "module.")), None)
+        if key is None:
+            raise KeyError(f"state_dict has no entry for {name}")
+        v = torch.as_tensor(sd[key]).detach().to(torch.float32).reshape(-1)
+        if v.numel() != rows * cols:
+            raise ValueError(f"{name}: expected {rows}x{cols} elements, got {v.numel()}")
+        flat[off:off + rows * cols] = v
+    return flat
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
