@@ -139,6 +139,10 @@ int* b2t_step_counters(b2t_engine* e);
 int b2t_greedy_edit(b2t_engine* e, const int* labels, int Smax, const int* in_len, const int* tgt_len, int* decoded,
                     int* dec_len, int* edit, void* stream);
 
+/* Profiling aid: device buffer of 2*T'*8 int64; CTA 0 of the layer-0 forward and top-layer backward recurrence
+ * kernels records clock64() at eight points of every time step.  NULL disables. */
+int b2t_debug_set_trace(b2t_engine* e, long long* device_buf);
+
 /* Number of kernels this library has launched on behalf of the calling process (bench accounting). */
 long long b2t_launch_count(void);
 

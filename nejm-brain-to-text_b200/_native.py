@@ -64,6 +64,7 @@ def _load():
         "b2t_backward": (ci, [vp, vp]),
         "b2t_optimizer_step": (ci, [vp, C.POINTER(AdamWArgs), vp, vp]),
         "b2t_step_counters": (vp, [vp]),
+        "b2t_debug_set_trace": (ci, [vp, vp]),
         "b2t_greedy_edit": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp]),
         "b2t_gemm_bf16": (ci, [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp, vp]),
     }

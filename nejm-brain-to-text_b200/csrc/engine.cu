@@ -139,9 +139,8 @@ struct b2t_engine {
   float *params, *grads, *m1, *m2;
   // carved buffers
   __nv_bfloat16* shadow;
-  __nv_bfloat16* whhT;        // [L][H][3H]
   __nv_bfloat16 *xs, *xd, *xu, *dxu, *dpre, *dGx, *dGh, *dlog16;
-  float *gx, *logits, *dlog32, *alpha, *dY[2], *dh0, *h_init, *h_final;
+  float *gx, *logits, *dlog32, *alpha, *dY[2], *dh0, *h_init, *h_final, *part;
   std::vector<LayerBuf> lay;
   int *done, *day_pad, *steps, *greedy_scratch;
   float *sumsq, *stats;
@@ -154,13 +153,13 @@ struct b2t_engine {
   bool plans_ok = false, use_unfold_copy = false;
   GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw;
   std::vector<GemmPlan> p_in, p_dwih, p_dwhh, p_dx;
-  std::vector<CUtensorMap> tm_w, tm_h, tm_wt;
-  CUtensorMap tm_g;
+  std::vector<CUtensorMap> tm_h;
   // state of the last forward
   bool have_fwd = false, have_dlogits = false, fwd_training = false;
   unsigned long long seed = 0;
   const int* day_idx = nullptr;
   bool states_given = false;
+  long long* trace = nullptr;   // optional device buffer [2][T'][8] for the recurrence cycle trace
 };
 
 static long long seg_off(const b2t_engine* e, const std::string& n) {
@@ -176,7 +175,6 @@ static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
   const size_t M = (size_t)(Tp > 0 ? Tp : 1) * Bp;
   const bool tr = e->training != 0;
   e->shadow = c.take<__nv_bfloat16>(e->n_params);
-  e->whhT = c.take<__nv_bfloat16>((size_t)L * H * 3 * H);
   e->xs = c.take<__nv_bfloat16>((size_t)Bp * T * D);
   e->xd = c.take<__nv_bfloat16>((size_t)Bp * T * D);
   e->xu = c.take<__nv_bfloat16>(M * e->K0);
@@ -207,6 +205,7 @@ static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
     e->dxu = c.take<__nv_bfloat16>(M * e->K0);
     e->dpre = c.take<__nv_bfloat16>((size_t)Bp * T * D);
     e->dh0 = c.take<float>((size_t)L * Bp * H);
+    e->part = c.take<float>((size_t)2 * (Bp / 16) * (H / 32) * (H / 32) * 512);
     e->sumsq = c.take<float>(4);
     e->stats = e->sumsq ? e->sumsq + 1 : nullptr;
     e->steps = c.take<int>(e->segs.size());
@@ -271,18 +270,17 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
 }
 extern "C" void b2t_engine_destroy(b2t_engine* e) { delete e; }
 extern "C" int* b2t_step_counters(b2t_engine* e) { return e ? e->steps : nullptr; }
+extern "C" int b2t_debug_set_trace(b2t_engine* e, long long* buf) {
+  if (!e) return fail(B2T_ERR_ARG, "null engine");
+  e->trace = buf;
+  return 0;
+}
 
 extern "C" int b2t_refresh_weights(b2t_engine* e, void* stream) {
   if (!e) return fail(B2T_ERR_ARG, "null engine");
   cudaStream_t st = (cudaStream_t)stream;
   cast_bf16_kernel<<<num_sms() * 4, 256, 0, st>>>(e->params, e->shadow, (size_t)e->n_params);
   CK(LAUNCHED());
-  for (int l = 0; l < e->L; ++l) {
-    const long long off = seg_off(e, "gru.weight_hh_l" + std::to_string(l));
-    dim3 grid((e->H + 31) / 32, (3 * e->H + 31) / 32), blk(32, 8);
-    transpose_bf16_kernel<<<grid, blk, 0, st>>>(e->shadow + off, e->whhT + (size_t)l * e->H * 3 * e->H, 3 * e->H, e->H);
-    CK(LAUNCHED());
-  }
   return 0;
 }
 
@@ -303,9 +301,7 @@ static int build_plans(b2t_engine* e) {
   e->p_dwih.assign(L, GemmPlan());
   e->p_dwhh.assign(L, GemmPlan());
   e->p_dx.assign(L, GemmPlan());
-  e->tm_w.assign(L, CUtensorMap());
   e->tm_h.assign(L, CUtensorMap());
-  e->tm_wt.assign(L, CUtensorMap());
   int rc;
   {  // day layer: xd[b] = softsign(xs[b] @ W_day[day_b] + b_day[day_b]) (+dropout)      rnn_model.py:95-103
     GemmSpec s;
@@ -346,9 +342,7 @@ static int build_plans(b2t_engine* e) {
       s.A = e->lay[l - 1].hdrop ? e->lay[l - 1].hdrop : e->lay[l - 1].hseq + (size_t)Bp * H;
       if ((rc = gemm_plan_build(&e->p_in[l], s))) return fail(B2T_ERR_CUDA, "input plan %d failed (%d)", l, rc);
     }
-    if (make_2d(&e->tm_w[l], e->shadow + seg_off(e, "gru.weight_hh_l" + sl), H, 3 * H, H, 32)) return fail(B2T_ERR_CUDA, "W_hh map failed");
     if (make_2d(&e->tm_h[l], e->lay[l].hseq, H, (uint64_t)(Tp + 1) * Bp, H, 16)) return fail(B2T_ERR_CUDA, "hseq map failed");
-    if (tr && make_2d(&e->tm_wt[l], e->whhT + (size_t)l * H * 3 * H, 3 * H, H, 3 * H, 32)) return fail(B2T_ERR_CUDA, "W_hh^T map failed");
   }
   {  // head: logits = top @ W_out^T + b_out                                       rnn_model.py:129
     GemmSpec s;
@@ -361,7 +355,6 @@ static int build_plans(b2t_engine* e) {
     if ((rc = gemm_plan_build(&e->p_head, s))) return fail(B2T_ERR_CUDA, "head plan failed (%d)", rc);
   }
   if (!tr) return 0;
-  if (make_2d(&e->tm_g, e->dGh, 3 * H, (uint64_t)Tp * Bp, 3 * H, 16)) return fail(B2T_ERR_CUDA, "dGh map failed");
   {  // dW_out[C][H] = dlogits^T top
     GemmSpec s;
     s.a_mn = 1; s.b_mn = 1; s.epi = EPI_STORE;
@@ -463,25 +456,23 @@ extern "C" int b2t_output_frames(const b2t_config* cfg, int T, int smooth_mode, 
   return To;
 }
 
-template <typename P>
-static cudaError_t launch_rec(void (*kern)(const CUtensorMap, const CUtensorMap, const P), const CUtensorMap& a, const CUtensorMap& b, const P& p,
-                              int grid, size_t smem, cudaStream_t st) {
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// The recurrence kernels allocate all 512 TMEM columns, so two CTAs must never share an SM: requesting more than
+// half of the shared memory forces one CTA per SM.  Cooperative launch guarantees that every CTA of the grid is
+// co-resident (they spin on each other's flags).
+constexpr size_t REC_SMEM_BYTES = 120 * 1024;
+static cudaError_t launch_rec_fwd(const CUtensorMap& tm, const RecFwdParams& p, int grid, cudaStream_t st) {
+  cudaError_t err = cudaFuncSetAttribute(gru_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM_BYTES);
   if (err != cudaSuccess) return err;
-  void* args[3] = {(void*)&a, (void*)&b, (void*)&p};
-  // cooperative launch: guarantees that every CTA of the grid is co-resident (they spin on each other's flags)
-  err = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(REC_THREADS), args, smem, st);
+  void* args[2] = {(void*)&tm, (void*)&p};
   ++g_launches;
-  return err;
+  return cudaLaunchCooperativeKernel((const void*)gru_rec_fwd_kernel, dim3(grid), dim3(REC_THREADS), args, REC_SMEM_BYTES, st);
 }
-
-static size_t rec_fwd_smem(int H) {
-  const int KC = H / 64;
-  return 1024 + (size_t)KC * 12288 + (size_t)(KC * 2048 > 4096 ? KC * 2048 : 4096) + 3 * 32 * REC_XPAD * 4 + 18 * 8 + 16;
-}
-static size_t rec_bwd_smem(int H) {
-  const int KC = 3 * H / 64;
-  return 1024 + (size_t)KC * 4096 + (size_t)(KC * 2048 > 12288 ? KC * 2048 : 12288) + 32 * REC_XPAD * 4 + 50 * 8 + 16;
+static cudaError_t launch_rec_bwd(const RecBwdParams& p, int grid, cudaStream_t st) {
+  cudaError_t err = cudaFuncSetAttribute(gru_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM_BYTES);
+  if (err != cudaSuccess) return err;
+  void* args[1] = {(void*)&p};
+  ++g_launches;
+  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd_kernel, dim3(grid), dim3(REC_THREADS), args, REC_SMEM_BYTES, st);
 }
 
 // ------------------------------------------------------------------------------------ forward
@@ -550,15 +541,17 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
     RecFwdParams rp;
     rp.H = H; rp.T = Tp; rp.Bpad = Bp; rp.n_slices = H / 32;
     rp.gx = e->gx; rp.bhh = e->params + seg_off(e, "gru.bias_hh_l" + std::to_string(l));
+    rp.whh = e->shadow + seg_off(e, "gru.weight_hh_l" + std::to_string(l));
     rp.hseq = e->lay[l].hseq; rp.h_init = hin; rp.h_final = e->h_final + (size_t)l * Bp * H;
     const bool save = a->training != 0;
     rp.hdrop = save ? e->lay[l].hdrop : nullptr;
     rp.R = save ? e->lay[l].R : nullptr; rp.Z = save ? e->lay[l].Z : nullptr;
     rp.Nn = save ? e->lay[l].Nn : nullptr; rp.HN = save ? e->lay[l].HN : nullptr;
     rp.done = e->done; rp.keep = keep_rnn; rp.seed = a->seed; rp.rng_offset = (unsigned long long)(l + 1) << 40;
+    rp.trace = (l == 0) ? e->trace : nullptr;
     // eval-mode forward through a training engine: the next layer reads hdrop if it exists, so keep it in sync
     if (!save && e->lay[l].hdrop) { rp.hdrop = e->lay[l].hdrop; rp.keep = 1.0f; }
-    CK(launch_rec(gru_rec_fwd_kernel, e->tm_w[l], e->tm_h[l], rp, grid, rec_fwd_smem(H), st));
+    CK(launch_rec_fwd(e->tm_h[l], rp, grid, st));
   }
   // 4. head
   CK(gemm_run(e->p_head, st)); ++g_launches;
@@ -668,13 +661,15 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     bp.H = H; bp.T = Tp; bp.Bpad = Bp; bp.n_slices = H / 32;
     bp.dY = e->dY[(L - 1 - l) & 1];
     bp.hseq = e->lay[l].hseq; bp.R = e->lay[l].R; bp.Z = e->lay[l].Z; bp.Nn = e->lay[l].Nn; bp.HN = e->lay[l].HN;
-    bp.dGx = e->dGx; bp.dGh = e->dGh;
+    bp.dGx = e->dGx; bp.dGh = e->dGh; bp.part = e->part;
+    bp.whh = e->shadow + seg_off(e, "gru.weight_hh_l" + sl);
     bp.dbih = e->grads + seg_off(e, "gru.bias_ih_l" + sl); bp.dbhh = e->grads + seg_off(e, "gru.bias_hh_l" + sl);
     bp.dh0 = e->dh0 + (size_t)l * Bp * H;
     bp.done = e->done; bp.n_valid = e->B;
     bp.keep = (l < L - 1) ? keep_rnn : 1.0f;
     bp.seed = e->seed; bp.rng_offset = (unsigned long long)(l + 1) << 40;
-    CK(launch_rec(gru_rec_bwd_kernel, e->tm_wt[l], e->tm_g, bp, grid, rec_bwd_smem(H), st));
+    bp.trace = (l == L - 1 && e->trace) ? e->trace + (size_t)Tp * 8 : nullptr;
+    CK(launch_rec_bwd(bp, grid, st));
     CK(gemm_run(e->p_dwih[l], st)); ++g_launches;
     CK(gemm_run(e->p_dwhh[l], st)); ++g_launches;
     CK(gemm_run(e->p_dx[l], st)); ++g_launches;
@@ -716,12 +711,6 @@ extern "C" int b2t_optimizer_step(b2t_engine* e, const b2t_adamw_args* a, float*
   CK(LAUNCHED());
   bump_steps_kernel<<<((int)e->segs.size() + 127) / 128, 128, 0, st>>>(e->d_segs, (int)e->segs.size(), e->touched, e->steps);
   CK(LAUNCHED());
-  for (int l = 0; l < e->L; ++l) {
-    const long long off = seg_off(e, "gru.weight_hh_l" + std::to_string(l));
-    dim3 grid((e->H + 31) / 32, (3 * e->H + 31) / 32), blk(32, 8);
-    transpose_bf16_kernel<<<grid, blk, 0, st>>>(e->shadow + off, e->whhT + (size_t)l * e->H * 3 * e->H, 3 * e->H, e->H);
-    CK(LAUNCHED());
-  }
   if (stats_out) CK(cudaMemcpyAsync(stats_out, e->stats, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }

@@ -6,16 +6,22 @@
 // gx = x W_ih^T + b_ih is produced for all time steps by the tcgen05 GEMM (gemm.cuh).
 //
 // Decomposition.  The batch is cut into groups of 16 trials and the hidden units into slices of 32.
-// CTA (slice s, group g) keeps the 96 rows {r,z,n} x 32 units of W_hh (bf16, 147 KB for H=768)
-// resident in shared memory for the whole sequence and, per time step, computes
-//     D[128 (96 used), 16] = W_slice[128, H] * h_{t-1}[16, H]^T
-// with H/16 tcgen05.mma (M=128, N=16, K=16) into TMEM.  h_{t-1} is fetched by TMA as the K-major
-// B operand (H/64 boxes of 16 rows x 128 B).  The three gate row-blocks land in TMEM lane
-// quarters 0,1,2; the epilogue warps move them through a 6 KB smem exchange so that one thread
-// owns (trial, 4 units) with all three gates, applies the gate math in fp32 (the hidden state itself
-// is carried in fp32 registers across steps), and writes h_t (bf16) for the next step plus the
-// activations BPTT needs.  Trials are independent, so only the H/32 CTAs of one batch group
-// synchronise per step, through a release/acquire counter in global memory.
+// CTA (slice s, group g) owns the 96 gate rows {r,z,n} x 32 units of W_hh for the whole sequence.
+// The weights live in TENSOR MEMORY as the A operand of tcgen05.mma (lane = gate row, 32-bit column =
+// two packed bf16 of K; 384 of the 512 TMEM columns for H = 768), so a time step never re-reads them
+// from shared memory: measured on B200, the smem-resident variant spent 3.6k cycles per step
+// streaming the 147 KB slice through the MMA's smem port for an N=16 product.
+//
+//   forward : D[128 (96 used), 16] = W_slice[128, H] (TMEM) * h_{t-1}[16, H]^T (smem, via TMA)
+//             The three gate row-blocks land in TMEM lane quarters 0,1,2; the epilogue warps move them
+//             through a 6 KB smem exchange so that one thread owns (trial, 4 units) with all gates, does
+//             the gate math in fp32 (h itself is carried in fp32 registers) and writes h_t (bf16).
+//   backward: the same CTA owns dG_t[16, 96] (its own 32 units x 3 gates) and keeps W_slice^T in TMEM:
+//             P[H, 16] = W_slice^T[H, 96] (TMEM, H/128 row blocks) * dG_t[16, 96]^T (smem, written
+//             locally).  P is this CTA's partial of dh_{t-1} for ALL units; the H/32 CTAs of a batch
+//             group exchange fp32 partials through L2 (reduce-scatter) once per step.
+// Trials are independent, so only the H/32 CTAs of one batch group synchronise per step, through a
+// release/acquire counter in global memory (cooperative launch guarantees co-residency).
 #pragma once
 #include "sm100.cuh"
 
@@ -23,14 +29,17 @@ namespace b2t {
 
 constexpr int REC_BG = 16;        // trials per batch group (UMMA N)
 constexpr int REC_US = 32;        // hidden units per CTA
-constexpr int REC_THREADS = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int REC_THREADS = 192;  // warp0 producer/poller, warp1 MMA + TMEM owner, warps 2..5 epilogue
 constexpr int REC_XPAD = 20;      // exchange row pitch (floats)
+constexpr int REC_TMEM_COLS = 512;
+constexpr int REC_D_COL = 384;    // accumulator columns start here (A uses [0, 384))
 
 struct RecFwdParams {
   int H, T, Bpad;                 // hidden size, time steps, padded batch (multiple of 16)
   int n_slices;                   // H / 32
   const float* gx;                // [T][Bpad][3H] fp32, includes b_ih
   const float* bhh;               // [3H]
+  const __nv_bfloat16* whh;       // [3H][H] bf16
   __nv_bfloat16* hseq;            // [(T+1)][Bpad][H]; slot 0 = initial state, slot t+1 = h_t
   const float* h_init;            // [Bpad][H] fp32 initial state (register carry)
   float* h_final;                 // [Bpad][H] fp32 (nullable)
@@ -39,10 +48,12 @@ struct RecFwdParams {
   int* done;                      // [n_groups][T] arrival counters, zeroed before launch
   float keep;                     // dropout keep prob for hdrop
   unsigned long long seed, rng_offset;
+  long long* trace;               // optional [T][8] clock64 samples from CTA 0 (profiling aid)
 };
 
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#define REC_TRACE(step, slot) do { if (p.trace && blockIdx.x == 0) p.trace[(step) * 8 + (slot)] = clock64(); } while (0)
 
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ void wait_counter(const int* ctr, int target) {
@@ -52,24 +63,39 @@ __device__ __forceinline__ void wait_counter(const int* ctr, int target) {
   }
 }
 
+// A operand from TMEM, B operand from shared memory.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // dropout decision for element (row m, unit j) of a [*, H] activation; same function in fwd and bwd.
 __device__ __forceinline__ uint4 rec_dropout_bits(unsigned long long seed, unsigned long long offset, unsigned long long elem4) {
   const unsigned long long c = elem4 + offset;
   return philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x6a7eu, 0), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
-// tmap_w : W_hh bf16 [3H][H]   dims (H, 3H)          box (64, 32)
-// tmap_h : hseq bf16          dims (H, (T+1)*Bpad)  box (64, 16)
+// tmap_h : hseq bf16   dims (H, (T+1)*Bpad)  box (64, 16)
 __global__ void __launch_bounds__(REC_THREADS, 1)
-gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h, const RecFwdParams p) {
+gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int KC = p.H / 64;                               // contraction chunks
-  uint8_t* sW = smem;                                    // KC x 12 KB (96 rows x 128 B)
-  uint8_t* sH = sW + KC * 12288;                         // KC x 2 KB (16 rows x 128 B); also absorbs the M=128 over-read of sW
-  float* sX = reinterpret_cast<float*>(sH + (KC * 2048 > 4096 ? KC * 2048 : 4096));   // [3][32][REC_XPAD]
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(sX + 3 * 32 * REC_XPAD);
-  uint64_t* bar_h = bar_w + 1;                           // [KC] (<= 16)
+  const int KC = p.H / 64;                               // 64-wide contraction chunks
+  uint8_t* sH = smem;                                    // KC x 2 KB (16 rows x 128 B, SWIZZLE_128B)
+  float* sX = reinterpret_cast<float*>(sH + KC * 2048);  // [3][32][REC_XPAD]
+  uint64_t* bar_h = reinterpret_cast<uint64_t*>(sX + 3 * 32 * REC_XPAD);   // [KC] (<= 16)
   uint64_t* bar_d = bar_h + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
 
@@ -79,50 +105,68 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   int* done = p.done + (size_t)grp * p.T;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_h);
-    mbar_init(bar_w, 1);
     for (int c = 0; c < KC; ++c) mbar_init(&bar_h[c], 1);
     mbar_init(bar_d, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<32>(tmem_slot);
+  if (warp == 1) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d = tmem_base + REC_D_COL;
+
+  // ---- one-time: W_hh slice -> TMEM.  Lane 32q+l holds gate q, unit j0+l; quarter 3 is zero.
+  if (warp >= 2) {
+    const int q = warp & 3;
+    const uint4* src = reinterpret_cast<const uint4*>(p.whh + ((size_t)(q < 3 ? q : 0) * p.H + j0 + lane) * p.H);
+    for (int w0 = 0; w0 < p.H / 2; w0 += 16) {
+      uint32_t v[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (q < 3) u = __ldg(src + w0 / 4 + i);
+        v[4 * i] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
+      }
+      tmem_st16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + w0, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp == 0) {
     if (elect_one()) {
-      // resident weights: per chunk three 32-row boxes (r, z, n rows of this unit slice)
-      mbar_arrive_expect_tx(bar_w, KC * 12288);
-      for (int c = 0; c < KC; ++c)
-        for (int g = 0; g < 3; ++g) tma_load_2d(sW + c * 12288 + g * 4096, &tmap_w, bar_w, c * 64, g * p.H + j0);
       for (int t = 0; t < p.T; ++t) {
         if (t > 0) {
           wait_counter(&done[t - 1], p.n_slices);
           fence_proxy_async_all();             // order the acquired generic-proxy writes before async-proxy reads
         }
+        REC_TRACE(t, 0);                       // flags acquired
         for (int c = 0; c < KC; ++c) {
           mbar_arrive_expect_tx(&bar_h[c], 2048);
           tma_load_2d(sH + c * 2048, &tmap_h, &bar_h[c], c * 64, t * p.Bpad + b0);   // slot t = h_{t-1}
         }
+        REC_TRACE(t, 1);                       // TMA issued
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, REC_BG, 0, 0);
-      mbar_wait(bar_w, 0);
       for (int t = 0; t < p.T; ++t) {
         for (int c = 0; c < KC; ++c) {
           mbar_wait(&bar_h[c], t & 1);
+          if (c == 0) REC_TRACE(t, 2);         // first operand chunk landed
           tc_fence_after();
-          const uint32_t sa = smem_u32(sW + c * 12288), sb = smem_u32(sH + c * 2048);
+          const uint32_t sb = smem_u32(sH + c * 2048);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_d, umma_smem_desc(sa + k * 32, 16, 1024), umma_smem_desc(sb + k * 32, 16, 1024), idesc, (c | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)     // accumulator k: the tensor pipe sees a dependent MMA only every 4th issue
+            umma_bf16_ts(tmem_d + k * REC_BG, tmem_base + (c * 4 + k) * 8, umma_smem_desc(sb + k * 32, 16, 1024), idesc, c != 0 ? 1u : 0u);
         }
         umma_commit(bar_d);
+        REC_TRACE(t, 3);                       // all MMAs issued
       }
     }
   } else {
@@ -151,18 +195,26 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       for (int g = 0; g < 3; ++g) gxv[g] = __ldg(reinterpret_cast<const float4*>(p.gx + row * 3 * p.H + g * p.H + j));
 
       mbar_wait(bar_d, t & 1);
+      if (e == 0) REC_TRACE(t, 4);             // accumulator complete
       tc_fence_after();
       if (q < 3) {
-        uint32_t v[16];
-        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16), v);
+        uint32_t v0[16], v1[16], v2[16], v3[16];
+        const uint32_t ta = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
+        tmem_ld16(ta, v0); tmem_ld16(ta + 16, v1); tmem_ld16(ta + 32, v2); tmem_ld16(ta + 48, v3);
         tmem_ld_wait();
         float4* dst = reinterpret_cast<float4*>(sX + (q * 32 + lane) * REC_XPAD);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        for (int i = 0; i < 4; ++i) {
+          float f[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            f[k] = (__uint_as_float(v0[4 * i + k]) + __uint_as_float(v1[4 * i + k])) + (__uint_as_float(v2[4 * i + k]) + __uint_as_float(v3[4 * i + k]));
+          dst[i] = make_float4(f[0], f[1], f[2], f[3]);
+        }
       }
       tc_fence_before();
       epi_bar_sync();
+      if (e == 0) REC_TRACE(t, 7);             // gates exchanged
       float hn[4], r[4], z[4], n[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -178,6 +230,16 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       }
       const size_t off = row * p.H + j;
       st_bf16x4(p.hseq + ((size_t)(t + 1) * p.Bpad + b) * p.H + j, h[0], h[1], h[2], h[3]);
+      if (e == 0) REC_TRACE(t, 5);             // h_t stored
+      // publish h_t: every thread's store is ordered before the CTA barrier; the release by one thread is
+      // cumulative over it (same pattern as a grid barrier).  The BPTT stash is written after the release,
+      // off the critical path of the other CTAs.
+      epi_bar_sync();
+      if (e == 0) {
+        fence_proxy_async_all();
+        red_release_add(&done[t], 1);
+        REC_TRACE(t, 6);                       // published
+      }
       if (train) {
         st_bf16x4(p.R + off, r[0], r[1], r[2], r[3]);
         st_bf16x4(p.Z + off, z[0], z[1], z[2], z[3]);
@@ -194,11 +256,6 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         }
         st_bf16x4(p.hdrop + off, d[0], d[1], d[2], d[3]);
       }
-      // publish h_t: generic stores -> (proxy fence, gpu fence) -> all epilogue threads done -> one release
-      fence_proxy_async_all();
-      __threadfence();
-      epi_bar_sync();
-      if (e == 0) red_release_add(&done[t], 1);
     }
     if (p.h_final) *reinterpret_cast<float4*>(p.h_final + (size_t)b * p.H + j) = make_float4(h[0], h[1], h[2], h[3]);
   }
@@ -207,7 +264,7 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<32>(tmem_d);
+    tmem_dealloc<REC_TMEM_COLS>(tmem_base);
   }
 }
 
@@ -217,17 +274,16 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 //   dr_pre = dn_pre*hn*r*(1-r)
 //   dGx_t = [dr_pre, dz_pre, dn_pre]        dGh_t = [dr_pre, dz_pre, dn_pre*r]
 //   dh_{t-1} = dh*z + dGh_t W_hh + dY_{t-1}
-// CTA (slice, group) owns 32 hidden units and keeps W_hh^T[32 units][3H] (147 KB) resident as the
-// A operand; the B operand is dGh_t[16 trials][3H] (K-major), fetched by TMA once every CTA of the
-// batch group has published its 96 columns of it.  dW_ih/dW_hh are GEMMs over dGx/dGh afterwards;
-// the bias gradients are accumulated here in registers and reduced with one atomicAdd per thread.
+// dW_ih/dW_hh are GEMMs over dGx/dGh afterwards; the bias gradients are accumulated here in registers.
 struct RecBwdParams {
   int H, T, Bpad, n_slices;
   const float* dY;                  // [T][Bpad][H] fp32 gradient wrt this layer's (dropped) output
   const __nv_bfloat16* hseq;        // [(T+1)][Bpad][H]
   const __nv_bfloat16 *R, *Z, *Nn, *HN;
+  const __nv_bfloat16* whh;         // [3H][H] bf16
   __nv_bfloat16* dGx;               // [T][Bpad][3H]
   __nv_bfloat16* dGh;               // [T][Bpad][3H]
+  float* part;                      // [2][n_groups][n_slices(dest)][n_slices(src)][16][32] fp32 partial sums of dh
   float* dbih;                      // [3H] (atomicAdd)
   float* dbhh;                      // [3H] (atomicAdd)
   float* dh0;                       // [Bpad][H] gradient wrt the initial state (written)
@@ -235,84 +291,103 @@ struct RecBwdParams {
   int n_valid;                      // trials < n_valid contribute (pad trials are masked out)
   float keep;                       // dropout applied to this layer's output in forward (1 => none)
   unsigned long long seed, rng_offset;
+  long long* trace;                 // optional [T][8] clock64 samples from CTA 0
 };
 
-// tmap_wt : W_hh^T bf16 [H][3H]  dims (3H, H)        box (64, 32)
-// tmap_g  : dGh bf16            dims (3H, T*Bpad)   box (64, 16)
 __global__ void __launch_bounds__(REC_THREADS, 1)
-gru_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_wt, const __grid_constant__ CUtensorMap tmap_g, const RecBwdParams p) {
+gru_rec_bwd_kernel(const RecBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int KC = 3 * p.H / 64;                           // contraction chunks over the 3H gate columns
-  uint8_t* sW = smem;                                    // KC x 4 KB (32 rows x 128 B)
-  uint8_t* sG = sW + KC * 4096;                          // KC x 2 KB; also absorbs the 12 KB M=128 over-read
-  float* sX = reinterpret_cast<float*>(sG + (KC * 2048 > 12288 ? KC * 2048 : 12288));  // [32][REC_XPAD]
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(sX + 32 * REC_XPAD);
-  uint64_t* bar_g = bar_w + 1;                           // [KC] (<= 48)
-  uint64_t* bar_d = bar_g + 48;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
+  uint8_t* sB = smem;                                    // 2 chunks x 2 KB: dG_t as K-major B operand [16 trials][128 kk] (kk = gate*32 + unit, 96 used)
+  uint64_t* bar_d = reinterpret_cast<uint64_t*>(sB + 4096);
+  uint64_t* bar_f = bar_d + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_f + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slice = blockIdx.x % p.n_slices, grp = blockIdx.x / p.n_slices;
+  const int NS = p.n_slices, NG = gridDim.x / NS;
+  const int slice = blockIdx.x % NS, grp = blockIdx.x / NS;
   const int j0 = slice * REC_US, b0 = grp * REC_BG;
+  const int MB = (p.H + 127) / 128;                      // 128-row blocks of the output (all hidden units)
   int* done = p.done + (size_t)grp * p.T;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmap_wt);
-    tma_prefetch_desc(&tmap_g);
-    mbar_init(bar_w, 1);
-    for (int c = 0; c < KC; ++c) mbar_init(&bar_g[c], 1);
     mbar_init(bar_d, 1);
+    mbar_init(bar_f, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<32>(tmem_slot);
+  if (warp == 1) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < 1024; i += REC_THREADS) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d = tmem_base + REC_D_COL;
 
-  // Steps are indexed s = 0..T-1 for t = T-1-s.  MMA s (s >= 1) consumes dGh_{t+1} and feeds dh_t.
+  // ---- one-time: W_slice^T -> TMEM.  Block mb, lane m holds output unit k = mb*128+m; column w packs
+  //      kk = 2w, 2w+1 with kk = gate*32 + unit (48 words per block, block pitch 64 columns).
+  if (warp >= 2) {
+    const int q = warp & 3;
+    for (int mb = 0; mb < MB; ++mb) {
+      const int k = mb * 128 + q * 32 + lane;
+      for (int w0 = 0; w0 < 48; w0 += 16) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int kk = 2 * (w0 + i);
+          uint32_t lo = 0, hi = 0;
+          if (k < p.H) {
+            const size_t r0 = ((size_t)(kk >> 5) * p.H + j0 + (kk & 31)) * p.H + k;
+            lo = __bfloat16_as_ushort(p.whh[r0]);
+            hi = __bfloat16_as_ushort(p.whh[r0 + p.H]);   // kk+1 is the next unit of the same gate
+          }
+          v[i] = lo | (hi << 16);
+        }
+        tmem_st16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mb * 64 + w0, v);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // Steps are indexed s = 0..T-1 for t = T-1-s.  The partials published at step s feed dh of step s+1.
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(bar_w, KC * 4096);
-      for (int c = 0; c < KC; ++c) tma_load_2d(sW + c * 4096, &tmap_wt, bar_w, c * 64, j0);
-      for (int s = 1; s <= p.T; ++s) {                   // s == T: extra product for the initial-state gradient
-        const int tsrc = p.T - s;                        // dGh_{t+1}
-        wait_counter(&done[tsrc], p.n_slices);
-        fence_proxy_async_all();
-        for (int c = 0; c < KC; ++c) {
-          mbar_arrive_expect_tx(&bar_g[c], 2048);
-          tma_load_2d(sG + c * 2048, &tmap_g, &bar_g[c], c * 64, tsrc * p.Bpad + b0);
-        }
+      for (int s = 0; s < p.T; ++s) {                    // forward the "all partials of step s are visible" event to the CTA
+        wait_counter(&done[s], NS);
+        REC_TRACE(s, 0);
+        mbar_arrive(bar_f);
       }
     }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, REC_BG, 0, 0);
-      mbar_wait(bar_w, 0);
-      for (int s = 1; s <= p.T; ++s) {
-        for (int c = 0; c < KC; ++c) {
-          mbar_wait(&bar_g[c], (s - 1) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(sW + c * 4096), sb = smem_u32(sG + c * 2048);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_d, umma_smem_desc(sa + k * 32, 16, 1024), umma_smem_desc(sb + k * 32, 16, 1024), idesc, (c | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(bar_d);
-      }
-    }
-  } else {
+  } else if (warp >= 2) {
     const int e = threadIdx.x - 64;
     const int q = warp & 3;
     const int bl = e >> 3, u0 = (e & 7) * 4;
     const int b = b0 + bl, j = j0 + u0;
     const bool valid = b < p.n_valid;
     const float inv_keep = 1.0f / p.keep;
+    constexpr uint32_t idesc = umma_idesc_bf16(128, REC_BG, 0, 0);
     float carry[4] = {0.f, 0.f, 0.f, 0.f};               // dh_{t+1} * z_{t+1}
     float accx[3][4], acch[4];                           // bias-gradient partial sums (dGh differs only in n)
 #pragma unroll
     for (int i = 0; i < 4; ++i) { accx[0][i] = accx[1][i] = accx[2][i] = 0.f; acch[i] = 0.f; }
+
+    auto gather_partials = [&](int s_prev, float (&P)[4]) {
+      // sum over the NS source CTAs of the partial for (trial bl, units u0..u0+3) published at step s_prev
+      const float* base = p.part + ((((size_t)(s_prev & 1) * NG + grp) * NS + slice) * NS) * 512 + bl * 32 + u0;
+      P[0] = P[1] = P[2] = P[3] = 0.f;
+      for (int src = 0; src < NS; src += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (src + i < NS) v[i] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(src + i) * 512));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (src + i < NS) { P[0] += v[i].x; P[1] += v[i].y; P[2] += v[i].z; P[3] += v[i].w; }
+      }
+    };
+
     for (int s = 0; s < p.T; ++s) {
       const int t = p.T - 1 - s;
       const size_t row = (size_t)t * p.Bpad + b;
@@ -330,21 +405,12 @@ gru_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_wt, const __grid_con
       }
       float dh[4];
       if (s > 0) {
-        mbar_wait(bar_d, (s - 1) & 1);
-        tc_fence_after();
-        if (q == 0) {
-          uint32_t v[16];
-          tmem_ld16(tmem_d, v);
-          tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(sX + lane * REC_XPAD);
+        mbar_wait(bar_f, (s - 1) & 1);                   // partials of step s-1 from every CTA of the group are visible
+        if (e == 0) REC_TRACE(s, 1);
+        float P[4];
+        gather_partials(s - 1, P);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-        }
-        tc_fence_before();
-        epi_bar_sync();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dh[i] = carry[i] + sX[(u0 + i) * REC_XPAD + bl] + dy[i];
+        for (int i = 0; i < 4; ++i) dh[i] = carry[i] + P[i] + dy[i];
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) dh[i] = dy[i];
@@ -362,36 +428,76 @@ gru_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_wt, const __grid_con
         carry[i] = d * z[i];
         accx[0][i] += gr[i]; accx[1][i] += gz[i]; accx[2][i] += gn[i]; acch[i] += gnh[i];
       }
+      // dGh_t -> shared memory as the K-major, 128B-swizzled B operand: row = trial, kk = gate*32 + unit
+      {
+        const float* gsel[3] = {gr, gz, gnh};
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const int kk = g * 32 + u0;                    // 4 consecutive kk, 8 bytes
+          const int chunk = kk >> 6, kl = kk & 63;
+          uint8_t* dst = sB + chunk * 2048 + bl * 128 + ((((kl >> 3) ^ (bl & 7)) & 7) << 4) + (kl & 7) * 2;
+          __nv_bfloat162 lo = __floats2bfloat162_rn(gsel[g][0], gsel[g][1]), hi = __floats2bfloat162_rn(gsel[g][2], gsel[g][3]);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&lo);
+          u.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(dst) = u;
+        }
+      }
+      fence_proxy_async_smem();                          // generic smem writes -> visible to the tensor-core (async) proxy
+      tc_fence_before();
+      epi_bar_sync();
+      if (e == 0) {
+        REC_TRACE(s, 2);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(sB);
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks) {                 // K = 96 = 6 x 16; the MB accumulators are independent chains
+          const uint64_t bdesc = umma_smem_desc(sb + (ks >> 2) * 2048 + (ks & 3) * 32, 16, 1024);
+          for (int mb = 0; mb < MB; ++mb) umma_bf16_ts(tmem_d + mb * 16, tmem_base + mb * 64 + ks * 8, bdesc, idesc, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_d);
+        REC_TRACE(s, 3);
+      }
+      // off the critical path: gate gradients for the weight-gradient GEMMs
       const size_t goff = row * 3 * p.H + j;
-      st_bf16x4(p.dGx + goff, gr[0], gr[1], gr[2], gr[3]);
-      st_bf16x4(p.dGx + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
-      st_bf16x4(p.dGx + goff + 2 * p.H, gn[0], gn[1], gn[2], gn[3]);
       st_bf16x4(p.dGh + goff, gr[0], gr[1], gr[2], gr[3]);
       st_bf16x4(p.dGh + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
       st_bf16x4(p.dGh + goff + 2 * p.H, gnh[0], gnh[1], gnh[2], gnh[3]);
-      fence_proxy_async_all();
-      __threadfence();
-      epi_bar_sync();
-      if (e == 0) red_release_add(&done[t], 1);
-    }
-    // gradient wrt the initial state: dh_{-1} = dh_0 * z_0 + dGh_0 W_hh (the extra product s == T)
-    {
-      mbar_wait(bar_d, (p.T - 1) & 1);
+      st_bf16x4(p.dGx + goff, gr[0], gr[1], gr[2], gr[3]);
+      st_bf16x4(p.dGx + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
+      st_bf16x4(p.dGx + goff + 2 * p.H, gn[0], gn[1], gn[2], gn[3]);
+
+      mbar_wait(bar_d, s & 1);
+      if (e == 0) REC_TRACE(s, 4);
       tc_fence_after();
-      if (q == 0) {
+      // partial sums -> L2: lane = output unit within its 32-unit destination slice, one 128 B line per trial
+      for (int mb = 0; mb < MB; ++mb) {
         uint32_t v[16];
-        tmem_ld16(tmem_d, v);
+        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + mb * 16, v);
         tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(sX + lane * REC_XPAD);
+        const int dest = mb * 4 + q;                     // destination slice = k / 32
+        if (dest < NS) {
+          float* dst = p.part + ((((size_t)(s & 1) * NG + grp) * NS + dest) * NS + slice) * 512 + lane;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          for (int i = 0; i < 16; ++i) dst[i * 32] = __uint_as_float(v[i]);
+        }
       }
+      if (e == 0) REC_TRACE(s, 5);
       tc_fence_before();
       epi_bar_sync();
+      if (e == 0) {
+        red_release_add(&done[s], 1);
+        REC_TRACE(s, 6);
+      }
+    }
+    // gradient wrt the initial state: dh_{-1} = dh_0 * z_0 + dGh_0 W_hh
+    {
+      mbar_wait(bar_f, (p.T - 1) & 1);
+      float P[4];
+      gather_partials(p.T - 1, P);
       float o[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = valid ? carry[i] + sX[(u0 + i) * REC_XPAD + bl] : 0.0f;
+      for (int i = 0; i < 4; ++i) o[i] = valid ? carry[i] + P[i] : 0.0f;
       *reinterpret_cast<float4*>(p.dh0 + (size_t)b * p.H + j) = make_float4(o[0], o[1], o[2], o[3]);
     }
 #pragma unroll
@@ -409,7 +515,7 @@ gru_rec_bwd_kernel(const __grid_constant__ CUtensorMap tmap_wt, const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<32>(tmem_d);
+    tmem_dealloc<REC_TMEM_COLS>(tmem_base);
   }
 }
 

@@ -164,10 +164,12 @@ __device__ __forceinline__ void red_release_add(int* p, int v) {
 }
 
 // ------------------------------------------------------------------ small math
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// One warp per SM sub-partition runs the gate math, so it is latency- not throughput-bound: keep the
+// dependent instruction chains short (MUFU.EX2 + MUFU.RCP; ~2 ulp, far below bf16 resolution).
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_f(float x) {
-  // tanh(x) = 2*sigmoid(2x) - 1 ; exact enough in fp32 (abs err ~1e-7), saturates cleanly.
-  return 2.0f / (1.0f + __expf(-2.0f * x)) - 1.0f;
+  // tanh(x) = 1 - 2/(exp(2x)+1); saturates cleanly for |x| large (exp -> inf gives 1, exp -> 0 gives -1)
+  return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f);
 }
 
 // Philox-4x32-10 counter RNG (Salmon et al. 2011); one call -> four 32-bit words.
