@@ -106,6 +106,10 @@ int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* stream);
 /* T' for an input of T frames under the given smoothing mode and cut. */
 int b2t_output_frames(const b2t_config* cfg, int T, int smooth_mode, int smooth_std_taps, int cut);
 
+/* Stand-alone Gaussian smoothing along time (data_augmentations.py:6-37): x, out device fp32 [B][T][D] ->
+ * [B][T_out][D]; mode 1 = 'same', 2 = 'valid'.  Returns T_out. */
+int b2t_gauss_smooth(const float* x, int B, int T, int D, float std, int size, int mode, float* out, void* stream);
+
 /* CTC on the logits of the last b2t_forward.  labels: device int32 [B][Smax]; in_len/tgt_len: device
  * int32 [B]; loss_out: device fp32 [B] (per-trial, reduction 'none').  With want_grad, the gradient of
  * grad_scale * sum_b loss_b (grad_scale = 1/global_batch reproduces torch.mean) is kept inside the

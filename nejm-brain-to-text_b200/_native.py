@@ -57,6 +57,7 @@ def _load():
         "b2t_refresh_weights": (ci, [vp, vp]),
         "b2t_forward": (ci, [vp, C.POINTER(ForwardArgs), vp]),
         "b2t_output_frames": (ci, [cfgp, ci, ci, ci, ci]),
+        "b2t_gauss_smooth": (ci, [vp, ci, ci, ci, cf, ci, ci, vp, vp]),
         "b2t_ctc_loss": (ci, [vp, vp, ci, vp, vp, cf, vp, ci, vp]),
         "b2t_ctc_loss_tbc": (ci, [vp, ci, ci, ci, vp, ci, vp, vp, cf, vp, vp, vp, ll, vp]),
         "b2t_ctc_workspace_bytes": (ll, [ci, ci, ci]),

@@ -16,6 +16,7 @@ namespace b2t {
 struct PreParams {
   const float* x;          // [B][T_in][D]
   __nv_bfloat16* out;      // [Bpad][T_alloc][D]; rows t >= T_out and trials >= B are zero-filled
+  float* out_f32;          // when non-null: fp32 output [B][T_alloc][D] instead (stand-alone gauss_smooth)
   int B, Bpad, T_in, T_alloc, D;
   int cut;                 // frames dropped from the front (random_cut)
   int ntaps, valid;        // ntaps == 0 => no smoothing
@@ -49,12 +50,14 @@ __global__ void pre_smooth_kernel(const PreParams p) {
   const int t0 = blockIdx.x * PRE_TT;
   if (d >= p.D) return;
   __nv_bfloat16* out = p.out + ((size_t)b * p.T_alloc + t0) * p.D + d;
+  float* out32 = p.out_f32 ? p.out_f32 + ((size_t)b * p.T_alloc + t0) * p.D + d : nullptr;
   const int T_len = p.T_in - p.cut;
   const int nt = p.ntaps > 0 ? p.ntaps : 1;
   const int left = (p.ntaps > 0 && !p.valid) ? (p.ntaps - 1) / 2 : 0;
   const int T_out = (p.ntaps > 0 && p.valid) ? T_len - p.ntaps + 1 : T_len;
   if (b >= p.B) {
-    for (int i = 0; i < PRE_TT && t0 + i < p.T_alloc; ++i) *reinterpret_cast<uint2*>(out + (size_t)i * p.D) = make_uint2(0, 0);
+    if (!out32)
+      for (int i = 0; i < PRE_TT && t0 + i < p.T_alloc; ++i) *reinterpret_cast<uint2*>(out + (size_t)i * p.D) = make_uint2(0, 0);
     return;
   }
   float off[4] = {0.f, 0.f, 0.f, 0.f};
@@ -114,7 +117,8 @@ __global__ void pre_smooth_kernel(const PreParams p) {
           for (int k = 0; k < 4; ++k) acc[k] += tp * win[w][k];
         }
       }
-      st_bf16x4(out + (size_t)to * p.D, acc[0], acc[1], acc[2], acc[3]);
+      if (out32) *reinterpret_cast<float4*>(out32 + (size_t)to * p.D) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      else st_bf16x4(out + (size_t)to * p.D, acc[0], acc[1], acc[2], acc[3]);
     }
   }
 }

@@ -730,6 +730,24 @@ extern "C" int b2t_greedy_edit(b2t_engine* e, const int* labels, int Smax, const
   return 0;
 }
 
+// ------------------------------------------------------------------------------------ stand-alone smoothing
+extern "C" int b2t_gauss_smooth(const float* x, int B, int T, int D, float std, int size, int mode, float* out, void* stream) {
+  if (!x || !out || B < 1 || T < 1 || D < 4 || D % 4 != 0 || D > 4096) return fail(B2T_ERR_ARG, "bad gauss_smooth arguments");
+  if (mode != 1 && mode != 2) return fail(B2T_ERR_ARG, "mode must be 1 ('same') or 2 ('valid')");
+  PreParams pp;
+  memset(&pp, 0, sizeof(pp));
+  int ntaps = 0;
+  if (gauss_taps(std, size, pp.taps, &ntaps)) return fail(B2T_ERR_UNSUPPORTED, "smoothing kernel has more than 16 taps");
+  const int T_out = mode == 2 ? T - ntaps + 1 : T;
+  if (T_out < 1) return fail(B2T_ERR_ARG, "input shorter than the smoothing kernel");
+  pp.x = x; pp.out = nullptr; pp.out_f32 = out; pp.B = B; pp.Bpad = B; pp.T_in = T; pp.T_alloc = T_out; pp.D = D;
+  pp.ntaps = ntaps; pp.valid = mode == 2;
+  dim3 grid((T_out + PRE_TT - 1) / PRE_TT, B);
+  pre_smooth_kernel<<<grid, D / 4, 0, (cudaStream_t)stream>>>(pp);
+  CK(LAUNCHED());
+  return T_out;
+}
+
 // ------------------------------------------------------------------------------------ GEMM test hook
 extern "C" int b2t_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int a_mn, int b_mn, int out_bf16, const float* bias,
                              void* stream) {
