@@ -83,11 +83,12 @@ def test_ctc_loss_matches_torch(mods):
     il = torch.tensor([40, 33, 25, 40, 12]); tl = torch.tensor([9, 5, 0, 1, 6])
     ours = mods["ctc"].ctc_loss(lp, tg.cuda(), il.cuda(), tl.cuda())
     ours.sum().backward()
-    ref_lp = lp.detach().cpu().requires_grad_()
+    # checker in float64 so that the comparison measures OUR fp32 log-space error, not the sum of two fp32 errors
+    ref_lp = lp.detach().cpu().double().requires_grad_()
     ref = torch.nn.functional.ctc_loss(ref_lp, tg, il, tl, blank=0, reduction="none", zero_infinity=False)
     ref.sum().backward()
     assert util.rel_err(ours.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
-    assert np.abs(lp.grad.cpu().numpy() - ref_lp.grad.numpy()).max() < 1e-5
+    assert np.abs(lp.grad.cpu().numpy() - ref_lp.grad.numpy()).max() < 2e-5       # fp32 alpha/beta over 40 frames, |grad| <= 1
 
 
 def _trainer_args(tmp, n_batches):
