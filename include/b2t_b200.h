@@ -150,6 +150,47 @@ int b2t_debug_set_trace(b2t_engine* e, long long* device_buf);
 /* Number of kernels this library has launched on behalf of the calling process (bench accounting). */
 long long b2t_launch_count(void);
 
+/* ------------------------------------------------------------------ n-gram CTC decoder (WFST token passing on the GPU)
+ * Mirrors the lm_decoder pybind surface (lm_decoder.cc:51-75) with integer status codes instead of glog aborts.
+ * A decoder owns `max_slots` independent utterance slots; slot 0 is what the single-utterance pybind API maps to,
+ * b2t_decoder_decode_batch drives all of them concurrently (one CTA per utterance). */
+typedef struct b2t_decode_options {   /* DecodeOptions(max_active, min_active, beam, lattice_beam, acoustic_scale, */
+  int max_active;                     /*               blank_skip_threshold, length_penalty, nbest)               */
+  int min_active;                     /* brain_speech_decoder.h:22-43                                              */
+  float beam;
+  float lattice_beam;
+  float acoustic_scale;
+  float blank_skip_threshold;
+  float length_penalty;
+  int nbest;
+} b2t_decode_options;
+
+typedef struct b2t_decoder b2t_decoder;
+
+const char* b2t_decoder_last_error(void);
+/* DecodeResource(fst_path, ..., dict_path, ...) + BrainSpeechDecoder(resource, opts) (brain_speech_decoder.h:45-98,110-148).
+ * fst_path: OpenFST binary TLG.fst (vector/standard); words_path: words.txt symbol table.  max_frames bounds the frames
+ * of one utterance; pools are sized from the options and overflow is reported as B2T_ERR_WORKSPACE. */
+b2t_decoder* b2t_decoder_create(const char* fst_path, const char* words_path, const b2t_decode_options* opt, int max_frames,
+                                int max_slots);
+void b2t_decoder_destroy(b2t_decoder* d);
+int b2t_decoder_set_options(b2t_decoder* d, const b2t_decode_options* opt);          /* SetOpt */
+int b2t_decoder_reset(b2t_decoder* d, int slot);                                      /* Reset */
+/* DecodeNumpy: host logits [T][C] (+ optional log_priors [T][C]); log_softmax, minus priors, blank column minus
+ * blank_penalty, then Decode().  After the call the slot's result list holds the partial 1-best. */
+int b2t_decoder_decode_logits(b2t_decoder* d, int slot, const float* logits, const float* log_priors, int T, int C,
+                              float blank_penalty);
+int b2t_decoder_decode_logprobs(b2t_decoder* d, int slot, const float* logp, int T, int C);   /* DecodeNumpyLogProbs */
+int b2t_decoder_finish(b2t_decoder* d, int slot);                                     /* FinishDecoding */
+int b2t_decoder_rescore(b2t_decoder* d, int slot);                                    /* Rescore: not implemented (next row N1) */
+int b2t_decoder_num_results(b2t_decoder* d, int slot);                                /* len(result()) */
+int b2t_decoder_get_result(b2t_decoder* d, int slot, int i, float* ac_score, float* lm_score, char* sentence, int cap);
+/* Batched extension: reset + decode (+ finish) N <= max_slots utterances concurrently; logits host [N][T][C]. */
+int b2t_decoder_decode_batch(b2t_decoder* d, const float* logits, const int* lens, int N, int T, int C, float blank_penalty,
+                             int finish);
+int b2t_decoder_stats(b2t_decoder* d, int slot, int* frames, long long* tokens, long long* links, double* kernel_ms);
+int b2t_decoder_tokens_per_frame(b2t_decoder* d, int slot, int* out, int cap);
+
 /* ------------------------------------------------------------------ test hooks (also used by tests/) */
 /* C[M,N] = A[M,K] * B^T with B given as [N,K] (b_mn == 0) or as [K,N] (b_mn == 1), A as [M,K]
  * (a_mn == 0) or [K,M] (a_mn == 1); bf16 inputs, fp32 or bf16 output, optional fp32 bias[N]. */

@@ -1,0 +1,1041 @@
+// GPU WFST token-passing decoder (the production n-gram CTC search) + host lattice post-processing, exported as
+// b2t_decoder_* in include/b2t_b200.h.
+//
+// Reference path replaced (language_model/runtime/core):
+//   decoder/ctc_wfst_beam_search.cc:70-160      frame feeder, blank-frame skipping, final n-best
+//   kaldi/decoder/lattice-faster-decoder.cc     ProcessEmitting :723-824, ProcessNonemitting :839-909,
+//                                               GetCutoff :651-720, FinalizeDecoding :632-647 (pruning :298-506)
+//   kaldi/decoder/lattice-faster-online-decoder.cc:59-177   back-pointer best path
+//   decoder/brain_speech_decoder.cc:103-137     Decode / UpdateResult;  utils/string.cc:121-146 ProcessBlank
+//   server/x86/python/lm_decoder.cc:14-49       DecodeNumpy / DecodeNumpyLogProbs
+//
+// Design.  One CTA per utterance ("slot"); the whole frame loop runs inside one kernel launch, so a batch of
+// utterances decodes concurrently on as many SMs with no host round trip per frame.  The graph (CSR, 16-byte arcs)
+// is read-only and shared; per slot there is a dense state -> (best cost, winning arc) table updated with 64-bit
+// atomicMin (recombination), a token pool and a link pool.  Per frame:
+//   1. best cost (block min) and the Kaldi cutoff (beam / max_active / min_active; exact k-th smallest by radix select)
+//   2. pass A over emitting arcs of the surviving tokens: exact next-frame best -> next_cutoff
+//   3. pass B: arcs below next_cutoff become forward links; atomicMin recombines tokens per destination state
+//   4. epsilon closure: relax input-epsilon arcs until no token improves, then emit the epsilon links
+//   5. back-pointers = source of the winning link; table entries of the frame are cleared
+// Kaldi tightens next_cutoff while it iterates (order dependent); we use its final value from the start, which
+// yields exactly the tokens that can survive the following frame's beam ("decode parity").
+// The irregular once-per-sentence work (final-cost pruning, best path, n-best) runs on the host from the
+// token/link pools.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b2t_b200.h"
+
+namespace {
+
+thread_local char g_derr[512] = "";
+int dfail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_derr, sizeof(g_derr), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define DCK(call)                                                                                                    \
+  do {                                                                                                               \
+    cudaError_t _e = (call);                                                                                         \
+    if (_e != cudaSuccess) return dfail(B2T_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+
+struct DArc { int il, ol; float w; int next; };
+struct DLink { int src, dst, il, ol; float graph, ac; };   // src/dst are token-pool indices
+
+constexpr unsigned long long EMPTY64 = ~0ull;
+constexpr int DEC_THREADS = 512;
+
+__host__ __device__ inline unsigned int fkey(float x) {
+  unsigned int k;
+#ifdef __CUDA_ARCH__
+  k = __float_as_uint(x);
+#else
+  memcpy(&k, &x, 4);
+#endif
+  return (k & 0x80000000u) ? ~k : (k | 0x80000000u);
+}
+__device__ inline float funkey(unsigned int k) {
+  k = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(k);
+}
+
+struct DecParams {
+  const DArc* arcs;
+  const long long* off;
+  const unsigned char* has_eps;
+  int nstates, start;
+  float beam, beam_delta, acoustic_scale, length_penalty;
+  int max_active, min_active;
+  unsigned long long* best64;   // [slots][nstates]
+  int* tokidx;                  // [slots][nstates]
+  int* tok_state; float* tok_cost; int* tok_bp; unsigned char* tok_dirty;   // [slots][tok_cap]
+  DLink* links;                 // [slots][link_cap]
+  int* frame_tok_off;           // [slots][max_frames + 3]  token-pool offset of frame_plus_one f; [.. + 1] = end
+  int* frame_link_off;          // [slots][max_frames + 3]
+  float* cost_offsets;          // [slots][max_frames]
+  int* counters;                // [slots][4]: 0 ntok, 1 nlink, 2 frames decoded, 3 status
+  const float* logp;            // [slots][max_frames][C]
+  const int* n_fed;             // [slots]
+  const int* slot_ids;          // [gridDim.x] slot handled by each CTA
+  int tok_cap, link_cap, max_frames, C;
+};
+
+__device__ float block_min(float v, float* sred) {
+  for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sred[0];
+  for (int i = 1; i < DEC_THREADS / 32; ++i) r = fminf(r, sred[i]);
+  __syncthreads();
+  return r;
+}
+
+// exact k-th smallest (0-based) of cost[0..n) by 4 radix passes; every thread returns the value
+__device__ float select_kth(const float* cost, int n, int k, unsigned int* hist, unsigned int* sh) {
+  unsigned int prefix = 0, mask = 0;
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int i = threadIdx.x; i < 256; i += DEC_THREADS) hist[i] = 0;
+    __syncthreads();
+    const int shift = pass * 8;
+    for (int i = threadIdx.x; i < n; i += DEC_THREADS) {
+      const unsigned int key = fkey(cost[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int acc = 0, d = 0;
+      for (; d < 256; ++d) {
+        if (acc + hist[d] > (unsigned int)k) break;
+        acc += hist[d];
+      }
+      sh[0] = d; sh[1] = acc;
+    }
+    __syncthreads();
+    prefix |= sh[0] << shift;
+    mask |= 255u << shift;
+    k -= (int)sh[1];
+    __syncthreads();
+  }
+  return funkey(prefix);
+}
+
+// Relax the input-epsilon arcs of the tokens [tb, *ntok) of one frame until no token improves (ProcessNonemitting),
+// then emit the epsilon forward links.  New tokens are appended to the pool.
+__device__ void eps_closure(const DecParams& p, unsigned long long* best64, int* tokidx, int* tok_state, unsigned char* dirty, DLink* links,
+                            int* counters, int tb, float cutoff, int* s_flag) {
+  // mark every token whose state has epsilon arcs
+  for (int i = tb + threadIdx.x; i < counters[0]; i += DEC_THREADS) dirty[i] = p.has_eps[tok_state[i]];
+  __syncthreads();
+  for (int round = 0; round < 64; ++round) {
+    if (threadIdx.x == 0) *s_flag = 0;
+    __syncthreads();
+    const int te = counters[0];
+    __syncthreads();
+    for (int i = tb + threadIdx.x; i < te; i += DEC_THREADS) {
+      if (!dirty[i]) continue;
+      dirty[i] = 0;
+      const int st = tok_state[i];
+      const float cur = funkey((unsigned int)(best64[st] >> 32));
+      if (cur >= cutoff) continue;
+      for (long long a = p.off[st]; a < p.off[st + 1]; ++a) {
+        const DArc arc = p.arcs[a];
+        if (arc.il != 0) continue;
+        const float tot = __fadd_rn(cur, arc.w);
+        if (tot < cutoff) {
+          const unsigned long long key = ((unsigned long long)fkey(tot) << 32) | (unsigned int)a;
+          const unsigned long long old = atomicMin(&best64[arc.next], key);
+          if (old == EMPTY64) {
+            const int slot = atomicAdd(&counters[0], 1);
+            if (slot < p.tok_cap) {
+              tok_state[slot] = arc.next;
+              tokidx[arc.next] = slot;
+              dirty[slot] = p.has_eps[arc.next];
+              if (dirty[slot]) *s_flag = 1;
+            } else {
+              counters[3] = 1;
+            }
+          } else if (key < old && (unsigned int)(old >> 32) != (unsigned int)(key >> 32)) {
+            // improved an existing token: its own epsilon arcs must be relaxed again
+            if (p.has_eps[arc.next]) {
+              // tokidx of a token created in this very round may not be visible yet; the creator marks it dirty itself
+              const int j = tokidx[arc.next];
+              if (j >= tb && j < p.tok_cap) dirty[j] = 1;
+              *s_flag = 1;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (counters[0] > p.tok_cap) { if (threadIdx.x == 0) { counters[0] = p.tok_cap; counters[3] = 1; } }
+    __syncthreads();
+    if (*s_flag == 0) break;
+    // tokens improved while tokidx was not yet visible: re-mark conservatively (cheap, frames are small)
+    for (int i = tb + threadIdx.x; i < counters[0]; i += DEC_THREADS)
+      if (p.has_eps[tok_state[i]]) dirty[i] = 1;
+    __syncthreads();
+  }
+  // epsilon links from the converged costs
+  const int te = counters[0];
+  for (int i = tb + threadIdx.x; i < te; i += DEC_THREADS) {
+    const int st = tok_state[i];
+    if (!p.has_eps[st]) continue;
+    const float cur = funkey((unsigned int)(best64[st] >> 32));
+    if (cur >= cutoff) continue;
+    for (long long a = p.off[st]; a < p.off[st + 1]; ++a) {
+      const DArc arc = p.arcs[a];
+      if (arc.il != 0) continue;
+      const float tot = __fadd_rn(cur, arc.w);
+      if (tot < cutoff) {
+        const int li = atomicAdd(&counters[1], 1);
+        if (li < p.link_cap) links[li] = DLink{i, tokidx[arc.next], 0, arc.ol, arc.w, 0.0f};
+        else counters[3] = 2;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && counters[1] > p.link_cap) counters[1] = p.link_cap;
+  __syncthreads();
+}
+
+// final costs of the frame's tokens, back-pointers (source of the winning link), and table clean-up
+__device__ void finish_frame(const DecParams& p, unsigned long long* best64, int* tokidx, int* tok_state, float* tok_cost, int* tok_bp,
+                             const DLink* links, const int* counters, int tb, int lb) {
+  const int te = counters[0], le = counters[1];
+  for (int i = tb + threadIdx.x; i < te; i += DEC_THREADS) tok_cost[i] = funkey((unsigned int)(best64[tok_state[i]] >> 32));
+  __syncthreads();
+  for (int l = lb + threadIdx.x; l < le; l += DEC_THREADS) {
+    const DLink k = links[l];
+    const float tot = k.il != 0 ? __fadd_rn(__fadd_rn(tok_cost[k.src], k.ac), k.graph) : __fadd_rn(tok_cost[k.src], k.graph);
+    const unsigned long long b = best64[tok_state[k.dst]];
+    if ((unsigned int)(b >> 32) == fkey(tot)) {
+      // the winning arc id disambiguates equal-cost links deterministically
+      const int st = tok_state[k.src];
+      const long long a = (long long)(unsigned int)b;
+      if (a >= p.off[st] && a < p.off[st + 1]) tok_bp[k.dst] = k.src;
+    }
+  }
+  __syncthreads();
+  for (int i = tb + threadIdx.x; i < te; i += DEC_THREADS) {
+    const int st = tok_state[i];
+    best64[st] = EMPTY64;
+    tokidx[st] = -1;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(DEC_THREADS, 1)
+wfst_decode_kernel(const DecParams p) {
+  __shared__ float sred[DEC_THREADS / 32];
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int sh[2];
+  __shared__ int s_flag;
+  __shared__ float s_prep;
+  const int slot = p.slot_ids[blockIdx.x];
+  unsigned long long* best64 = p.best64 + (size_t)slot * p.nstates;
+  int* tokidx = p.tokidx + (size_t)slot * p.nstates;
+  int* tok_state = p.tok_state + (size_t)slot * p.tok_cap;
+  float* tok_cost = p.tok_cost + (size_t)slot * p.tok_cap;
+  int* tok_bp = p.tok_bp + (size_t)slot * p.tok_cap;
+  unsigned char* dirty = p.tok_dirty + (size_t)slot * p.tok_cap;
+  DLink* links = p.links + (size_t)slot * p.link_cap;
+  int* ftok = p.frame_tok_off + (size_t)slot * (p.max_frames + 3);
+  int* flink = p.frame_link_off + (size_t)slot * (p.max_frames + 3);
+  float* coff = p.cost_offsets + (size_t)slot * p.max_frames;
+  int* counters = p.counters + slot * 4;
+  const float* logp = p.logp + (size_t)slot * p.max_frames * p.C;
+  const int n_fed = p.n_fed[slot];
+
+  if (counters[2] < 0) {
+    // ---- InitDecoding (lattice-faster-decoder.cc:58-75): start token + epsilon closure with cutoff = beam
+    if (threadIdx.x == 0) {
+      counters[0] = 1; counters[1] = 0;
+      tok_state[0] = p.start; tok_bp[0] = -1;
+      best64[p.start] = ((unsigned long long)fkey(0.0f) << 32);
+      tokidx[p.start] = 0;
+      ftok[0] = 0; flink[0] = 0;
+    }
+    __syncthreads();
+    eps_closure(p, best64, tokidx, tok_state, dirty, links, counters, 0, p.beam, &s_flag);
+    finish_frame(p, best64, tokidx, tok_state, tok_cost, tok_bp, links, counters, 0, 0);
+    if (threadIdx.x == 0) { tok_bp[0] = -1; ftok[1] = counters[0]; flink[1] = counters[1]; counters[2] = 0; }
+    __syncthreads();
+  }
+
+  for (int frame = counters[2]; frame < n_fed; ++frame) {
+    if (counters[3] != 0) break;
+    const int tb = ftok[frame], te = ftok[frame + 1], n = te - tb;
+    const float* ll = logp + (size_t)frame * p.C;
+    // ---- 1. best cost + cutoff (GetCutoff, :651-720)
+    float v = INFINITY;
+    for (int i = tb + threadIdx.x; i < te; i += DEC_THREADS) v = fminf(v, tok_cost[i]);
+    const float best = block_min(v, sred);
+    float cur_cutoff, adaptive_beam;
+    {
+      const float beam_cutoff = __fadd_rn(best, p.beam);
+      float max_cut = INFINITY, min_cut = INFINITY;
+      if (n > p.max_active) max_cut = select_kth(tok_cost + tb, n, p.max_active, hist, sh);
+      if (max_cut < beam_cutoff) {
+        adaptive_beam = __fadd_rn(__fsub_rn(max_cut, best), p.beam_delta);
+        cur_cutoff = max_cut;
+      } else {
+        if (n > p.min_active) min_cut = p.min_active == 0 ? best : select_kth(tok_cost + tb, n, p.min_active, hist, sh);
+        if (min_cut > beam_cutoff) {
+          adaptive_beam = __fadd_rn(__fsub_rn(min_cut, best), p.beam_delta);
+          cur_cutoff = min_cut;
+        } else {
+          adaptive_beam = p.beam;
+          cur_cutoff = beam_cutoff;
+        }
+      }
+    }
+    const float cost_offset = n > 0 ? -best : 0.0f;
+    // ---- prepass on the best token (first one holding the minimum), its own association of the sum (:756-774)
+    if (threadIdx.x == 0) s_prep = INFINITY;
+    __syncthreads();
+    {
+      int cand = 0x7fffffff;
+      for (int i = tb + threadIdx.x; i < te; i += DEC_THREADS)
+        if (tok_cost[i] == best) { cand = i; break; }
+      for (int o = 16; o; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+      __shared__ int s_cand[DEC_THREADS / 32];
+      if ((threadIdx.x & 31) == 0) s_cand[threadIdx.x >> 5] = cand;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int b = s_cand[0];
+        for (int i = 1; i < DEC_THREADS / 32; ++i) b = min(b, s_cand[i]);
+        float nc = INFINITY;
+        if (b != 0x7fffffff) {
+          const int st = tok_state[b];
+          const float tc = tok_cost[b];
+          for (long long a = p.off[st]; a < p.off[st + 1]; ++a) {
+            const DArc arc = p.arcs[a];
+            if (arc.il == 0) continue;
+            const float like = __fmul_rn(p.acoustic_scale, ll[arc.il - 1]);
+            float nw = __fadd_rn(__fsub_rn(__fadd_rn(arc.w, cost_offset), like), tc);
+            if (st != arc.next) nw = __fadd_rn(nw, p.length_penalty);
+            nc = fminf(nc, __fadd_rn(nw, adaptive_beam));
+          }
+        }
+        s_prep = nc;
+      }
+      __syncthreads();
+    }
+    // ---- 2. pass A: exact best cost of the next frame
+    v = INFINITY;
+    for (int i = tb + threadIdx.x; i < te; i += DEC_THREADS) {
+      const float tc = tok_cost[i];
+      if (!(tc <= cur_cutoff)) continue;
+      const int st = tok_state[i];
+      for (long long a = p.off[st]; a < p.off[st + 1]; ++a) {
+        const DArc arc = p.arcs[a];
+        if (arc.il == 0) continue;
+        const float ac = __fsub_rn(cost_offset, __fmul_rn(p.acoustic_scale, ll[arc.il - 1]));
+        const float g = st != arc.next ? __fadd_rn(arc.w, p.length_penalty) : arc.w;
+        v = fminf(v, __fadd_rn(__fadd_rn(tc, ac), g));
+      }
+    }
+    const float next_best = block_min(v, sred);
+    const float next_cutoff = fminf(s_prep, __fadd_rn(next_best, adaptive_beam));
+    // ---- 3. pass B: links + recombination
+    const int tb_new = counters[0], lb_new = counters[1];
+    __syncthreads();
+    for (int i = tb + threadIdx.x; i < te; i += DEC_THREADS) {
+      const float tc = tok_cost[i];
+      if (!(tc <= cur_cutoff)) continue;
+      const int st = tok_state[i];
+      for (long long a = p.off[st]; a < p.off[st + 1]; ++a) {
+        const DArc arc = p.arcs[a];
+        if (arc.il == 0) continue;
+        const float ac = __fsub_rn(cost_offset, __fmul_rn(p.acoustic_scale, ll[arc.il - 1]));
+        const float g = st != arc.next ? __fadd_rn(arc.w, p.length_penalty) : arc.w;
+        const float tot = __fadd_rn(__fadd_rn(tc, ac), g);
+        if (tot >= next_cutoff) continue;
+        const int li = atomicAdd(&counters[1], 1);
+        if (li >= p.link_cap) { counters[3] = 2; continue; }
+        const unsigned long long key = ((unsigned long long)fkey(tot) << 32) | (unsigned int)a;
+        const unsigned long long old = atomicMin(&best64[arc.next], key);
+        if (old == EMPTY64) {
+          const int ns = atomicAdd(&counters[0], 1);
+          if (ns < p.tok_cap) { tok_state[ns] = arc.next; tokidx[arc.next] = ns; }
+          else counters[3] = 1;
+        }
+        links[li] = DLink{i, arc.next /* state for now */, arc.il, arc.ol, g, ac};
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { counters[0] = min(counters[0], p.tok_cap); counters[1] = min(counters[1], p.link_cap); }
+    __syncthreads();
+    // destination state -> token index
+    for (int l = lb_new + threadIdx.x; l < counters[1]; l += DEC_THREADS) links[l].dst = tokidx[links[l].dst];
+    __syncthreads();
+    // ---- 4. epsilon closure + 5. finish
+    if (threadIdx.x == 0) coff[frame] = cost_offset;
+    eps_closure(p, best64, tokidx, tok_state, dirty, links, counters, tb_new, next_cutoff, &s_flag);
+    // emitting links carry the frame's source costs; epsilon links the converged ones: tok_cost of sources of
+    // emitting links is final already (previous frame)
+    finish_frame(p, best64, tokidx, tok_state, tok_cost, tok_bp, links, counters, tb_new, lb_new);
+    if (threadIdx.x == 0) { ftok[frame + 2] = counters[0]; flink[frame + 2] = counters[1]; counters[2] = frame + 1; }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct HostGraph {
+  int start = -1;
+  std::vector<float> fin;
+  std::vector<long long> off;
+  std::vector<DArc> arcs;
+  std::vector<unsigned char> has_eps;
+};
+
+bool rd(FILE* f, void* p, size_t n) { return fread(p, 1, n, f) == n; }
+bool rd_str(FILE* f, std::string* s) {
+  int32_t n;
+  if (!rd(f, &n, 4) || n < 0 || n > (1 << 20)) return false;
+  s->resize(n);
+  return n == 0 || rd(f, &(*s)[0], n);
+}
+bool skip_symbols(FILE* f) {
+  int32_t magic; std::string name; int64_t avail, size;
+  if (!rd(f, &magic, 4) || !rd_str(f, &name) || !rd(f, &avail, 8) || !rd(f, &size, 8)) return false;
+  for (int64_t i = 0; i < size; ++i) { std::string s; int64_t k; if (!rd_str(f, &s) || !rd(f, &k, 8)) return false; }
+  return true;
+}
+// OpenFST binary "vector" FST with "standard" arcs (what fst::Fst<StdArc>::Read loads for TLG.fst)
+int load_fst(const char* path, HostGraph* g) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return dfail(B2T_ERR_ARG, "cannot open FST %s", path);
+  int32_t magic = 0, version = 0, flags = 0; std::string ft, at; uint64_t props; int64_t start, ns, na;
+  bool ok = rd(f, &magic, 4) && magic == 2125659606 && rd_str(f, &ft) && rd_str(f, &at) && rd(f, &version, 4) && rd(f, &flags, 4) &&
+            rd(f, &props, 8) && rd(f, &start, 8) && rd(f, &ns, 8) && rd(f, &na, 8);
+  if (!ok || ft != "vector" || at != "standard") { fclose(f); return dfail(B2T_ERR_UNSUPPORTED, "%s: only OpenFST vector/standard FSTs are supported", path); }
+  if (((flags & 1) && !skip_symbols(f)) || ((flags & 2) && !skip_symbols(f))) { fclose(f); return dfail(B2T_ERR_ARG, "%s: bad embedded symbol table", path); }
+  g->start = (int)start;
+  g->fin.resize(ns); g->off.resize(ns + 1); g->has_eps.assign(ns, 0);
+  g->arcs.clear(); g->arcs.reserve(na > 0 ? na : 0);
+  for (int64_t s = 0; s < ns; ++s) {
+    float fw; int64_t cnt;
+    if (!rd(f, &fw, 4) || !rd(f, &cnt, 8)) { fclose(f); return dfail(B2T_ERR_ARG, "%s: truncated", path); }
+    g->fin[s] = fw; g->off[s] = (long long)g->arcs.size();
+    for (int64_t a = 0; a < cnt; ++a) {
+      DArc arc;
+      if (!rd(f, &arc, 16)) { fclose(f); return dfail(B2T_ERR_ARG, "%s: truncated", path); }
+      if (arc.il == 0) g->has_eps[s] = 1;
+      g->arcs.push_back(arc);
+    }
+  }
+  g->off[ns] = (long long)g->arcs.size();
+  fclose(f);
+  if (g->arcs.size() >= (1ull << 32)) return dfail(B2T_ERR_UNSUPPORTED, "graphs with >= 2^32 arcs are not supported yet");
+  return 0;
+}
+
+struct HResult { float ac, lm; std::string sentence; };
+
+struct Slot {
+  std::vector<float> fed;           // fed frames [n][C]
+  int n_fed = 0, num_frames = 0, last_best = 0;
+  bool last_blank = false, decoded_any = false, finished = false;
+  std::vector<float> last_frame;
+  std::vector<HResult> results;
+};
+
+}  // namespace
+
+struct b2t_decoder {
+  HostGraph g;
+  std::vector<std::string> words;
+  b2t_decode_options opt;
+  int max_frames, max_slots, C = 0;
+  int tok_cap, link_cap;
+  // device
+  DArc* d_arcs = nullptr; long long* d_off = nullptr; unsigned char* d_has_eps = nullptr;
+  unsigned long long* d_best = nullptr; int* d_tokidx = nullptr;
+  int *d_tok_state = nullptr, *d_tok_bp = nullptr; float* d_tok_cost = nullptr; unsigned char* d_dirty = nullptr;
+  DLink* d_links = nullptr;
+  int *d_ftok = nullptr, *d_flink = nullptr, *d_counters = nullptr, *d_nfed = nullptr, *d_slot_ids = nullptr;
+  float *d_coff = nullptr, *d_logp = nullptr;
+  std::vector<Slot> slots;
+  cudaStream_t stream = nullptr;
+  double last_kernel_ms = 0.0;
+};
+
+namespace {
+
+int read_words(const char* path, std::vector<std::string>* w) {
+  FILE* f = fopen(path, "r");
+  if (!f) return dfail(B2T_ERR_ARG, "cannot open symbol table %s", path);
+  char buf[1024]; int id;
+  while (fscanf(f, "%1023s %d", buf, &id) == 2) {
+    if (id < 0) continue;
+    if ((size_t)id >= w->size()) w->resize(id + 1);
+    (*w)[id] = buf;
+  }
+  fclose(f);
+  return 0;
+}
+
+std::string process_blank(const std::string& s) {   // utils/string.cc:121-146
+  std::string r;
+  for (char c : s) {
+    if (c != ' ') r.push_back(c);
+    else if (!r.empty() && r.back() != ' ') r.push_back(' ');
+  }
+  if (!r.empty() && r.back() == ' ') r.pop_back();
+  for (char& c : r) c = (char)tolower((unsigned char)c);
+  return r;
+}
+
+void push_result(b2t_decoder* d, Slot& s, const std::vector<int>& w, float graph, float acoustic) {   // brain_speech_decoder.cc:113-137
+  HResult r;
+  r.lm = -graph;
+  r.ac = -acoustic / d->opt.acoustic_scale;
+  for (int id : w) r.sentence += ' ' + (id >= 0 && id < (int)d->words.size() ? d->words[id] : std::string("<unk>"));
+  r.sentence = process_blank(r.sentence);
+  s.results.push_back(r);
+}
+
+// ---- host view of one slot's token lattice
+struct Lattice {
+  int F = 0;                               // number of frame_plus_one levels with tokens (frames decoded + 1)
+  std::vector<int> ftok, flink;            // offsets per level (size F + 1)
+  std::vector<int> state, bp; std::vector<float> cost;
+  std::vector<DLink> links;
+  std::vector<float> coff;
+  std::vector<int> lbeg;                   // links sorted by src: lbeg[tok] .. lbeg[tok+1]
+  std::vector<int> frame_of;
+};
+
+int fetch_lattice(b2t_decoder* d, int slot, Lattice* L) {
+  int counters[4];
+  DCK(cudaMemcpyAsync(counters, d->d_counters + slot * 4, sizeof(counters), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaStreamSynchronize(d->stream));
+  if (counters[3] == 1) return dfail(B2T_ERR_WORKSPACE, "decoder token pool overflow (capacity %d): raise max_active-derived capacity or lower beam", d->tok_cap);
+  if (counters[3] == 2) return dfail(B2T_ERR_WORKSPACE, "decoder link pool overflow (capacity %d)", d->link_cap);
+  const int nf = counters[2], nt = counters[0], nl = counters[1];
+  L->F = nf + 1;
+  L->ftok.resize(L->F + 1); L->flink.resize(L->F + 1);
+  DCK(cudaMemcpyAsync(L->ftok.data(), d->d_ftok + (size_t)slot * (d->max_frames + 3), (L->F + 1) * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaMemcpyAsync(L->flink.data(), d->d_flink + (size_t)slot * (d->max_frames + 3), (L->F + 1) * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  L->state.resize(nt); L->bp.resize(nt); L->cost.resize(nt); L->links.resize(nl); L->coff.resize(nf);
+  DCK(cudaMemcpyAsync(L->state.data(), d->d_tok_state + (size_t)slot * d->tok_cap, nt * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaMemcpyAsync(L->bp.data(), d->d_tok_bp + (size_t)slot * d->tok_cap, nt * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaMemcpyAsync(L->cost.data(), d->d_tok_cost + (size_t)slot * d->tok_cap, nt * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+  if (nl) DCK(cudaMemcpyAsync(L->links.data(), d->d_links + (size_t)slot * d->link_cap, nl * sizeof(DLink), cudaMemcpyDeviceToHost, d->stream));
+  if (nf) DCK(cudaMemcpyAsync(L->coff.data(), d->d_coff + (size_t)slot * d->max_frames, nf * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaStreamSynchronize(d->stream));
+  // order links by source token (stable) and index them
+  std::stable_sort(L->links.begin(), L->links.end(), [](const DLink& a, const DLink& b) { return a.src < b.src; });
+  L->lbeg.assign(nt + 1, 0);
+  for (const DLink& k : L->links) L->lbeg[k.src + 1]++;
+  for (int i = 0; i < nt; ++i) L->lbeg[i + 1] += L->lbeg[i];
+  L->frame_of.resize(nt);
+  for (int f = 0; f < L->F; ++f)
+    for (int i = L->ftok[f]; i < L->ftok[f + 1]; ++i) L->frame_of[i] = f;
+  return 0;
+}
+
+inline float link_ac(const Lattice& L, const DLink& k) {   // acoustic cost with the per-frame offset removed (GetRawLattice :164-171)
+  return k.il != 0 ? k.ac - L.coff[L.frame_of[k.src]] : k.ac;
+}
+
+// back-pointer best path (lattice-faster-online-decoder.cc:59-177)
+bool best_path(const b2t_decoder* d, const Lattice& L, bool use_final, std::vector<int>* words, float* graph, float* acoustic) {
+  words->clear();
+  const int fb = L.ftok[L.F - 1], fe = L.ftok[L.F];
+  bool any_final = false;
+  if (use_final)
+    for (int i = fb; i < fe; ++i)
+      if (d->g.fin[L.state[i]] != INFINITY) any_final = true;
+  float best_cost = INFINITY, best_final = 0.0f;
+  int best = -1;
+  // the reference walks the frame's token list, which is in reverse creation order: the LAST created token among
+  // equal costs is seen first and wins; iterate descending to reproduce that
+  for (int i = fe - 1; i >= fb; --i) {
+    float cost = L.cost[i], fc = 0.0f;
+    if (use_final && any_final) {
+      fc = d->g.fin[L.state[i]];
+      cost = fc != INFINITY ? cost + fc : INFINITY;
+    }
+    if (cost < best_cost) { best_cost = cost; best = i; best_final = fc; }
+  }
+  if (best < 0) return false;
+  std::vector<std::pair<float, float>> ws;
+  std::vector<int> rw;
+  int tok = best;
+  while (tok >= 0) {
+    const int b = L.bp[tok];
+    float gc = 0.0f, ac = 0.0f;
+    int ol = 0;
+    if (b >= 0) {
+      float best_link = INFINITY;
+      for (int l = L.lbeg[b]; l < L.lbeg[b + 1]; ++l) {
+        const DLink& k = L.links[l];
+        if (k.dst != tok) continue;
+        const float c = k.graph + k.ac;
+        if (c < best_link) { best_link = c; gc = k.graph; ac = link_ac(L, k); ol = k.ol; }
+      }
+      if (best_link == INFINITY) return false;
+    }
+    ws.push_back({gc, ac});
+    if (ol != 0) rw.push_back(ol);
+    tok = b;
+  }
+  float tg = 0.0f, ta = 0.0f;
+  for (int i = (int)ws.size() - 1; i >= 0; --i) { tg = tg + ws[i].first; ta = ta + ws[i].second; }
+  tg = tg + best_final;
+  std::reverse(rw.begin(), rw.end());
+  *words = rw; *graph = tg; *acoustic = ta;
+  return true;
+}
+
+// FinalizeDecoding (:632-647): exact backward pruning with final costs.  Returns per-token extra cost (inf = pruned)
+// and a keep flag per link.
+void prune_final(const b2t_decoder* d, const Lattice& L, std::vector<float>* extra_out, std::vector<char>* keep_out) {
+  const int nt = (int)L.state.size();
+  const float lb = d->opt.lattice_beam;
+  std::vector<float> extra(nt, 0.0f);
+  std::vector<char> keep(L.links.size(), 1);
+  const int fb = L.ftok[L.F - 1], fe = L.ftok[L.F];
+  bool any_final = false;
+  float best_final = INFINITY, best_plain = INFINITY;
+  for (int i = fb; i < fe; ++i) {
+    const float fc = d->g.fin[L.state[i]];
+    if (fc != INFINITY) any_final = true;
+    best_plain = std::min(best_plain, L.cost[i]);
+    best_final = std::min(best_final, L.cost[i] + fc);
+  }
+  const float final_best = best_final != INFINITY ? best_final : best_plain;
+  auto sweep = [&](int f, bool last) {
+    bool changed = true;
+    while (changed) {
+      changed = false;
+      for (int i = L.ftok[f + 1] - 1; i >= L.ftok[f]; --i) {     // the reference walks tokens in reverse creation order
+        float te;
+        if (last) {
+          const float fc = any_final ? d->g.fin[L.state[i]] : 0.0f;
+          te = L.cost[i] + fc - final_best;
+        } else te = INFINITY;
+        for (int l = L.lbeg[i]; l < L.lbeg[i + 1]; ++l) {
+          if (!keep[l]) continue;
+          const DLink& k = L.links[l];
+          float lec = extra[k.dst] + ((L.cost[i] + k.ac + k.graph) - L.cost[k.dst]);
+          if (lec > lb) keep[l] = 0;
+          else {
+            if (lec < 0.0f) lec = 0.0f;
+            if (lec < te) te = lec;
+          }
+        }
+        if (last && te > lb) te = INFINITY;
+        bool diff;
+        if (last) {      // !ApproxEqual(old, new, 1e-5)   (kaldi-math.h)
+          const float o = extra[i], df = fabsf(o - te);
+          diff = !(o == te || (df != INFINITY && df == df && df <= 1.0e-05f * (fabsf(o) + fabsf(te))));
+        } else {         // fabs(new - old) > delta with delta == 0 (NaN from inf - inf compares false)
+          diff = fabsf(te - extra[i]) > 0.0f;
+        }
+        if (diff) changed = true;
+        extra[i] = te;
+      }
+    }
+  };
+  sweep(L.F - 1, true);
+  for (int f = L.F - 2; f >= 0; --f) sweep(f, false);
+  *extra_out = extra; *keep_out = keep;
+}
+
+// n cheapest distinct word sequences over the pruned lattice: per-token top-K distinct
+// word-sequence hypotheses in topological order; exact for K >= n.
+struct WordTrie {
+  std::vector<std::pair<int, int>> node{{-1, 0}};
+  std::unordered_map<unsigned long long, int> idx;
+  int extend(int n, int w) {
+    const unsigned long long key = ((unsigned long long)(unsigned int)n << 32) | (unsigned int)w;
+    auto it = idx.find(key);
+    if (it != idx.end()) return it->second;
+    node.push_back({n, w});
+    return idx[key] = (int)node.size() - 1;
+  }
+  std::vector<int> words(int n) const {
+    std::vector<int> w;
+    for (; n > 0; n = node[n].first) w.push_back(node[n].second);
+    std::reverse(w.begin(), w.end());
+    return w;
+  }
+};
+struct Hyp { int seq; float g, a; };
+inline bool hyp_better(const Hyp& x, const Hyp& y) {
+  const float fx = x.g + x.a, fy = y.g + y.a;
+  if (fx != fy) return fx < fy;
+  return x.g < y.g;
+}
+
+void nbest_from_lattice(b2t_decoder* d, Slot& s, const Lattice& L, const std::vector<float>& extra, const std::vector<char>& keep) {
+  const int nt = (int)L.state.size();
+  const int K = std::max(1, d->opt.nbest);
+  // topological order inside each level with respect to epsilon links (Kahn)
+  std::vector<int> order; order.reserve(nt);
+  std::vector<int> indeg(nt, 0);
+  for (size_t l = 0; l < L.links.size(); ++l)
+    if (keep[l] && L.links[l].il == 0 && extra[L.links[l].src] != INFINITY && extra[L.links[l].dst] != INFINITY) indeg[L.links[l].dst]++;
+  for (int f = 0; f < L.F; ++f) {
+    const size_t first = order.size();
+    for (int i = L.ftok[f]; i < L.ftok[f + 1]; ++i)
+      if (extra[i] != INFINITY && indeg[i] == 0) order.push_back(i);
+    for (size_t q = first; q < order.size(); ++q) {
+      const int i = order[q];
+      for (int l = L.lbeg[i]; l < L.lbeg[i + 1]; ++l)
+        if (keep[l] && L.links[l].il == 0 && extra[L.links[l].dst] != INFINITY && --indeg[L.links[l].dst] == 0) order.push_back(L.links[l].dst);
+    }
+  }
+  bool any_final = false;
+  for (int i = L.ftok[L.F - 1]; i < L.ftok[L.F]; ++i)
+    if (d->g.fin[L.state[i]] != INFINITY) any_final = true;
+  WordTrie trie;
+  std::vector<std::vector<Hyp>> hyps(nt);
+  hyps[0].push_back({0, 0.0f, 0.0f});
+  std::vector<Hyp> finals;
+  auto merge = [&](std::vector<Hyp>& v, const Hyp& h) {
+    for (Hyp& e : v)
+      if (e.seq == h.seq) { if (hyp_better(h, e)) e = h; return; }
+    v.push_back(h);
+  };
+  auto trim = [&](std::vector<Hyp>& v) {
+    if ((int)v.size() > K) {
+      std::partial_sort(v.begin(), v.begin() + K, v.end(), hyp_better);
+      v.resize(K);
+    }
+  };
+  for (int i : order) {
+    std::vector<Hyp>& hv = hyps[i];
+    if (hv.empty()) continue;
+    trim(hv);
+    if (L.frame_of[i] == L.F - 1) {
+      const float fc = any_final ? d->g.fin[L.state[i]] : 0.0f;
+      if (fc != INFINITY)
+        for (const Hyp& h : hv) merge(finals, Hyp{h.seq, h.g + fc, h.a});
+    }
+    for (int l = L.lbeg[i]; l < L.lbeg[i + 1]; ++l) {
+      if (!keep[l]) continue;
+      const DLink& k = L.links[l];
+      if (extra[k.dst] == INFINITY) continue;
+      const float ac = link_ac(L, k);
+      for (const Hyp& h : hv) merge(hyps[k.dst], Hyp{k.ol != 0 ? trie.extend(h.seq, k.ol) : h.seq, h.g + k.graph, h.a + ac});
+    }
+    std::vector<Hyp>().swap(hv);
+  }
+  std::stable_sort(finals.begin(), finals.end(), hyp_better);
+  if (!finals.empty()) {
+    const float limit = finals[0].g + finals[0].a + d->opt.lattice_beam + 1e-4f;
+    for (size_t i = 0; i < finals.size() && (int)i < K; ++i) {
+      if (finals[i].g + finals[i].a > limit) break;
+      push_result(d, s, trie.words(finals[i].seq), finals[i].g, finals[i].a);
+    }
+  }
+}
+
+void log_softmax_row(const float* x, int C, float* out) {
+  float m = x[0];
+  for (int c = 1; c < C; ++c) m = std::max(m, x[c]);
+  double s = 0.0;
+  for (int c = 0; c < C; ++c) s += std::exp((double)(x[c] - m));
+  const float ls = (float)std::log(s);
+  for (int c = 0; c < C; ++c) out[c] = (x[c] - m) - ls;
+}
+
+// CtcWfstBeamSearch::Search frame selection (ctc_wfst_beam_search.cc:70-111): which frames are fed to the search
+int feed_frames(b2t_decoder* d, Slot& s, const float* logp, int T, int C) {
+  for (int i = 0; i < T; ++i) {
+    const float* row = logp + (size_t)i * C;
+    const float blank_score = std::exp(row[0]);
+    if (blank_score > d->opt.blank_skip_threshold) {
+      s.last_blank = true;
+      s.last_frame.assign(row, row + C);
+    } else {
+      int cur_best = 0;
+      for (int c = 1; c < C; ++c)
+        if (row[c] > row[cur_best]) cur_best = c;
+      if (cur_best != 0 && s.last_blank && cur_best == s.last_best) {
+        if (s.n_fed >= d->max_frames) return dfail(B2T_ERR_ARG, "utterance longer than the decoder's max_frames (%d)", d->max_frames);
+        s.fed.insert(s.fed.end(), s.last_frame.begin(), s.last_frame.end());
+        s.n_fed++;
+      }
+      s.last_best = cur_best;
+      if (s.n_fed >= d->max_frames) return dfail(B2T_ERR_ARG, "utterance longer than the decoder's max_frames (%d)", d->max_frames);
+      s.fed.insert(s.fed.end(), row, row + C);
+      s.n_fed++;
+      s.last_blank = false;
+    }
+    s.num_frames++;
+  }
+  return 0;
+}
+
+int launch_slots(b2t_decoder* d, const std::vector<int>& ids) {
+  if (ids.empty()) return 0;
+  std::vector<int> nfed(d->max_slots, 0);
+  for (int i = 0; i < d->max_slots; ++i) nfed[i] = d->slots[i].n_fed;
+  DCK(cudaMemcpyAsync(d->d_nfed, nfed.data(), d->max_slots * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  DCK(cudaMemcpyAsync(d->d_slot_ids, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  DecParams p;
+  p.arcs = d->d_arcs; p.off = d->d_off; p.has_eps = d->d_has_eps; p.nstates = (int)d->g.fin.size(); p.start = d->g.start;
+  p.beam = d->opt.beam; p.beam_delta = 0.5f; p.acoustic_scale = d->opt.acoustic_scale; p.length_penalty = d->opt.length_penalty;
+  p.max_active = d->opt.max_active; p.min_active = d->opt.min_active;
+  p.best64 = d->d_best; p.tokidx = d->d_tokidx; p.tok_state = d->d_tok_state; p.tok_cost = d->d_tok_cost; p.tok_bp = d->d_tok_bp;
+  p.tok_dirty = d->d_dirty; p.links = d->d_links; p.frame_tok_off = d->d_ftok; p.frame_link_off = d->d_flink; p.cost_offsets = d->d_coff;
+  p.counters = d->d_counters; p.logp = d->d_logp; p.n_fed = d->d_nfed; p.slot_ids = d->d_slot_ids;
+  p.tok_cap = d->tok_cap; p.link_cap = d->link_cap; p.max_frames = d->max_frames; p.C = d->C;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, d->stream);
+  wfst_decode_kernel<<<(int)ids.size(), DEC_THREADS, 0, d->stream>>>(p);
+  cudaEventRecord(e1, d->stream);
+  DCK(cudaGetLastError());
+  DCK(cudaStreamSynchronize(d->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  d->last_kernel_ms = ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+int upload_fed(b2t_decoder* d, int slot, int from_frame) {
+  Slot& s = d->slots[slot];
+  if (s.n_fed > from_frame)
+    DCK(cudaMemcpyAsync(d->d_logp + ((size_t)slot * d->max_frames + from_frame) * d->C, s.fed.data() + (size_t)from_frame * d->C,
+                        (size_t)(s.n_fed - from_frame) * d->C * sizeof(float), cudaMemcpyHostToDevice, d->stream));
+  return 0;
+}
+
+int reset_slot(b2t_decoder* d, int slot) {
+  Slot& s = d->slots[slot];
+  s = Slot();
+  const int init[4] = {0, 0, -1, 0};
+  DCK(cudaMemcpyAsync(d->d_counters + slot * 4, init, sizeof(init), cudaMemcpyHostToDevice, d->stream));
+  return 0;
+}
+
+int partial_result(b2t_decoder* d, int slot) {   // ctc_wfst_beam_search.cc:112-120: 1-best without final costs after every chunk
+  Slot& s = d->slots[slot];
+  s.results.clear();
+  if (s.n_fed == 0) return 0;
+  Lattice L;
+  int rc = fetch_lattice(d, slot, &L);
+  if (rc) return rc;
+  std::vector<int> w; float g, a;
+  if (best_path(d, L, false, &w, &g, &a)) push_result(d, s, w, g, a);
+  return 0;
+}
+
+int finish_slot(b2t_decoder* d, int slot) {      // ctc_wfst_beam_search.cc:123-160
+  Slot& s = d->slots[slot];
+  s.results.clear();
+  s.finished = true;
+  if (s.n_fed == 0) return 0;
+  Lattice L;
+  int rc = fetch_lattice(d, slot, &L);
+  if (rc) return rc;
+  if (d->opt.nbest == 1) {
+    std::vector<int> w; float g, a;
+    if (best_path(d, L, true, &w, &g, &a)) push_result(d, s, w, g, a);
+  } else {
+    std::vector<float> extra; std::vector<char> keep;
+    prune_final(d, L, &extra, &keep);
+    nbest_from_lattice(d, s, L, extra, keep);
+  }
+  return 0;
+}
+
+int ensure_C(b2t_decoder* d, int C) {
+  if (d->C == 0) {
+    d->C = C;
+    if (cudaMalloc(&d->d_logp, (size_t)d->max_slots * d->max_frames * C * sizeof(float)) != cudaSuccess) return dfail(B2T_ERR_CUDA, "cudaMalloc(logp) failed");
+  } else if (d->C != C) return dfail(B2T_ERR_ARG, "class count changed from %d to %d", d->C, C);
+  int max_il = 0;
+  for (const DArc& a : d->g.arcs) max_il = std::max(max_il, a.il);
+  if (max_il > C) return dfail(B2T_ERR_ARG, "graph has input label %d but the posteriors have only %d classes", max_il, C);
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* b2t_decoder_last_error(void) { return g_derr; }
+
+b2t_decoder* b2t_decoder_create(const char* fst_path, const char* words_path, const b2t_decode_options* opt, int max_frames, int max_slots) {
+  if (!fst_path || !words_path || !opt || max_frames < 1 || max_slots < 1) { dfail(B2T_ERR_ARG, "bad arguments"); return nullptr; }
+  if (fst_path[0] == '\0') { dfail(B2T_ERR_UNSUPPORTED, "empty fst_path selects the LM-free CtcPrefixBeamSearch; use b2t_prefix_beam_search"); return nullptr; }
+  if (!(opt->beam > 0.0f && opt->max_active > 1 && opt->lattice_beam > 0.0f && opt->min_active <= opt->max_active)) {
+    dfail(B2T_ERR_ARG, "invalid decode options (LatticeFasterDecoderConfig::Check)"); return nullptr;
+  }
+  b2t_decoder* d = new b2t_decoder();
+  if (load_fst(fst_path, &d->g) || read_words(words_path, &d->words)) { delete d; return nullptr; }
+  d->opt = *opt; d->max_frames = max_frames; d->max_slots = max_slots;
+  // pools: a frame holds at most ~max_active expanded tokens times the out-degree; sized generously and checked
+  const long long per_frame = std::min<long long>((long long)std::max(opt->max_active, 1000) * 6, 200000);
+  d->tok_cap = (int)std::min<long long>(per_frame * (max_frames + 1), 24000000);
+  d->link_cap = (int)std::min<long long>((long long)d->tok_cap * 3, 60000000);
+  const size_t ns = d->g.fin.size(), na = d->g.arcs.size();
+  bool ok = cudaStreamCreate(&d->stream) == cudaSuccess;
+  ok = ok && cudaMalloc(&d->d_arcs, std::max<size_t>(na, 1) * sizeof(DArc)) == cudaSuccess && cudaMalloc(&d->d_off, (ns + 1) * sizeof(long long)) == cudaSuccess &&
+       cudaMalloc(&d->d_has_eps, ns) == cudaSuccess && cudaMalloc(&d->d_best, (size_t)max_slots * ns * 8) == cudaSuccess &&
+       cudaMalloc(&d->d_tokidx, (size_t)max_slots * ns * 4) == cudaSuccess && cudaMalloc(&d->d_tok_state, (size_t)max_slots * d->tok_cap * 4) == cudaSuccess &&
+       cudaMalloc(&d->d_tok_cost, (size_t)max_slots * d->tok_cap * 4) == cudaSuccess && cudaMalloc(&d->d_tok_bp, (size_t)max_slots * d->tok_cap * 4) == cudaSuccess &&
+       cudaMalloc(&d->d_dirty, (size_t)max_slots * d->tok_cap) == cudaSuccess && cudaMalloc(&d->d_links, (size_t)max_slots * d->link_cap * sizeof(DLink)) == cudaSuccess &&
+       cudaMalloc(&d->d_ftok, (size_t)max_slots * (max_frames + 3) * 4) == cudaSuccess && cudaMalloc(&d->d_flink, (size_t)max_slots * (max_frames + 3) * 4) == cudaSuccess &&
+       cudaMalloc(&d->d_coff, (size_t)max_slots * max_frames * 4) == cudaSuccess && cudaMalloc(&d->d_counters, (size_t)max_slots * 16) == cudaSuccess &&
+       cudaMalloc(&d->d_nfed, (size_t)max_slots * 4) == cudaSuccess && cudaMalloc(&d->d_slot_ids, (size_t)max_slots * 4) == cudaSuccess;
+  if (!ok) { dfail(B2T_ERR_CUDA, "decoder allocation failed: %s (states %zu, slots %d, token pool %d)", cudaGetErrorString(cudaGetLastError()), ns, max_slots, d->tok_cap); b2t_decoder_destroy(d); return nullptr; }
+  cudaMemcpy(d->d_arcs, d->g.arcs.data(), na * sizeof(DArc), cudaMemcpyHostToDevice);
+  cudaMemcpy(d->d_off, d->g.off.data(), (ns + 1) * sizeof(long long), cudaMemcpyHostToDevice);
+  cudaMemcpy(d->d_has_eps, d->g.has_eps.data(), ns, cudaMemcpyHostToDevice);
+  cudaMemset(d->d_best, 0xff, (size_t)max_slots * ns * 8);
+  cudaMemset(d->d_tokidx, 0xff, (size_t)max_slots * ns * 4);
+  d->slots.resize(max_slots);
+  for (int i = 0; i < max_slots; ++i) reset_slot(d, i);
+  cudaStreamSynchronize(d->stream);
+  return d;
+}
+
+void b2t_decoder_destroy(b2t_decoder* d) {
+  if (!d) return;
+  void* ptrs[] = {d->d_arcs, d->d_off, d->d_has_eps, d->d_best, d->d_tokidx, d->d_tok_state, d->d_tok_cost, d->d_tok_bp, d->d_dirty, d->d_links,
+                  d->d_ftok, d->d_flink, d->d_coff, d->d_counters, d->d_nfed, d->d_slot_ids, d->d_logp};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+int b2t_decoder_set_options(b2t_decoder* d, const b2t_decode_options* opt) {
+  if (!d || !opt) return dfail(B2T_ERR_ARG, "null argument");
+  // NOTE: the reference's SetOpt only reaches acoustic_scale / nbest / blank_skip (the Kaldi config copy is never
+  // updated).  Here every field takes effect from the next Reset().
+  d->opt = *opt;
+  return 0;
+}
+
+int b2t_decoder_reset(b2t_decoder* d, int slot) {
+  if (!d || slot < 0 || slot >= d->max_slots) return dfail(B2T_ERR_ARG, "bad slot");
+  // the state table is clean after every frame, so only the counters need re-arming
+  return reset_slot(d, slot);
+}
+
+int b2t_decoder_decode_logprobs(b2t_decoder* d, int slot, const float* logp, int T, int C) {
+  if (!d || slot < 0 || slot >= d->max_slots || (!logp && T > 0) || T < 0 || C < 1) return dfail(B2T_ERR_ARG, "bad arguments");
+  int rc = ensure_C(d, C);
+  if (rc) return rc;
+  Slot& s = d->slots[slot];
+  if (s.finished) return dfail(B2T_ERR_STATE, "Decode() after FinishDecoding(): call Reset() first");
+  if (T == 0) return 0;
+  const int before = s.n_fed;
+  if ((rc = feed_frames(d, s, logp, T, C))) return rc;
+  if ((rc = upload_fed(d, slot, before))) return rc;
+  if ((rc = launch_slots(d, std::vector<int>{slot}))) return rc;
+  return partial_result(d, slot);
+}
+
+int b2t_decoder_decode_logits(b2t_decoder* d, int slot, const float* logits, const float* log_priors, int T, int C, float blank_penalty) {
+  if (!logits && T > 0) return dfail(B2T_ERR_ARG, "null logits");
+  std::vector<float> lp((size_t)T * C);
+  for (int t = 0; t < T; ++t) {                     // lm_decoder.cc:30-36
+    log_softmax_row(logits + (size_t)t * C, C, &lp[(size_t)t * C]);
+    if (log_priors)
+      for (int c = 0; c < C; ++c) lp[(size_t)t * C + c] -= log_priors[(size_t)t * C + c];
+    lp[(size_t)t * C] -= blank_penalty;
+  }
+  return b2t_decoder_decode_logprobs(d, slot, lp.data(), T, C);
+}
+
+int b2t_decoder_finish(b2t_decoder* d, int slot) {
+  if (!d || slot < 0 || slot >= d->max_slots) return dfail(B2T_ERR_ARG, "bad slot");
+  return finish_slot(d, slot);
+}
+
+int b2t_decoder_rescore(b2t_decoder* d, int slot) {
+  (void)d; (void)slot;
+  return dfail(B2T_ERR_UNSUPPORTED, "Rescore() (lattice LM rescoring with G.fst / G_no_prune.fst) is the 'next' row N1 and is not implemented yet");
+}
+
+int b2t_decoder_num_results(b2t_decoder* d, int slot) {
+  if (!d || slot < 0 || slot >= d->max_slots) return dfail(B2T_ERR_ARG, "bad slot");
+  return (int)d->slots[slot].results.size();
+}
+
+int b2t_decoder_get_result(b2t_decoder* d, int slot, int i, float* ac_score, float* lm_score, char* sentence, int cap) {
+  if (!d || slot < 0 || slot >= d->max_slots) return dfail(B2T_ERR_ARG, "bad slot");
+  const Slot& s = d->slots[slot];
+  if (i < 0 || i >= (int)s.results.size()) return dfail(B2T_ERR_ARG, "result index out of range");
+  if (ac_score) *ac_score = s.results[i].ac;
+  if (lm_score) *lm_score = s.results[i].lm;
+  if (sentence && cap > 0) snprintf(sentence, cap, "%s", s.results[i].sentence.c_str());
+  return (int)s.results[i].sentence.size();
+}
+
+// Batched extension: reset + decode + finish N utterances concurrently (one CTA each).  logits: host [N][T][C];
+// lens[n] <= T frames are used.  Results are read per slot n afterwards.
+int b2t_decoder_decode_batch(b2t_decoder* d, const float* logits, const int* lens, int N, int T, int C, float blank_penalty, int finish) {
+  if (!d || !logits || !lens || N < 1 || N > d->max_slots) return dfail(B2T_ERR_ARG, "bad batch arguments (N must be <= max_slots)");
+  int rc = ensure_C(d, C);
+  if (rc) return rc;
+  std::vector<int> ids;
+  std::vector<float> lp;
+  for (int n = 0; n < N; ++n) {
+    if ((rc = reset_slot(d, n))) return rc;
+    const int Tn = std::min(std::max(lens[n], 0), T);
+    lp.resize((size_t)Tn * C);
+    for (int t = 0; t < Tn; ++t) {
+      log_softmax_row(logits + ((size_t)n * T + t) * C, C, &lp[(size_t)t * C]);
+      lp[(size_t)t * C] -= blank_penalty;
+    }
+    if ((rc = feed_frames(d, d->slots[n], lp.data(), Tn, C))) return rc;
+    if ((rc = upload_fed(d, n, 0))) return rc;
+    ids.push_back(n);
+  }
+  if ((rc = launch_slots(d, ids))) return rc;
+  if (finish)
+    for (int n = 0; n < N; ++n)
+      if ((rc = finish_slot(d, n))) return rc;
+  return 0;
+}
+
+int b2t_decoder_stats(b2t_decoder* d, int slot, int* frames, long long* tokens, long long* links, double* kernel_ms) {
+  if (!d || slot < 0 || slot >= d->max_slots) return dfail(B2T_ERR_ARG, "bad slot");
+  int c[4];
+  if (cudaMemcpy(c, d->d_counters + slot * 4, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return dfail(B2T_ERR_CUDA, "stats copy failed");
+  if (frames) *frames = c[2];
+  if (tokens) *tokens = c[0];
+  if (links) *links = c[1];
+  if (kernel_ms) *kernel_ms = d->last_kernel_ms;
+  return 0;
+}
+
+int b2t_decoder_tokens_per_frame(b2t_decoder* d, int slot, int* out, int cap) {
+  if (!d || slot < 0 || slot >= d->max_slots || !out) return dfail(B2T_ERR_ARG, "bad arguments");
+  int c[4];
+  if (cudaMemcpy(c, d->d_counters + slot * 4, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return dfail(B2T_ERR_CUDA, "copy failed");
+  const int nf = std::max(c[2], 0);
+  std::vector<int> ft(nf + 2);
+  if (cudaMemcpy(ft.data(), d->d_ftok + (size_t)slot * (d->max_frames + 3), (nf + 2) * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return dfail(B2T_ERR_CUDA, "copy failed");
+  for (int f = 0; f < nf && f < cap; ++f) out[f] = ft[f + 2] - ft[f + 1];
+  return nf;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+"""GPU parity tests of the WFST decoder (lm_decoder drop-in) against the C++ oracle on generated TLG graphs.
+
+Parity definition (SURVEY.md section 7 / DESIGN.md): integer outputs -- the 1-best word sequence, the n-best SET of
+word sequences -- identical; scores within 1e-3; per-frame token counts identical when max_active is not binding
+(when it is, Kaldi's result depends on hash iteration order and only the 1-best / scores are compared)."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import decoder_util as D
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import make_toy_tlg as TLG  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def LM(pkg):
+    import b2t_pkg
+    return b2t_pkg.submodule("lm_decoder")
+
+
+@pytest.fixture(scope="module")
+def graph(tmp_path_factory):
+    d = tmp_path_factory.mktemp("tlg")
+    fst, words = str(d / "TLG.fst"), str(d / "words.txt")
+    info = TLG.build(fst, words, n_words=300, seed=2)
+    return fst, words, info
+
+
+def _ours(LM, fst, words, opts, **kw):
+    return LM.BrainSpeechDecoder(LM.DecodeResource(fst, "", "", words, ""), LM.DecodeOptions(*opts), **kw)
+
+
+def _cmp(ours, ref, tol=1e-3):
+    assert len(ours) == len(ref), (len(ours), len(ref))
+    assert ours[0].sentence == ref[0][2]
+    assert {r.sentence for r in ours} == {r[2] for r in ref}
+    byref = {r[2]: r for r in ref}
+    for r in ours:
+        assert abs(r.ac_score - byref[r.sentence][0]) < tol * max(1.0, abs(r.ac_score)), r
+        assert abs(r.lm_score - byref[r.sentence][1]) < tol * max(1.0, abs(r.lm_score)), r
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_nbest_matches_oracle(LM, graph, seed):
+    fst, words, info = graph
+    rng = np.random.RandomState(seed)
+    seq = rng.randint(0, 300, size=rng.randint(2, 6))
+    logits = TLG.render_logits([info["prons"][w] for w in seq], T=110, seed=seed, noise=1.2)
+    opts = (7000, 200, 14.0, 8.0, 0.6, 1.0, 0.0, 50)
+    ref = D.OracleDecoder(fst, words, *opts)
+    ref.decode_logits(logits, np.zeros_like(logits), math.log(3.0))
+    ref.finish()
+    dec = _ours(LM, fst, words, opts, max_frames=128)
+    dec.Reset()
+    LM.DecodeNumpy(dec, logits, np.zeros_like(logits), math.log(3.0))
+    partial = dec.result()
+    assert len(partial) == 1 and dec.DecodedSomething()
+    dec.FinishDecoding()
+    _cmp(dec.result(), ref.results())
+    if ref.tokens_per_frame().max() <= 7000:                       # max_active not binding: token sets must agree exactly
+        assert np.array_equal(dec.tokens_per_frame(), ref.tokens_per_frame())
+
+
+def test_one_best_chunked_and_reset(LM, graph):
+    fst, words, info = graph
+    logits = TLG.render_logits([info["prons"][w] for w in [10, 20, 30]], T=100, seed=9)
+    opts = (3000, 200, 12.0, 6.0, 0.6, 1.0, 0.0, 1)
+    ref = D.OracleDecoder(fst, words, *opts)
+    lp = logits - np.log(np.exp(logits).sum(1, keepdims=True))
+    ref.decode_logprobs(lp.astype(np.float32)); ref.finish()
+    dec = _ours(LM, fst, words, opts, max_frames=128)
+    for rep in range(2):                                           # second pass exercises Reset()
+        dec.Reset()
+        for i in range(0, 100, 32):
+            LM.DecodeNumpyLogProbs(dec, lp[i:i + 32].astype(np.float32))
+        dec.FinishDecoding()
+        _cmp(dec.result(), ref.results())
+
+
+def test_blank_skip_and_length_penalty(LM, graph):
+    fst, words, info = graph
+    logits = TLG.render_logits([info["prons"][w] for w in [40, 41]], T=90, seed=4, peak=9.0, noise=0.3)
+    logits[logits.argmax(1) == 0, 0] += 10.0
+    opts = (7000, 200, 14.0, 8.0, 0.6, 0.9, -0.5, 20)
+    ref = D.OracleDecoder(fst, words, *opts)
+    ref.decode_logits(logits, None, 0.0); ref.finish()
+    dec = _ours(LM, fst, words, opts, max_frames=128)
+    LM.DecodeNumpy(dec, logits, np.zeros_like(logits), 0.0)
+    dec.FinishDecoding()
+    _cmp(dec.result(), ref.results())
+    assert len(dec.tokens_per_frame()) == len(ref.tokens_per_frame()) < 90
+
+
+def test_max_active_binding_one_best(LM, graph):
+    fst, words, info = graph
+    logits = TLG.render_logits([info["prons"][w] for w in [7, 8, 9, 10]], T=120, seed=11, noise=1.5)
+    opts = (300, 50, 16.0, 6.0, 0.5, 1.0, 0.0, 10)                 # tiny max_active: pruning is order dependent in Kaldi
+    ref = D.OracleDecoder(fst, words, *opts)
+    ref.decode_logits(logits, None, 0.0); ref.finish()
+    dec = _ours(LM, fst, words, opts, max_frames=128)
+    LM.DecodeNumpy(dec, logits, np.zeros_like(logits), 0.0)
+    dec.FinishDecoding()
+    ours, r = dec.result(), ref.results()
+    assert ours[0].sentence == r[0][2]
+    assert abs(ours[0].ac_score - r[0][0]) < 1e-3 * abs(r[0][0]) and abs(ours[0].lm_score - r[0][1]) < 1e-3 * max(1.0, abs(r[0][1]))
+
+
+def test_batch_decode_equals_single(LM, graph):
+    fst, words, info = graph
+    opts = (7000, 200, 14.0, 8.0, 0.6, 1.0, 0.0, 10)
+    N, T = 12, 100
+    rng = np.random.RandomState(5)
+    batch = np.stack([TLG.render_logits([info["prons"][w] for w in rng.randint(0, 300, size=3)], T=T, seed=100 + n) for n in range(N)])
+    dec = _ours(LM, fst, words, opts, max_frames=128, max_slots=N)
+    dec.DecodeBatch(batch, blank_penalty=math.log(2.0))
+    single = _ours(LM, fst, words, opts, max_frames=128)
+    for n in range(N):
+        single.Reset()
+        LM.DecodeNumpy(single, batch[n], np.zeros_like(batch[n]), math.log(2.0))
+        single.FinishDecoding()
+        a, b = dec.result(slot=n), single.result()
+        assert [r.sentence for r in a] == [r.sentence for r in b]
+        assert all(abs(x.ac_score - y.ac_score) < 1e-4 and abs(x.lm_score - y.lm_score) < 1e-4 for x, y in zip(a, b))
+
+
+def test_errors_are_exceptions(LM, graph, pkg):
+    fst, words, info = graph
+    with pytest.raises(pkg._native.B2TError):
+        _ours(LM, "/nonexistent/TLG.fst", words, (7000, 200, 17.0, 8.0, 0.3, 1.0, 0.0, 10))
+    dec = _ours(LM, fst, words, (7000, 200, 17.0, 8.0, 0.3, 1.0, 0.0, 10), max_frames=16)
+    with pytest.raises(pkg._native.B2TError):
+        LM.DecodeNumpy(dec, np.zeros((40, 41), np.float32), np.zeros((40, 41), np.float32), 0.0)   # longer than max_frames
+    with pytest.raises(pkg._native.B2TError):
+        dec.Rescore()
