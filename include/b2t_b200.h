@@ -191,6 +191,14 @@ int b2t_decoder_decode_batch(b2t_decoder* d, const float* logits, const int* len
 int b2t_decoder_stats(b2t_decoder* d, int slot, int* frames, long long* tokens, long long* links, double* kernel_ms);
 int b2t_decoder_tokens_per_frame(b2t_decoder* d, int slot, int* out, int cap);
 
+/* LM-free CTC prefix beam search (ctc_prefix_beam_search.cc:44-136), batched over utterances.
+ * logp: host [N][T][C] log-probabilities; lens: host [N].  Outputs (host, best first): ids [N][second_beam][max_len],
+ * len / score / viterbi [N][second_beam], times [N][second_beam][max_len], n_hyp [N]. */
+const char* b2t_prefix_last_error(void);
+int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int C, int blank, int first_beam, int second_beam,
+                           int max_len, int* out_ids, int* out_len, float* out_score, float* out_viterbi, int* out_times,
+                           int* out_n);
+
 /* ------------------------------------------------------------------ test hooks (also used by tests/) */
 /* C[M,N] = A[M,K] * B^T with B given as [N,K] (b_mn == 0) or as [K,N] (b_mn == 1), A as [M,K]
  * (a_mn == 0) or [K,M] (a_mn == 1); bf16 inputs, fp32 or bf16 output, optional fp32 bias[N]. */

@@ -154,3 +154,26 @@ def DecodeNumpy(decoder: BrainSpeechDecoder, logits, log_priors, blank_penalty, 
 def DecodeNumpyLogProbs(decoder: BrainSpeechDecoder, logp, slot: int = 0):
     """lm_decoder.cc:39-49."""
     decoder.Decode(np.ascontiguousarray(logp, dtype=np.float32), slot)
+
+
+_lib.b2t_prefix_last_error.restype = C.c_char_p
+_lib.b2t_prefix_beam_search.argtypes = [_vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _vp, _vp, _vp, _vp, _vp, _vp]
+
+
+def ctc_prefix_beam_search(logp, lens=None, blank=0, first_beam_size=10, second_beam_size=10, max_len=None):
+    """CtcPrefixBeamSearch over a batch: logp [N, T, C] (or [T, C]) float32 log-probabilities.
+    Returns, per utterance, a list of (token ids, score, viterbi score, viterbi times), best first."""
+    a = np.ascontiguousarray(logp, dtype=np.float32)
+    if a.ndim == 2:
+        a = a[None]
+    Nn, T, Cc = a.shape
+    ln = np.full((Nn,), T, dtype=np.int32) if lens is None else np.ascontiguousarray(lens, dtype=np.int32)
+    ml = int(max_len or max(T, 1))
+    ids = np.zeros((Nn, second_beam_size, ml), np.int32); ol = np.zeros((Nn, second_beam_size), np.int32)
+    sc = np.zeros((Nn, second_beam_size), np.float32); vt = np.zeros_like(sc); tm = np.zeros_like(ids); nh = np.zeros((Nn,), np.int32)
+    rc = _lib.b2t_prefix_beam_search(a.ctypes.data, ln.ctypes.data, Nn, T, Cc, int(blank), int(first_beam_size), int(second_beam_size), ml,
+                                     ids.ctypes.data, ol.ctypes.data, sc.ctypes.data, vt.ctypes.data, tm.ctypes.data, nh.ctypes.data)
+    if rc < 0:
+        raise N.B2TError(f"ctc_prefix_beam_search failed ({rc}): {_lib.b2t_prefix_last_error().decode()}")
+    return [[(ids[n, r, :ol[n, r]].tolist(), float(sc[n, r]), float(vt[n, r]), tm[n, r, :ol[n, r]].tolist()) for r in range(nh[n])]
+            for n in range(Nn)]

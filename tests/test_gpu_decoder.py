@@ -138,3 +138,26 @@ def test_errors_are_exceptions(LM, graph, pkg):
         LM.DecodeNumpy(dec, np.zeros((40, 41), np.float32), np.zeros((40, 41), np.float32), 0.0)   # longer than max_frames
     with pytest.raises(pkg._native.B2TError):
         dec.Rescore()
+
+
+def test_prefix_beam_golden_and_oracle(LM):
+    """The reference's golden 3x3 vector (ctc_prefix_beam_search_test.cc:18-59) and random parity vs the oracle."""
+    data = np.log(np.array([0.25, 0.40, 0.35, 0.40, 0.35, 0.25, 0.10, 0.50, 0.40], dtype=np.float32).reshape(3, 3))
+    res = LM.ctc_prefix_beam_search(data, first_beam_size=3, second_beam_size=3)[0]
+    assert [r[0] for r in res] == [[2, 1], [1, 2], [1]]
+    for got, want in zip([math.exp(r[1]) for r in res], [0.2185, 0.1550, 0.1525]):
+        assert abs(got - want) < 4e-6 * want
+    for got, want in zip([math.exp(r[2]) for r in res], [0.07, 0.064, 0.07]):
+        assert abs(got - want) < 4e-6 * want
+    assert [r[3] for r in res] == [[0, 2], [0, 2], [2]]
+    rng = np.random.RandomState(0)
+    x = rng.randn(6, 60, 41).astype(np.float32) * 2.0
+    x[..., 0] += 2.5
+    lp = x - np.log(np.exp(x).sum(-1, keepdims=True))
+    lens = np.array([60, 45, 60, 10, 0, 33], dtype=np.int32)
+    ours = LM.ctc_prefix_beam_search(lp, lens=lens)
+    for n in range(6):
+        ref = D.prefix_search(lp[n, :lens[n]]) if lens[n] > 0 else [([], 0.0, 0.0, [])]
+        assert [r[0] for r in ours[n]] == [r[0] for r in ref]                        # identical hypotheses, same order
+        assert all(abs(a[1] - b[1]) < 1e-4 and abs(a[2] - b[2]) < 1e-4 for a, b in zip(ours[n], ref))
+        assert [r[3] for r in ours[n]] == [r[3] for r in ref]
