@@ -207,6 +207,179 @@ ctc_loss_grad_kernel(const CtcParams p) {
   if (p.dbias && tid < p.C) atomicAdd(p.dbias + tid, dbacc);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-per-trial variant for label sequences with 2*Smax+1 <= 32*CPL (CPL <= 4): no block barriers at all.
+// Lane i owns the CPL consecutive lattice cells s in [i*CPL, (i+1)*CPL); neighbours come from warp shuffles; the
+// per-class occupancy of a frame is accumulated in linear space (a posterior, <= 1) with shared-memory atomics.
+// Same arithmetic as the block kernel above (row-normalised fp32 recursions, shifts in double).
+template <int CPL>
+__global__ void __launch_bounds__(32)
+ctc_loss_grad_warp_kernel(const CtcParams p) {
+  extern __shared__ double ctc_smem_d[];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int Lmax = 2 * p.Smax + 1;
+  double* shiftA = ctc_smem_d;
+  float* lp = reinterpret_cast<float*>(shiftA + p.T);
+  float* occ = lp + (size_t)p.T * p.C;                        // [C]
+  int Tb = p.in_len[b];
+  Tb = Tb < 0 ? 0 : (Tb > p.T ? p.T : Tb);
+  const int S = p.tgt_len[b];
+  const int L = 2 * S + 1;
+  const float NINF = -CUDART_INF_F;
+  const unsigned FULL = 0xffffffffu;
+
+  int ext[CPL];
+  bool skip[CPL], skipf[CPL];                                 // may come from s-2 / may go to s+2
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int s = lane * CPL + j;
+    auto lab = [&](int q) { return (q & 1) ? p.labels[(size_t)b * p.Smax + (q >> 1)] : p.blank; };
+    ext[j] = s < L ? lab(s) : p.blank;
+    skip[j] = s < L && s >= 2 && ext[j] != p.blank && ext[j] != lab(s - 2);
+    skipf[j] = s + 2 < L && lab(s + 2) != p.blank && lab(s + 2) != ext[j];
+  }
+  for (int t = 0; t < Tb; ++t) {                              // log-softmax rows (2 classes per lane for C <= 64)
+    const float* row = p.logits + ((size_t)t * p.Bpad + b) * p.ldl;
+    float m = NINF;
+    for (int c = lane; c < p.C; c += 32) m = fmaxf(m, row[c]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    float sum = 0.f;
+    for (int c = lane; c < p.C; c += 32) sum += expf(row[c] - m);
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    const float lz = m + logf(sum);
+    for (int c = lane; c < p.C; c += 32) lp[t * p.C + c] = row[c] - lz;
+  }
+  __syncwarp();
+
+  float* alpha = p.alpha + (size_t)b * p.T * Lmax;
+  float a[CPL];
+  double accA = 0.0;
+  for (int t = 0; t < Tb; ++t) {
+    float na[CPL];
+    if (t == 0) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int s = lane * CPL + j;
+        na[j] = (s == 0) ? lp[p.blank] : ((s == 1 && s < L) ? lp[ext[j]] : NINF);
+      }
+    } else {
+      float l1 = __shfl_up_sync(FULL, a[CPL - 1], 1);
+      float l2 = CPL >= 2 ? __shfl_up_sync(FULL, a[CPL >= 2 ? CPL - 2 : 0], 1) : __shfl_up_sync(FULL, a[0], 2);
+      if (lane == 0) { l1 = NINF; l2 = NINF; }
+      if (CPL == 1 && lane == 1) l2 = NINF;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int s = lane * CPL + j;
+        const float a1 = j >= 1 ? a[j >= 1 ? j - 1 : 0] : l1;
+        const float a2 = j >= 2 ? a[j >= 2 ? j - 2 : 0] : (j == 1 ? l1 : l2);
+        na[j] = s < L ? lse3(a[j], a1, skip[j] ? a2 : NINF) + lp[t * p.C + ext[j]] : NINF;
+      }
+    }
+    float m = na[0];
+#pragma unroll
+    for (int j = 1; j < CPL; ++j) m = fmaxf(m, na[j]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    const float sh = (m == NINF) ? 0.f : m;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      a[j] = na[j] - sh;
+      const int s = lane * CPL + j;
+      if (s < L) alpha[(size_t)t * Lmax + s] = a[j];
+    }
+    accA += (double)sh;
+    if (lane == 0) shiftA[t] = accA;
+  }
+  double ll;
+  {
+    // alpha_T(L-1) and alpha_T(L-2) live in some lanes; fetch them with shuffles
+    float last = NINF, last2 = NINF;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int s = lane * CPL + j;
+      if (s == L - 1) last = a[j];
+      if (s == L - 2) last2 = a[j];
+    }
+    for (int o = 16; o; o >>= 1) { last = fmaxf(last, __shfl_xor_sync(FULL, last, o)); last2 = fmaxf(last2, __shfl_xor_sync(FULL, last2, o)); }
+    if (Tb > 0) ll = (double)lse2(last, last2) + accA;
+    else ll = (S == 0) ? 0.0 : -(double)CUDART_INF_F;
+  }
+  if (lane == 0) p.loss[b] = (float)(-ll);
+  if (!p.dlogits && !p.dlogits_bf16) return;
+  __syncwarp();
+
+  float dbacc[2] = {0.f, 0.f};
+  float bt[CPL];
+  double accB = 0.0;
+  for (int t = p.T - 1; t >= 0; --t) {
+    float* drow = p.dlogits ? p.dlogits + ((size_t)t * p.Bpad + b) * p.ldl : nullptr;
+    __nv_bfloat16* drow16 = p.dlogits_bf16 ? p.dlogits_bf16 + ((size_t)t * p.Bpad + b) * p.ldl : nullptr;
+    if (t >= Tb) {
+      for (int c = lane; c < p.ldl; c += 32) {
+        if (drow) drow[c] = 0.f;
+        if (drow16) drow16[c] = __float2bfloat16_rn(0.f);
+      }
+      continue;
+    }
+    float nb[CPL];
+    if (t == Tb - 1) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int s = lane * CPL + j;
+        nb[j] = (s < L && (s == L - 1 || s == L - 2)) ? lp[t * p.C + ext[j]] : NINF;
+      }
+    } else {
+      float r1 = __shfl_down_sync(FULL, bt[0], 1);
+      float r2 = CPL >= 2 ? __shfl_down_sync(FULL, bt[CPL >= 2 ? 1 : 0], 1) : __shfl_down_sync(FULL, bt[0], 2);
+      if (lane == 31) { r1 = NINF; r2 = NINF; }
+      if (CPL == 1 && lane == 30) r2 = NINF;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const int s = lane * CPL + j;
+        const float b1 = j + 1 < CPL ? bt[j + 1 < CPL ? j + 1 : 0] : r1;
+        const float b2 = j + 2 < CPL ? bt[j + 2 < CPL ? j + 2 : 0] : (j + 1 < CPL ? r1 : r2);
+        nb[j] = s < L ? lse3(bt[j], s + 1 < L ? b1 : NINF, skipf[j] ? b2 : NINF) + lp[t * p.C + ext[j]] : NINF;
+      }
+    }
+    float m = nb[0];
+#pragma unroll
+    for (int j = 1; j < CPL; ++j) m = fmaxf(m, nb[j]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    const float sh = (m == NINF) ? 0.f : m;
+    accB += (double)sh;
+    const float base = (float)(shiftA[t] + accB - ll);
+    for (int c = lane; c < p.C; c += 32) occ[c] = 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      bt[j] = nb[j] - sh;
+      const int s = lane * CPL + j;
+      if (s < L) {
+        const float ab = alpha[(size_t)t * Lmax + s] + bt[j] + base;       // log of the (doubly emitted) path mass through (t, s)
+        const float w = expf(ab - lp[t * p.C + ext[j]]);
+        if (w > 0.f) atomicAdd(&occ[ext[j]], w);
+      }
+    }
+    __syncwarp();
+    int k = 0;
+    for (int c = lane; c < p.ldl; c += 32, ++k) {
+      float g = 0.f;
+      if (c < p.C) {
+        g = (expf(lp[t * p.C + c]) - occ[c]) * p.grad_scale;
+        if (k < 2) dbacc[k] += g;
+      }
+      if (drow) drow[c] = g;
+      if (drow16) drow16[c] = __float2bfloat16_rn(g);
+    }
+    __syncwarp();
+  }
+  if (p.dbias) {
+    int k = 0;
+    for (int c = lane; c < p.C && k < 2; c += 32, ++k) atomicAdd(p.dbias + c, dbacc[k]);
+  }
+}
+
+inline size_t ctc_warp_smem_bytes(int T, int C) { return (size_t)T * sizeof(double) + ((size_t)T * C + C) * sizeof(float) + 16; }
+
 inline size_t ctc_smem_bytes(int T, int C, int Smax) {
   const int Lmax = 2 * Smax + 1;
   return (size_t)T * sizeof(double) + ((size_t)T * C + 4 * (size_t)Lmax) * sizeof(float) + 16;

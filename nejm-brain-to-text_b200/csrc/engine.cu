@@ -568,10 +568,29 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
 }
 
 // ------------------------------------------------------------------------------------ CTC
+template <int CPL>
+static int run_ctc_warp(const CtcParams& cp, int B, size_t smem, cudaStream_t st) {
+  CK(cudaFuncSetAttribute(ctc_loss_grad_warp_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_loss_grad_warp_kernel<CPL><<<B, 32, smem, st>>>(cp);
+  CK(LAUNCHED());
+  return 0;
+}
+
 static int run_ctc(const CtcParams& cp, int B, cudaStream_t st) {
+  if (cp.C > CTC_THREADS || cp.ldl > CTC_THREADS) return fail(B2T_ERR_UNSUPPORTED, "too many classes");
+  const int Lmax = 2 * cp.Smax + 1;
+  const size_t wsmem = ctc_warp_smem_bytes(cp.T, cp.C);
+  if (Lmax <= 128 && cp.C <= 64 && wsmem <= 200 * 1024) {     // warp-per-trial kernel: no block barriers
+    const int cpl = (Lmax + 31) / 32;
+    switch (cpl) {
+      case 1: return run_ctc_warp<1>(cp, B, wsmem, st);
+      case 2: return run_ctc_warp<2>(cp, B, wsmem, st);
+      case 3: return run_ctc_warp<3>(cp, B, wsmem, st);
+      default: return run_ctc_warp<4>(cp, B, wsmem, st);
+    }
+  }
   const size_t smem = ctc_smem_bytes(cp.T, cp.C, cp.Smax);
   if (smem > 200 * 1024) return fail(B2T_ERR_UNSUPPORTED, "CTC problem too large for shared memory (T=%d, S=%d)", cp.T, cp.Smax);
-  if (cp.C > CTC_THREADS || cp.ldl > CTC_THREADS) return fail(B2T_ERR_UNSUPPORTED, "too many classes");
   CK(cudaFuncSetAttribute(ctc_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ctc_loss_grad_kernel<<<B, CTC_THREADS, smem, st>>>(cp);
   CK(LAUNCHED());

@@ -75,12 +75,21 @@ def test_autograd_path_matches_reference_grads(mods):
     assert abs(float(gn) - float(rest["grad_norm"])) < 3e-2 * float(rest["grad_norm"])
 
 
-def test_ctc_loss_matches_torch(mods):
-    g = torch.Generator().manual_seed(0)
-    T, B, C, S = 40, 5, 41, 9
+@pytest.mark.parametrize("T,B,S,cap", [(40, 5, 9, None), (97, 8, 45, None), (30, 4, 3, None), (170, 3, 80, None), (60, 4, 20, 70)])
+def test_ctc_loss_matches_torch(mods, T, B, S, cap):
+    """Both CTC kernels (warp-per-trial for 2S+1 <= 128, block-per-trial beyond) against torch in float64.
+    Covers empty targets, repeated labels, ragged input lengths and an infeasible-looking short input."""
+    g = torch.Generator().manual_seed(T * 31 + S)
+    C = 41
     lp = torch.randn(T, B, C, generator=g).log_softmax(2).cuda().requires_grad_()
-    tg = torch.randint(1, C, (B, S), generator=g)
-    il = torch.tensor([40, 33, 25, 40, 12]); tl = torch.tensor([9, 5, 0, 1, 6])
+    Sw = cap or S                                              # padded label width decides which kernel runs
+    tg = torch.randint(1, C, (B, Sw), generator=g)
+    tg[0, 1:4] = tg[0, 0]                                      # repeated labels need blanks in between
+    il = torch.randint(max(2 * S + 2, T // 2), T + 1, (B,), generator=g).clamp(max=T)
+    il[0] = T
+    tl = torch.randint(1, S + 1, (B,), generator=g)
+    tl[-1] = 0                                                 # empty target
+    tl[0] = min(S, 6)
     ours = mods["ctc"].ctc_loss(lp, tg.cuda(), il.cuda(), tl.cuda())
     ours.sum().backward()
     # checker in float64 so that the comparison measures OUR fp32 log-space error, not the sum of two fp32 errors
@@ -88,7 +97,7 @@ def test_ctc_loss_matches_torch(mods):
     ref = torch.nn.functional.ctc_loss(ref_lp, tg, il, tl, blank=0, reduction="none", zero_infinity=False)
     ref.sum().backward()
     assert util.rel_err(ours.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
-    assert np.abs(lp.grad.cpu().numpy() - ref_lp.grad.numpy()).max() < 2e-5       # fp32 alpha/beta over 40 frames, |grad| <= 1
+    assert np.abs(lp.grad.cpu().numpy() - ref_lp.grad.numpy()).max() < 1e-5       # |grad| <= 1
 
 
 def _trainer_args(tmp, n_batches):
