@@ -124,10 +124,14 @@ struct Carver {
   }
 };
 
-constexpr int LDL = 64;   // pitch (elements) of logits / dlogits rows: 128 B in bf16, TMA friendly
+constexpr int LDL = 64;        // pitch (elements) of logits / dlogits rows: 128 B in bf16, TMA friendly
+constexpr int MAX_CHUNKS = 8;  // time chunks of the layer wave-front
+constexpr int MAX_LANES = 3;   // concurrent recurrence launches (side streams)
 
 struct LayerBuf {
-  __nv_bfloat16 *hseq, *hdrop, *R, *Z, *Nn, *HN;
+  __nv_bfloat16 *hseq, *hdrop, *R, *Z, *Nn, *HN, *dGx, *dGh;
+  float *gx, *dY, *part, *h_state, *dh_state;
+  int *done_f, *done_b;
 };
 
 struct b2t_engine {
@@ -139,10 +143,11 @@ struct b2t_engine {
   float *params, *grads, *m1, *m2;
   // carved buffers
   __nv_bfloat16* shadow;
-  __nv_bfloat16 *xs, *xd, *xu, *dxu, *dpre, *dGx, *dGh, *dlog16;
-  float *gx, *logits, *dlog32, *alpha, *dY[2], *dh0, *h_init, *h_final, *part;
+  __nv_bfloat16 *xs, *xd, *xu, *dxu, *dpre, *dlog16;
+  float *logits, *dlog32, *alpha;
   std::vector<LayerBuf> lay;
-  int *done, *day_pad, *steps, *greedy_scratch;
+  int *done_all, *steps, *greedy_scratch;
+  size_t done_elems = 0;
   float *sumsq, *stats;
   Segment* d_segs;
   ChunkRef* d_chunks;
@@ -150,10 +155,17 @@ struct b2t_engine {
   float* touched;             // tail of the gradient buffer: [n_days]
   // current shape + plans
   int B = 0, Bpad = 0, T_in = 0, T_out = 0, Tp = 0, M = 0;
+  int BG = 16, n_tchunks = 1, n_lanes = 1;
+  int tc_begin[MAX_CHUNKS + 1];
   bool plans_ok = false, use_unfold_copy = false;
-  GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw;
-  std::vector<GemmPlan> p_in, p_dwih, p_dwhh, p_dx;
+  GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw, p_in0, p_dx0;
+  std::vector<GemmPlan> p_dwih, p_dwhh;
+  std::vector<std::vector<GemmPlan>> p_in, p_dx;     // [layer >= 1][chunk]
   std::vector<CUtensorMap> tm_h;
+  // side streams / events of the wave-front
+  cudaStream_t lane[MAX_LANES + 1] = {nullptr, nullptr, nullptr, nullptr};   // [MAX_LANES] = bulk stream (weight-gradient GEMMs)
+  cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 1] = {nullptr, nullptr, nullptr, nullptr}, ev_top = nullptr;
+  std::vector<cudaEvent_t> ev_r, ev_dx;              // [layer * MAX_CHUNKS + chunk]
   // state of the last forward
   bool have_fwd = false, have_dlogits = false, fwd_training = false;
   unsigned long long seed = 0;
@@ -172,40 +184,46 @@ static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
   Carver c{reinterpret_cast<uint8_t*>(ws), 0, cap, dry};
   const int Bp = r16(e->maxB), T = e->maxT, D = e->D, H = e->H, L = e->L;
   const int Tp = e->cfg.patch_size > 0 ? (T - e->patch) / e->stride + 1 : T;
-  const size_t M = (size_t)(Tp > 0 ? Tp : 1) * Bp;
+  const int Tq = Tp > 0 ? Tp : 1;
+  const size_t M = (size_t)Tq * Bp;
   const bool tr = e->training != 0;
+  const int NS = H / 32, NG = Bp / 16;
   e->shadow = c.take<__nv_bfloat16>(e->n_params);
   e->xs = c.take<__nv_bfloat16>((size_t)Bp * T * D);
   e->xd = c.take<__nv_bfloat16>((size_t)Bp * T * D);
   e->xu = c.take<__nv_bfloat16>(M * e->K0);
-  e->gx = c.take<float>(M * 3 * H);
   e->lay.resize(L);
+  e->done_elems = (size_t)2 * L * NG * Tq;
+  e->done_all = c.take<int>(e->done_elems + 16);
   for (int l = 0; l < L; ++l) {
-    e->lay[l].hseq = c.take<__nv_bfloat16>((M + Bp) * H);
-    e->lay[l].hdrop = (tr && l < L - 1) ? c.take<__nv_bfloat16>(M * H) : nullptr;
-    e->lay[l].R = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
-    e->lay[l].Z = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
-    e->lay[l].Nn = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
-    e->lay[l].HN = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    LayerBuf& b = e->lay[l];
+    b.gx = c.take<float>(M * 3 * H);
+    b.hseq = c.take<__nv_bfloat16>((M + Bp) * H);
+    b.hdrop = (tr && l < L - 1) ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    b.R = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    b.Z = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    b.Nn = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    b.HN = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    b.h_state = c.take<float>((size_t)Bp * H);
+    b.done_f = dry ? nullptr : e->done_all + (size_t)(2 * l) * NG * Tq;
+    b.done_b = dry ? nullptr : e->done_all + (size_t)(2 * l + 1) * NG * Tq;
+    b.dGx = b.dGh = nullptr; b.dY = b.part = b.dh_state = nullptr;
+    if (tr) {
+      b.dGx = c.take<__nv_bfloat16>(M * 3 * H);
+      b.dGh = c.take<__nv_bfloat16>(M * 3 * H);
+      b.dY = c.take<float>(M * H);
+      b.part = c.take<float>((size_t)2 * NG * NS * NS * 16 * 32);
+      b.dh_state = c.take<float>((size_t)Bp * H);
+    }
   }
-  e->h_init = c.take<float>((size_t)L * Bp * H);
-  e->h_final = c.take<float>((size_t)L * Bp * H);
   e->logits = c.take<float>(M * LDL);
   e->dlog32 = c.take<float>(M * LDL);
   e->dlog16 = c.take<__nv_bfloat16>(M * LDL);
-  e->alpha = c.take<float>((size_t)e->maxB * (Tp > 0 ? Tp : 1) * (2 * e->maxS + 1));
-  e->done = c.take<int>((size_t)(Bp / 16) * (Tp > 0 ? Tp : 1) + 16);
-  e->day_pad = c.take<int>(Bp);
+  e->alpha = c.take<float>((size_t)e->maxB * Tq * (2 * e->maxS + 1));
   e->greedy_scratch = c.take<int>((size_t)e->maxB * 2 * (e->maxS + 1));
   if (tr) {
-    e->dY[0] = c.take<float>(M * H);
-    e->dY[1] = c.take<float>(M * H);
-    e->dGx = c.take<__nv_bfloat16>(M * 3 * H);
-    e->dGh = c.take<__nv_bfloat16>(M * 3 * H);
     e->dxu = c.take<__nv_bfloat16>(M * e->K0);
     e->dpre = c.take<__nv_bfloat16>((size_t)Bp * T * D);
-    e->dh0 = c.take<float>((size_t)L * Bp * H);
-    e->part = c.take<float>((size_t)2 * (Bp / 16) * (H / 32) * (H / 32) * 512);
     e->sumsq = c.take<float>(4);
     e->stats = e->sumsq ? e->sumsq + 1 : nullptr;
     e->steps = c.take<int>(e->segs.size());
@@ -229,6 +247,19 @@ extern "C" long long b2t_workspace_bytes(const b2t_config* cfg, int max_batch, i
   return (long long)carve(&e, nullptr, 0, true);
 }
 
+extern "C" void b2t_engine_destroy(b2t_engine* e) {
+  if (!e) return;
+  for (int i = 0; i <= MAX_LANES; ++i) {
+    if (e->lane[i]) cudaStreamDestroy(e->lane[i]);
+    if (e->ev_lane_end[i]) cudaEventDestroy(e->ev_lane_end[i]);
+  }
+  if (e->ev_start) cudaEventDestroy(e->ev_start);
+  if (e->ev_top) cudaEventDestroy(e->ev_top);
+  for (cudaEvent_t ev : e->ev_r) if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->ev_dx) if (ev) cudaEventDestroy(ev);
+  delete e;
+}
+
 extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, int max_T, int max_label_len, int training, float* params,
                                          float* grads, float* exp_avg, float* exp_avg_sq, void* workspace, long long workspace_bytes) {
   if (check_cfg(cfg)) return nullptr;
@@ -250,6 +281,17 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
   e->params = params; e->grads = grads; e->m1 = exp_avg; e->m2 = exp_avg_sq;
   carve(e, workspace, (size_t)workspace_bytes, false);
   e->touched = grads ? grads + e->n_params : nullptr;
+  bool ok = cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_top, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i <= MAX_LANES && ok; ++i)
+    ok = cudaStreamCreateWithFlags(&e->lane[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->ev_lane_end[i], cudaEventDisableTiming) == cudaSuccess;
+  e->ev_r.assign((size_t)e->L * MAX_CHUNKS, nullptr);
+  e->ev_dx.assign((size_t)e->L * MAX_CHUNKS, nullptr);
+  for (size_t i = 0; i < e->ev_r.size() && ok; ++i)
+    ok = cudaEventCreateWithFlags(&e->ev_r[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->ev_dx[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { fail(B2T_ERR_CUDA, "stream/event creation failed"); b2t_engine_destroy(e); return nullptr; }
   if (training) {
     std::vector<Segment> hs;
     std::vector<ChunkRef> hc;
@@ -262,13 +304,12 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
         cudaMemcpy(e->d_chunks, hc.data(), hc.size() * sizeof(ChunkRef), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(e->steps, 0, e->segs.size() * sizeof(int)) != cudaSuccess) {
       fail(B2T_ERR_CUDA, "engine setup copies failed");
-      delete e;
+      b2t_engine_destroy(e);
       return nullptr;
     }
   }
   return e;
 }
-extern "C" void b2t_engine_destroy(b2t_engine* e) { delete e; }
 extern "C" int* b2t_step_counters(b2t_engine* e) { return e ? e->steps : nullptr; }
 extern "C" int b2t_debug_set_trace(b2t_engine* e, long long* buf) {
   if (!e) return fail(B2T_ERR_ARG, "null engine");
@@ -287,20 +328,33 @@ extern "C" int b2t_refresh_weights(b2t_engine* e, void* stream) {
 // ------------------------------------------------------------------------------------ plans
 static int make_2d(CUtensorMap* tm, const void* p, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows) {
   const uint64_t dims[4] = {inner, rows, 1, 1};
-  const uint64_t str[3] = {ld, ld * rows > 8 ? 8 : 8, 8};
+  const uint64_t str[3] = {ld, 8, 8};
   const uint32_t box[4] = {64, box_rows, 1, 1};
-  (void)str;
-  const uint64_t s2[3] = {ld, 8, 8};
-  return make_tmap_bf16_4d(tm, p, dims, s2, box);
+  return make_tmap_bf16_4d(tm, p, dims, str, box);
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
 }
 
 static int build_plans(b2t_engine* e) {
   const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp, M = e->M, K0 = e->K0, T = e->T_in;
   const bool tr = e->training != 0;
-  e->p_in.assign(L, GemmPlan());
+  // ---- recurrence geometry: trials per CTA, concurrent launches, time chunks
+  e->BG = (Bp % 32 == 0) ? 32 : 16;
+  const int ctas = (H / 32) * (Bp / e->BG);
+  e->n_lanes = std::max(1, std::min(MAX_LANES, num_sms() / std::max(ctas, 1)));
+  e->n_lanes = std::max(1, std::min(e->n_lanes, env_int("B2T_REC_LANES", MAX_LANES)));
+  int nch = env_int("B2T_REC_CHUNKS", 0);
+  if (nch <= 0) nch = (e->n_lanes > 1 && Tp >= 48) ? 4 : 1;
+  nch = std::max(1, std::min(std::min(nch, MAX_CHUNKS), Tp));
+  e->n_tchunks = nch;
+  for (int c = 0; c <= nch; ++c) e->tc_begin[c] = (int)((long long)c * Tp / nch);
   e->p_dwih.assign(L, GemmPlan());
   e->p_dwhh.assign(L, GemmPlan());
-  e->p_dx.assign(L, GemmPlan());
+  e->p_in.assign(L, std::vector<GemmPlan>(nch));
+  e->p_dx.assign(L, std::vector<GemmPlan>(nch));
   e->tm_h.assign(L, CUtensorMap());
   int rc;
   {  // day layer: xd[b] = softsign(xs[b] @ W_day[day_b] + b_day[day_b]) (+dropout)      rnn_model.py:95-103
@@ -315,34 +369,44 @@ static int build_plans(b2t_engine* e) {
     s.keep = 1.0f;
     if ((rc = gemm_plan_build(&e->p_day, s))) return fail(B2T_ERR_CUDA, "day-layer plan failed (%d)", rc);
   }
-  for (int l = 0; l < L; ++l) {
-    const std::string sl = std::to_string(l);
+  {  // layer-0 input projection over the whole sequence (does not depend on any recurrence)
     GemmSpec s;
     s.a_mn = 0; s.b_mn = 0; s.epi = EPI_STORE; s.out_bf16 = 0;
-    s.N = 3 * H;
-    s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
-    s.C = e->gx; s.ldc = 3 * H;
-    s.bias = e->params + seg_off(e, "gru.bias_ih_l" + sl);
-    if (l == 0) {
-      s.K = K0; s.ldb = K0; s.M = M;
-      if (!e->use_unfold_copy) {   // strided patch view of xd (rnn_model.py:106-119), never materialised
-        s.A = e->xd; s.a_rin = Bp; s.a_rout = Tp; s.a_rin_stride = (long long)T * D; s.a_rout_stride = (long long)e->stride * D;
-        rc = gemm_plan_build(&e->p_in[0], s);
-        if (rc) {
-          fprintf(stderr, "b2t: strided patch tensor map rejected (%d); falling back to a materialised unfold\n", rc);
-          e->use_unfold_copy = true;
-        }
+    s.N = 3 * H; s.K = K0; s.ldb = K0; s.M = M;
+    s.B = e->shadow + seg_off(e, "gru.weight_ih_l0");
+    s.C = e->lay[0].gx; s.ldc = 3 * H;
+    s.bias = e->params + seg_off(e, "gru.bias_ih_l0");
+    rc = -1;
+    if (!e->use_unfold_copy) {   // strided patch view of xd (rnn_model.py:106-119), never materialised
+      s.A = e->xd; s.a_rin = Bp; s.a_rout = Tp; s.a_rin_stride = (long long)T * D; s.a_rout_stride = (long long)e->stride * D;
+      rc = gemm_plan_build(&e->p_in0, s);
+      if (rc) {
+        fprintf(stderr, "b2t: strided patch tensor map rejected (%d); falling back to a materialised unfold\n", rc);
+        e->use_unfold_copy = true;
       }
-      if (e->use_unfold_copy) {
-        s.a_rin = 0; s.A = e->xu; s.lda = K0;
-        if ((rc = gemm_plan_build(&e->p_in[0], s))) return fail(B2T_ERR_CUDA, "L0 input plan failed (%d)", rc);
-      }
-    } else {
-      s.K = H; s.ldb = H; s.M = M; s.lda = H;
-      s.A = e->lay[l - 1].hdrop ? e->lay[l - 1].hdrop : e->lay[l - 1].hseq + (size_t)Bp * H;
-      if ((rc = gemm_plan_build(&e->p_in[l], s))) return fail(B2T_ERR_CUDA, "input plan %d failed (%d)", l, rc);
     }
-    if (make_2d(&e->tm_h[l], e->lay[l].hseq, H, (uint64_t)(Tp + 1) * Bp, H, 16)) return fail(B2T_ERR_CUDA, "hseq map failed");
+    if (e->use_unfold_copy) {
+      s.a_rin = 0; s.A = e->xu; s.lda = K0;
+      if ((rc = gemm_plan_build(&e->p_in0, s))) return fail(B2T_ERR_CUDA, "L0 input plan failed (%d)", rc);
+    }
+  }
+  for (int l = 0; l < L; ++l) {
+    const std::string sl = std::to_string(l);
+    if (l > 0) {
+      const __nv_bfloat16* in = e->lay[l - 1].hdrop ? e->lay[l - 1].hdrop : e->lay[l - 1].hseq + (size_t)Bp * H;
+      for (int c = 0; c < nch; ++c) {      // per time chunk: rows [t0*Bp, t1*Bp)
+        const long long r0 = (long long)e->tc_begin[c] * Bp, rows = (long long)(e->tc_begin[c + 1] - e->tc_begin[c]) * Bp;
+        GemmSpec s;
+        s.a_mn = 0; s.b_mn = 0; s.epi = EPI_STORE; s.out_bf16 = 0;
+        s.M = rows; s.N = 3 * H; s.K = H; s.lda = H; s.ldb = H;
+        s.A = in + r0 * H;
+        s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
+        s.C = e->lay[l].gx + r0 * 3 * H; s.ldc = 3 * H;
+        s.bias = e->params + seg_off(e, "gru.bias_ih_l" + sl);
+        if ((rc = gemm_plan_build(&e->p_in[l][c], s))) return fail(B2T_ERR_CUDA, "input plan %d/%d failed (%d)", l, c, rc);
+      }
+    }
+    if (make_2d(&e->tm_h[l], e->lay[l].hseq, H, (uint64_t)(Tp + 1) * Bp, H, e->BG)) return fail(B2T_ERR_CUDA, "hseq map failed");
   }
   {  // head: logits = top @ W_out^T + b_out                                       rnn_model.py:129
     GemmSpec s;
@@ -368,7 +432,7 @@ static int build_plans(b2t_engine* e) {
     s.a_mn = 0; s.b_mn = 1; s.epi = EPI_STORE;
     s.M = M; s.N = H; s.K = e->C;
     s.A = e->dlog16; s.lda = LDL; s.B = e->shadow + seg_off(e, "out.weight"); s.ldb = H;
-    s.C = e->dY[0]; s.ldc = H;
+    s.C = e->lay[L - 1].dY; s.ldc = H;
     if ((rc = gemm_plan_build(&e->p_dytop, s))) return fail(B2T_ERR_CUDA, "dY_top plan failed (%d)", rc);
   }
   for (int l = 0; l < L; ++l) {
@@ -377,7 +441,7 @@ static int build_plans(b2t_engine* e) {
       GemmSpec s;
       s.a_mn = 1; s.b_mn = 1; s.epi = EPI_STORE;
       s.M = 3 * H; s.K = M;
-      s.A = e->dGx; s.lda = 3 * H;
+      s.A = e->lay[l].dGx; s.lda = 3 * H;
       s.C = e->grads + seg_off(e, "gru.weight_ih_l" + sl);
       if (l == 0) {
         s.N = K0; s.ldc = K0;
@@ -398,19 +462,27 @@ static int build_plans(b2t_engine* e) {
       GemmSpec s;
       s.a_mn = 1; s.b_mn = 1; s.epi = EPI_STORE;
       s.M = 3 * H; s.N = H; s.K = M;
-      s.A = e->dGh; s.lda = 3 * H; s.B = e->lay[l].hseq; s.ldb = H;
+      s.A = e->lay[l].dGh; s.lda = 3 * H; s.B = e->lay[l].hseq; s.ldb = H;
       s.C = e->grads + seg_off(e, "gru.weight_hh_l" + sl); s.ldc = H;
       if ((rc = gemm_plan_build(&e->p_dwhh[l], s))) return fail(B2T_ERR_CUDA, "dW_hh plan %d failed (%d)", l, rc);
     }
-    {  // dX = dGx W_ih
+    if (l == 0) {  // dX_unf = dGx W_ih (whole sequence), folded afterwards
       GemmSpec s;
       s.a_mn = 0; s.b_mn = 1; s.epi = EPI_STORE;
-      s.M = M; s.K = 3 * H;
-      s.A = e->dGx; s.lda = 3 * H;
-      s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
-      if (l == 0) { s.N = K0; s.ldb = K0; s.out_bf16 = 1; s.C = e->dxu; s.ldc = K0; }
-      else { s.N = H; s.ldb = H; s.out_bf16 = 0; s.C = e->dY[(L - l) & 1]; s.ldc = H; }
-      if ((rc = gemm_plan_build(&e->p_dx[l], s))) return fail(B2T_ERR_CUDA, "dX plan %d failed (%d)", l, rc);
+      s.M = M; s.K = 3 * H; s.A = e->lay[0].dGx; s.lda = 3 * H;
+      s.B = e->shadow + seg_off(e, "gru.weight_ih_l0");
+      s.N = K0; s.ldb = K0; s.out_bf16 = 1; s.C = e->dxu; s.ldc = K0;
+      if ((rc = gemm_plan_build(&e->p_dx0, s))) return fail(B2T_ERR_CUDA, "dX plan 0 failed (%d)", rc);
+    } else {
+      for (int c = 0; c < nch; ++c) {   // dY_{l-1}[chunk] = dGx_l[chunk] W_ih_l
+        const long long r0 = (long long)e->tc_begin[c] * Bp, rows = (long long)(e->tc_begin[c + 1] - e->tc_begin[c]) * Bp;
+        GemmSpec s;
+        s.a_mn = 0; s.b_mn = 1; s.epi = EPI_STORE;
+        s.M = rows; s.K = 3 * H; s.A = e->lay[l].dGx + r0 * 3 * H; s.lda = 3 * H;
+        s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
+        s.N = H; s.ldb = H; s.out_bf16 = 0; s.C = e->lay[l - 1].dY + r0 * H; s.ldc = H;
+        if ((rc = gemm_plan_build(&e->p_dx[l][c], s))) return fail(B2T_ERR_CUDA, "dX plan %d/%d failed (%d)", l, c, rc);
+      }
     }
   }
   {  // dW_day[day_b] += xs[b]^T dpre[b]
@@ -460,22 +532,33 @@ extern "C" int b2t_output_frames(const b2t_config* cfg, int T, int smooth_mode, 
 // half of the shared memory forces one CTA per SM.  Cooperative launch guarantees that every CTA of the grid is
 // co-resident (they spin on each other's flags).
 constexpr size_t REC_SMEM_BYTES = 120 * 1024;
-static cudaError_t launch_rec_fwd(const CUtensorMap& tm, const RecFwdParams& p, int grid, cudaStream_t st) {
-  cudaError_t err = cudaFuncSetAttribute(gru_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM_BYTES);
+template <int BG>
+static cudaError_t launch_rec_fwd_t(const CUtensorMap& tm, const RecFwdParams& p, int grid, cudaStream_t st) {
+  cudaError_t err = cudaFuncSetAttribute(gru_rec_fwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM_BYTES);
   if (err != cudaSuccess) return err;
   void* args[2] = {(void*)&tm, (void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_rec_fwd_kernel, dim3(grid), dim3(REC_THREADS), args, REC_SMEM_BYTES, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_rec_fwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kThreads), args, REC_SMEM_BYTES, st);
 }
-static cudaError_t launch_rec_bwd(const RecBwdParams& p, int grid, cudaStream_t st) {
-  cudaError_t err = cudaFuncSetAttribute(gru_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM_BYTES);
+template <int BG>
+static cudaError_t launch_rec_bwd_t(const RecBwdParams& p, int grid, cudaStream_t st) {
+  cudaError_t err = cudaFuncSetAttribute(gru_rec_bwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM_BYTES);
   if (err != cudaSuccess) return err;
   void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd_kernel, dim3(grid), dim3(REC_THREADS), args, REC_SMEM_BYTES, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kThreads), args, REC_SMEM_BYTES, st);
+}
+static cudaError_t launch_rec_fwd(int BG, const CUtensorMap& tm, const RecFwdParams& p, int grid, cudaStream_t st) {
+  return BG == 32 ? launch_rec_fwd_t<32>(tm, p, grid, st) : launch_rec_fwd_t<16>(tm, p, grid, st);
+}
+static cudaError_t launch_rec_bwd(int BG, const RecBwdParams& p, int grid, cudaStream_t st) {
+  return BG == 32 ? launch_rec_bwd_t<32>(p, grid, st) : launch_rec_bwd_t<16>(p, grid, st);
 }
 
 // ------------------------------------------------------------------------------------ forward
+// Wave-front schedule.  Layer l runs on side stream ("lane") l % n_lanes; its time chunk c needs chunk c of the layer
+// below (event) and its own chunk c-1 (stream order).  Tasks are issued diagonal by diagonal so that every lane's FIFO
+// is in dependency order.  With 48-CTA launches (H = 768, B = 64, BG = 32) three lanes run concurrently on 144 SMs.
 extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* stream) {
   if (!e || !a || !a->x || !a->day_idx) return fail(B2T_ERR_ARG, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -495,7 +578,8 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
   const int Tp = b2t_output_frames(&e->cfg, a->T, a->smooth_mode, ntaps, cut);
   if (Tp < 1) return fail(B2T_ERR_ARG, "input too short: T=%d gives no output frame", a->T);
   const int Bp = r16(a->B);
-  if ((H / 32) * (Bp / 16) > num_sms()) return fail(B2T_ERR_UNSUPPORTED, "batch %d needs %d co-resident CTAs (> %d SMs); split the batch", a->B, (H / 32) * (Bp / 16), num_sms());
+  if ((H / 32) * (Bp / ((Bp % 32 == 0) ? 32 : 16)) > num_sms())
+    return fail(B2T_ERR_UNSUPPORTED, "batch %d needs more co-resident CTAs than the %d SMs; split the batch", a->B, num_sms());
   if (!e->plans_ok || e->B != a->B || e->T_in != a->T || e->Tp != Tp || e->T_out != T_out || e->day_idx != a->day_idx) {
     e->B = a->B; e->Bpad = Bp; e->T_in = a->T; e->T_out = T_out; e->Tp = Tp; e->M = Tp * Bp; e->day_idx = a->day_idx;
     e->plans_ok = false;
@@ -509,51 +593,70 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
   e->states_given = a->states != nullptr;
   const float keep_in = (a->training && e->cfg.input_dropout > 0.f) ? 1.0f - e->cfg.input_dropout : 1.0f;
   const float keep_rnn = (a->training && e->cfg.rnn_dropout > 0.f) ? 1.0f - e->cfg.rnn_dropout : 1.0f;
+  const int BG = e->BG, nch = e->n_tchunks, NL = e->n_lanes;
+  const int n_groups = Bp / BG, grid = (H / 32) * n_groups;
 
-  // 1. augmentation + smoothing -> xs (bf16)
-  pp.x = a->x; pp.out = e->xs; pp.B = a->B; pp.Bpad = Bp; pp.T_in = a->T; pp.T_alloc = a->T; pp.D = D;
+  // 1. augmentation + smoothing -> xs (bf16); 2. day layer; 3. layer-0 input projection (whole sequence)
+  pp.x = a->x; pp.out = e->xs; pp.out_f32 = nullptr; pp.B = a->B; pp.Bpad = Bp; pp.T_in = a->T; pp.T_alloc = a->T; pp.D = D;
   pp.cut = cut; pp.ntaps = ntaps; pp.valid = a->smooth_mode == 2;
   pp.white_std = a->training ? a->white_noise_std : 0.f;
   pp.offset_std = a->training ? a->offset_noise_std : 0.f;
   pp.white = a->white_noise; pp.offset = a->offset_noise; pp.use_philox = 1;
   pp.seed = a->seed; pp.rng_offset = 0;
   {
-    dim3 grid((a->T + PRE_TT - 1) / PRE_TT, Bp);
-    pre_smooth_kernel<<<grid, D / 4, 0, st>>>(pp);
+    dim3 g((a->T + PRE_TT - 1) / PRE_TT, Bp);
+    pre_smooth_kernel<<<g, D / 4, 0, st>>>(pp);
     CK(LAUNCHED());
   }
-  // 2. day layer
   e->p_day.p.keep = keep_in; e->p_day.p.seed = a->seed; e->p_day.p.rng_offset = 0;
   CK(gemm_run(e->p_day, st)); ++g_launches;
-  // 3. GRU stack
-  const int n_groups = Bp / 16, grid = (H / 32) * n_groups;
-  for (int l = 0; l < L; ++l) {
-    if (l == 0 && e->use_unfold_copy) {
-      unfold_kernel<<<num_sms() * 4, 256, 0, st>>>(e->xd, e->xu, Bp, a->T, D, Tp, e->patch, e->stride);
-      CK(LAUNCHED());
-    }
-    CK(gemm_run(e->p_in[l], st)); ++g_launches;
-    float* hin = e->h_init + (size_t)l * Bp * H;
-    init_state_kernel<<<(Bp * H + 255) / 256, 256, 0, st>>>(e->params + seg_off(e, "h0"), a->states ? a->states + (size_t)l * a->B * H : nullptr,
-                                                             a->B, Bp, H, e->lay[l].hseq, hin);
+  if (e->use_unfold_copy) {
+    unfold_kernel<<<num_sms() * 4, 256, 0, st>>>(e->xd, e->xu, Bp, a->T, D, Tp, e->patch, e->stride);
     CK(LAUNCHED());
-    CK(cudaMemsetAsync(e->done, 0, (size_t)n_groups * Tp * sizeof(int), st));
-    RecFwdParams rp;
-    rp.H = H; rp.T = Tp; rp.Bpad = Bp; rp.n_slices = H / 32;
-    rp.gx = e->gx; rp.bhh = e->params + seg_off(e, "gru.bias_hh_l" + std::to_string(l));
-    rp.whh = e->shadow + seg_off(e, "gru.weight_hh_l" + std::to_string(l));
-    rp.hseq = e->lay[l].hseq; rp.h_init = hin; rp.h_final = e->h_final + (size_t)l * Bp * H;
-    const bool save = a->training != 0;
-    rp.hdrop = save ? e->lay[l].hdrop : nullptr;
-    rp.R = save ? e->lay[l].R : nullptr; rp.Z = save ? e->lay[l].Z : nullptr;
-    rp.Nn = save ? e->lay[l].Nn : nullptr; rp.HN = save ? e->lay[l].HN : nullptr;
-    rp.done = e->done; rp.keep = keep_rnn; rp.seed = a->seed; rp.rng_offset = (unsigned long long)(l + 1) << 40;
-    rp.trace = (l == 0) ? e->trace : nullptr;
-    // eval-mode forward through a training engine: the next layer reads hdrop if it exists, so keep it in sync
-    if (!save && e->lay[l].hdrop) { rp.hdrop = e->lay[l].hdrop; rp.keep = 1.0f; }
-    CK(launch_rec_fwd(e->tm_h[l], rp, grid, st));
   }
-  // 4. head
+  CK(gemm_run(e->p_in0, st)); ++g_launches;
+  CK(cudaMemsetAsync(e->done_all, 0, e->done_elems * sizeof(int), st));
+  for (int l = 0; l < L; ++l) {
+    init_state_kernel<<<(Bp * H + 255) / 256, 256, 0, st>>>(e->params + seg_off(e, "h0"), a->states ? a->states + (size_t)l * a->B * H : nullptr,
+                                                             a->B, Bp, H, e->lay[l].hseq, e->lay[l].h_state);
+    CK(LAUNCHED());
+  }
+  CK(cudaEventRecord(e->ev_start, st));
+  for (int i = 0; i < NL; ++i) CK(cudaStreamWaitEvent(e->lane[i], e->ev_start, 0));
+
+  // 4. GRU stack, wave-front over (layer, chunk)
+  const bool save = a->training != 0;
+  for (int d = 0; d < nch + L - 1; ++d) {
+    for (int l = 0; l < L; ++l) {
+      const int c = d - l;
+      if (c < 0 || c >= nch) continue;
+      cudaStream_t ls = e->lane[l % NL];
+      if (l > 0) {
+        CK(cudaStreamWaitEvent(ls, e->ev_r[(size_t)(l - 1) * MAX_CHUNKS + c], 0));
+        CK(gemm_run(e->p_in[l][c], ls)); ++g_launches;
+      }
+      RecFwdParams rp;
+      rp.H = H; rp.Bpad = Bp; rp.t_begin = e->tc_begin[c]; rp.t_end = e->tc_begin[c + 1]; rp.T = Tp; rp.n_slices = H / 32;
+      rp.gx = e->lay[l].gx; rp.bhh = e->params + seg_off(e, "gru.bias_hh_l" + std::to_string(l));
+      rp.whh = e->shadow + seg_off(e, "gru.weight_hh_l" + std::to_string(l));
+      rp.hseq = e->lay[l].hseq; rp.h_state = e->lay[l].h_state;
+      rp.hdrop = save ? e->lay[l].hdrop : nullptr;
+      rp.R = save ? e->lay[l].R : nullptr; rp.Z = save ? e->lay[l].Z : nullptr;
+      rp.Nn = save ? e->lay[l].Nn : nullptr; rp.HN = save ? e->lay[l].HN : nullptr;
+      rp.done = e->lay[l].done_f; rp.keep = keep_rnn; rp.seed = a->seed; rp.rng_offset = (unsigned long long)(l + 1) << 40;
+      rp.trace = (l == 0) ? e->trace : nullptr;
+      // eval-mode forward through a training engine: the next layer reads hdrop if it exists, so keep it in sync
+      if (!save && e->lay[l].hdrop) { rp.hdrop = e->lay[l].hdrop; rp.keep = 1.0f; }
+      CK(launch_rec_fwd(BG, e->tm_h[l], rp, grid, ls));
+      CK(cudaEventRecord(e->ev_r[(size_t)l * MAX_CHUNKS + c], ls));
+    }
+  }
+  // join: the user stream continues after the top layer's last chunk (which transitively follows everything else)
+  for (int i = 0; i < NL; ++i) {
+    CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
+    CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));
+  }
+  // 5. head
   CK(gemm_run(e->p_head, st)); ++g_launches;
   if (a->logits_out) {
     gather_logits_kernel<<<num_sms() * 2, 256, 0, st>>>(e->logits, Tp, a->B, Bp, LDL, e->C, a->logits_out);
@@ -561,7 +664,7 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
   }
   if (a->hidden_out) {
     for (int l = 0; l < L; ++l)
-      CK(cudaMemcpyAsync(a->hidden_out + (size_t)l * a->B * H, e->h_final + (size_t)l * Bp * H, (size_t)a->B * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(a->hidden_out + (size_t)l * a->B * H, e->lay[l].h_state, (size_t)a->B * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   e->have_fwd = true;
   return Tp;
@@ -656,7 +759,9 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp;
   const float keep_in = e->cfg.input_dropout > 0.f ? 1.0f - e->cfg.input_dropout : 1.0f;
   const float keep_rnn = e->cfg.rnn_dropout > 0.f ? 1.0f - e->cfg.rnn_dropout : 1.0f;
-  // zero what is accumulated with atomics: biases, h0, day params of the touched days, touched flags
+  const int BG = e->BG, nch = e->n_tchunks, NL = e->n_lanes;
+  const int n_groups = Bp / BG, grid = (H / 32) * n_groups;
+  // zero what is accumulated with atomics: biases, h0, day params, touched flags
   CK(cudaMemsetAsync(e->touched, 0, r64(e->cfg.n_days) * sizeof(float), st));
   mark_days_kernel<<<(e->B + 127) / 128, 128, 0, st>>>(e->day_idx, e->B, e->touched);
   CK(LAUNCHED());
@@ -666,48 +771,73 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   for (int l = 0; l < L; ++l)
     CK(cudaMemsetAsync(e->grads + seg_off(e, "gru.bias_ih_l" + std::to_string(l)), 0, (size_t)2 * r64(3 * H) * sizeof(float), st));
   CK(cudaMemsetAsync(e->grads + seg_off(e, "out.bias"), 0, (size_t)(r64(e->C) + r64(H)) * sizeof(float), st));
+  CK(cudaMemsetAsync(e->done_all, 0, e->done_elems * sizeof(int), st));
 
   // head
   colsum_kernel<<<64, 64, 0, st>>>(e->dlog32, (size_t)e->M, LDL, e->C, e->grads + seg_off(e, "out.bias"));
   CK(LAUNCHED());
   CK(gemm_run(e->p_dwout, st)); ++g_launches;
   CK(gemm_run(e->p_dytop, st)); ++g_launches;
-  const int n_groups = Bp / 16, grid = (H / 32) * n_groups;
-  for (int l = L - 1; l >= 0; --l) {
-    const std::string sl = std::to_string(l);
-    CK(cudaMemsetAsync(e->done, 0, (size_t)n_groups * Tp * sizeof(int), st));
-    RecBwdParams bp;
-    bp.H = H; bp.T = Tp; bp.Bpad = Bp; bp.n_slices = H / 32;
-    bp.dY = e->dY[(L - 1 - l) & 1];
-    bp.hseq = e->lay[l].hseq; bp.R = e->lay[l].R; bp.Z = e->lay[l].Z; bp.Nn = e->lay[l].Nn; bp.HN = e->lay[l].HN;
-    bp.dGx = e->dGx; bp.dGh = e->dGh; bp.part = e->part;
-    bp.whh = e->shadow + seg_off(e, "gru.weight_hh_l" + sl);
-    bp.dbih = e->grads + seg_off(e, "gru.bias_ih_l" + sl); bp.dbhh = e->grads + seg_off(e, "gru.bias_hh_l" + sl);
-    bp.dh0 = e->dh0 + (size_t)l * Bp * H;
-    bp.done = e->done; bp.n_valid = e->B;
-    bp.keep = (l < L - 1) ? keep_rnn : 1.0f;
-    bp.seed = e->seed; bp.rng_offset = (unsigned long long)(l + 1) << 40;
-    bp.trace = (l == L - 1 && e->trace) ? e->trace + (size_t)Tp * 8 : nullptr;
-    CK(launch_rec_bwd(bp, grid, st));
-    CK(gemm_run(e->p_dwih[l], st)); ++g_launches;
-    CK(gemm_run(e->p_dwhh[l], st)); ++g_launches;
-    CK(gemm_run(e->p_dx[l], st)); ++g_launches;
-    if (!e->states_given) {
-      reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, st>>>(e->dh0 + (size_t)l * Bp * H, e->B, H, e->grads + seg_off(e, "h0"));
-      CK(LAUNCHED());
+  CK(cudaEventRecord(e->ev_top, st));
+  for (int i = 0; i < NL; ++i) CK(cudaStreamWaitEvent(e->lane[i], e->ev_top, 0));
+  CK(cudaStreamWaitEvent(e->lane[MAX_LANES], e->ev_top, 0));
+
+  // wave-front over (layer descending, time chunk descending); k counts chunks from the end of the sequence
+  for (int d = 0; d < nch + L - 1; ++d) {
+    for (int l = L - 1; l >= 0; --l) {
+      const int k = d - (L - 1 - l);
+      if (k < 0 || k >= nch) continue;
+      const int c = nch - 1 - k;
+      const std::string sl = std::to_string(l);
+      cudaStream_t ls = e->lane[l % NL];
+      if (l < L - 1) CK(cudaStreamWaitEvent(ls, e->ev_dx[(size_t)(l + 1) * MAX_CHUNKS + c], 0));   // dY_l[chunk c] is ready
+      RecBwdParams bp;
+      bp.H = H; bp.Bpad = Bp; bp.n_slices = H / 32; bp.T = Tp;
+      bp.t_begin = e->tc_begin[c]; bp.t_end = e->tc_begin[c + 1]; bp.first_chunk = (c == nch - 1);
+      bp.dY = e->lay[l].dY;
+      bp.hseq = e->lay[l].hseq; bp.R = e->lay[l].R; bp.Z = e->lay[l].Z; bp.Nn = e->lay[l].Nn; bp.HN = e->lay[l].HN;
+      bp.whh = e->shadow + seg_off(e, "gru.weight_hh_l" + sl);
+      bp.dGx = e->lay[l].dGx; bp.dGh = e->lay[l].dGh; bp.part = e->lay[l].part;
+      bp.dbih = e->grads + seg_off(e, "gru.bias_ih_l" + sl); bp.dbhh = e->grads + seg_off(e, "gru.bias_hh_l" + sl);
+      bp.dh_state = e->lay[l].dh_state;
+      bp.done = e->lay[l].done_b; bp.n_valid = e->B;
+      bp.keep = (l < L - 1) ? keep_rnn : 1.0f;
+      bp.seed = e->seed; bp.rng_offset = (unsigned long long)(l + 1) << 40;
+      bp.trace = (l == L - 1 && c == nch - 1 && e->trace) ? e->trace + (size_t)Tp * 8 : nullptr;
+      CK(launch_rec_bwd(BG, bp, grid, ls));
+      if (l > 0) {
+        CK(gemm_run(e->p_dx[l][c], ls)); ++g_launches;
+        CK(cudaEventRecord(e->ev_dx[(size_t)l * MAX_CHUNKS + c], ls));
+      }
+      if (c == 0) {   // the layer's recurrence is complete: weight gradients over the whole sequence, on the bulk stream
+        cudaStream_t bs = e->lane[MAX_LANES];
+        CK(cudaEventRecord(e->ev_r[(size_t)l * MAX_CHUNKS], ls));
+        CK(cudaStreamWaitEvent(bs, e->ev_r[(size_t)l * MAX_CHUNKS], 0));
+        CK(gemm_run(e->p_dwih[l], bs)); ++g_launches;
+        CK(gemm_run(e->p_dwhh[l], bs)); ++g_launches;
+        if (!e->states_given) {
+          reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bs>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
+          CK(LAUNCHED());
+        }
+        if (l == 0) {   // patch fold + day layer
+          CK(gemm_run(e->p_dx0, bs)); ++g_launches;
+          FoldParams fp;
+          fp.dxu = e->dxu; fp.xd = e->xd; fp.dpre = e->dpre; fp.dbias_day = e->grads + seg_off(e, "day_biases.0"); fp.bias_pitch = (int)r64(D);
+          fp.day_idx = e->day_idx; fp.B = e->B; fp.Bpad = Bp; fp.T_alloc = e->T_in; fp.T_valid = e->T_out; fp.D = D; fp.Tp = Tp;
+          fp.patch = e->patch; fp.stride = e->stride; fp.keep = keep_in; fp.seed = e->seed; fp.rng_offset = 0;
+          dim3 g((e->T_in + FOLD_TT - 1) / FOLD_TT, Bp);
+          fold_dpre_kernel<<<g, D / 4, 0, bs>>>(fp);
+          CK(LAUNCHED());
+          CK(gemm_run(e->p_daydw, bs)); ++g_launches;
+        }
+      }
     }
   }
-  // patch fold + day layer
-  FoldParams fp;
-  fp.dxu = e->dxu; fp.xd = e->xd; fp.dpre = e->dpre; fp.dbias_day = e->grads + seg_off(e, "day_biases.0"); fp.bias_pitch = (int)r64(D);
-  fp.day_idx = e->day_idx; fp.B = e->B; fp.Bpad = Bp; fp.T_alloc = e->T_in; fp.T_valid = e->T_out; fp.D = D; fp.Tp = Tp;
-  fp.patch = e->patch; fp.stride = e->stride; fp.keep = keep_in; fp.seed = e->seed; fp.rng_offset = 0;
-  {
-    dim3 g((e->T_in + FOLD_TT - 1) / FOLD_TT, Bp);
-    fold_dpre_kernel<<<g, D / 4, 0, st>>>(fp);
-    CK(LAUNCHED());
+  for (int i = 0; i <= MAX_LANES; ++i) {
+    if (i < MAX_LANES && i >= NL) continue;
+    CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
+    CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));
   }
-  CK(gemm_run(e->p_daydw, st)); ++g_launches;
   e->have_dlogits = false;
   return 0;
 }

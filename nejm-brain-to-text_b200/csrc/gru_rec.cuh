@@ -1,25 +1,29 @@
-// Persistent GRU recurrence kernels for sm_100a (one launch per layer and direction).
+// Persistent GRU recurrence kernels for sm_100a (one launch per layer, direction and time chunk).
 //
 // Reference semantics: torch.nn.GRU as used at rnn_model.py:65-72,126 (gate order r,z,n):
 //   r = sig(gx_r + W_hr h + b_hr)   z = sig(gx_z + W_hz h + b_hz)
 //   n = tanh(gx_n + r * (W_hn h + b_hn))      h' = (1-z) * n + z * h
 // gx = x W_ih^T + b_ih is produced for all time steps by the tcgen05 GEMM (gemm.cuh).
 //
-// Decomposition.  The batch is cut into groups of 16 trials and the hidden units into slices of 32.
-// CTA (slice s, group g) owns the 96 gate rows {r,z,n} x 32 units of W_hh for the whole sequence.
+// Decomposition.  The batch is cut into groups of BG trials (16 or 32) and the hidden units into slices of 32.
+// CTA (slice s, group g) owns the 96 gate rows {r,z,n} x 32 units of W_hh for the whole chunk.
 // The weights live in TENSOR MEMORY as the A operand of tcgen05.mma (lane = gate row, 32-bit column =
-// two packed bf16 of K; 384 of the 512 TMEM columns for H = 768), so a time step never re-reads them
-// from shared memory: measured on B200, the smem-resident variant spent 3.6k cycles per step
-// streaming the 147 KB slice through the MMA's smem port for an N=16 product.
+// two packed bf16 of K), so a time step never re-reads them from shared memory.
 //
-//   forward : D[128 (96 used), 16] = W_slice[128, H] (TMEM) * h_{t-1}[16, H]^T (smem, via TMA)
+//   forward : D[128 (96 used), BG] = W_slice[128, H] (TMEM) * h_{t-1}[BG, H]^T (smem, via TMA)
 //             The three gate row-blocks land in TMEM lane quarters 0,1,2; the epilogue warps move them
-//             through a 6 KB smem exchange so that one thread owns (trial, 4 units) with all gates, does
+//             through a small smem exchange so that one thread owns (trial, 4 units) with all gates, does
 //             the gate math in fp32 (h itself is carried in fp32 registers) and writes h_t (bf16).
-//   backward: the same CTA owns dG_t[16, 96] (its own 32 units x 3 gates) and keeps W_slice^T in TMEM:
-//             P[H, 16] = W_slice^T[H, 96] (TMEM, H/128 row blocks) * dG_t[16, 96]^T (smem, written
+//   backward: the same CTA owns dG_t[BG, 96] (its own 32 units x 3 gates) and keeps W_slice^T in TMEM:
+//             P[H, BG] = W_slice^T[H, 96] (TMEM, H/128 row blocks) * dG_t[BG, 96]^T (smem, written
 //             locally).  P is this CTA's partial of dh_{t-1} for ALL units; the H/32 CTAs of a batch
 //             group exchange fp32 partials through L2 (reduce-scatter) once per step.
+//
+// Measured on B200 (profiles/r1_mma_dispatch_microbench.md): a tcgen05.mma with N <= 64 costs a fixed ~50 cycles,
+// so the step is bound by the NUMBER of MMAs (48 forward, 36 backward) and by the publish/acquire round trip through
+// L2, not by N.  BG = 32 therefore costs the same per step as BG = 16 but needs half the CTAs (48 for H = 768,
+// B = 64), which lets the engine run the chunks of up to three layers concurrently (wave-front over layers and
+// time chunks, see engine.cu).  A chunk [t_begin, t_end) carries its state in fp32 (h / dh) between launches.
 // Trials are independent, so only the H/32 CTAs of one batch group synchronise per step, through a
 // release/acquire counter in global memory (cooperative launch guarantees co-residency).
 #pragma once
@@ -27,25 +31,29 @@
 
 namespace b2t {
 
-constexpr int REC_BG = 16;        // trials per batch group (UMMA N)
 constexpr int REC_US = 32;        // hidden units per CTA
-constexpr int REC_THREADS = 192;  // warp0 producer/poller, warp1 MMA + TMEM owner, warps 2..5 epilogue
-constexpr int REC_XPAD = 20;      // exchange row pitch (floats)
 constexpr int REC_TMEM_COLS = 512;
-constexpr int REC_D_COL = 384;    // accumulator columns start here (A uses [0, 384))
+
+template <int BG> struct RecCfg {
+  static constexpr int kEpiWarps = BG / 4;            // 4 (BG=16) or 8 (BG=32): one thread per (trial, 4 units)
+  static constexpr int kEpiThreads = 32 * kEpiWarps;
+  static constexpr int kThreads = 64 + kEpiThreads;   // warp0 producer/poller, warp1 MMA + TMEM owner
+  static constexpr int kXPitch = BG + 4;              // exchange row pitch (floats)
+};
 
 struct RecFwdParams {
-  int H, T, Bpad;                 // hidden size, time steps, padded batch (multiple of 16)
+  int H, Bpad;                    // hidden size, padded batch (multiple of BG)
+  int t_begin, t_end;             // time steps of this chunk
   int n_slices;                   // H / 32
   const float* gx;                // [T][Bpad][3H] fp32, includes b_ih
   const float* bhh;               // [3H]
   const __nv_bfloat16* whh;       // [3H][H] bf16
   __nv_bfloat16* hseq;            // [(T+1)][Bpad][H]; slot 0 = initial state, slot t+1 = h_t
-  const float* h_init;            // [Bpad][H] fp32 initial state (register carry)
-  float* h_final;                 // [Bpad][H] fp32 (nullable)
+  float* h_state;                 // [Bpad][H] fp32: h_{t_begin-1} on entry, h_{t_end-1} on exit (chunk carry / final state)
   __nv_bfloat16* hdrop;           // [T][Bpad][H] dropout(h_t) for the next layer (nullable => not written)
   __nv_bfloat16 *R, *Z, *Nn, *HN; // [T][Bpad][H] stash for BPTT (nullable when not training)
-  int* done;                      // [n_groups][T] arrival counters, zeroed before launch
+  int* done;                      // [n_groups][T] arrival counters, zeroed before the first chunk
+  int T;                          // total steps (stride of `done`)
   float keep;                     // dropout keep prob for hdrop
   unsigned long long seed, rng_offset;
   long long* trace;               // optional [T][8] clock64 samples from CTA 0 (profiling aid)
@@ -54,7 +62,7 @@ struct RecFwdParams {
 #define REC_TRACE(step, slot) do { if (p.trace && blockIdx.x == 0) p.trace[(step) * 8 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 __device__ __forceinline__ void wait_counter(const int* ctr, int target) {
   uint32_t spins = 0;
@@ -87,22 +95,27 @@ __device__ __forceinline__ uint4 rec_dropout_bits(unsigned long long seed, unsig
   return philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x6a7eu, 0), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
-// tmap_h : hseq bf16   dims (H, (T+1)*Bpad)  box (64, 16)
-__global__ void __launch_bounds__(REC_THREADS, 1)
+// tmap_h : hseq bf16   dims (H, (T+1)*Bpad)  box (64, BG)
+template <int BG>
+__global__ void __launch_bounds__(RecCfg<BG>::kThreads, 1)
 gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParams p) {
+  using Cfg = RecCfg<BG>;
+  constexpr int XP = Cfg::kXPitch;
+  constexpr int CHUNK_BYTES = BG * 128;                  // BG rows x 64 bf16
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int KC = p.H / 64;                               // 64-wide contraction chunks
-  uint8_t* sH = smem;                                    // KC x 2 KB (16 rows x 128 B, SWIZZLE_128B)
-  float* sX = reinterpret_cast<float*>(sH + KC * 2048);  // [3][32][REC_XPAD]
-  uint64_t* bar_h = reinterpret_cast<uint64_t*>(sX + 3 * 32 * REC_XPAD);   // [KC] (<= 16)
+  uint8_t* sH = smem;                                    // KC x CHUNK_BYTES (SWIZZLE_128B)
+  float* sX = reinterpret_cast<float*>(sH + KC * CHUNK_BYTES);   // [3][32][XP]
+  uint64_t* bar_h = reinterpret_cast<uint64_t*>(sX + 3 * 32 * XP);   // [KC] (<= 16)
   uint64_t* bar_d = bar_h + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % p.n_slices, grp = blockIdx.x / p.n_slices;
-  const int j0 = slice * REC_US, b0 = grp * REC_BG;
+  const int j0 = slice * REC_US, b0 = grp * BG;
   int* done = p.done + (size_t)grp * p.T;
+  const int a_cols = p.H / 2;                            // TMEM columns of the A operand; accumulator follows
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_h);
@@ -115,13 +128,13 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d = tmem_base + REC_D_COL;
+  const uint32_t tmem_d = tmem_base + a_cols;
 
   // ---- one-time: W_hh slice -> TMEM.  Lane 32q+l holds gate q, unit j0+l; quarter 3 is zero.
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     const int q = warp & 3;
     const uint4* src = reinterpret_cast<const uint4*>(p.whh + ((size_t)(q < 3 ? q : 0) * p.H + j0 + lane) * p.H);
-    for (int w0 = 0; w0 < p.H / 2; w0 += 16) {
+    for (int w0 = 0; w0 < a_cols; w0 += 16) {
       uint32_t v[16];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -139,45 +152,48 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
 
   if (warp == 0) {
     if (elect_one()) {
-      for (int t = 0; t < p.T; ++t) {
-        if (t > 0) {
+      for (int t = p.t_begin; t < p.t_end; ++t) {
+        if (t > p.t_begin) {
           wait_counter(&done[t - 1], p.n_slices);
           fence_proxy_async_all();             // order the acquired generic-proxy writes before async-proxy reads
         }
         REC_TRACE(t, 0);                       // flags acquired
         for (int c = 0; c < KC; ++c) {
-          mbar_arrive_expect_tx(&bar_h[c], 2048);
-          tma_load_2d(sH + c * 2048, &tmap_h, &bar_h[c], c * 64, t * p.Bpad + b0);   // slot t = h_{t-1}
+          mbar_arrive_expect_tx(&bar_h[c], CHUNK_BYTES);
+          tma_load_2d(sH + c * CHUNK_BYTES, &tmap_h, &bar_h[c], c * 64, t * p.Bpad + b0);   // slot t = h_{t-1}
         }
         REC_TRACE(t, 1);                       // TMA issued
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, REC_BG, 0, 0);
-      for (int t = 0; t < p.T; ++t) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BG, 0, 0);
+      for (int t = p.t_begin; t < p.t_end; ++t) {
+        const uint32_t par = (uint32_t)(t - p.t_begin) & 1u;
         for (int c = 0; c < KC; ++c) {
-          mbar_wait(&bar_h[c], t & 1);
+          mbar_wait(&bar_h[c], par);
           if (c == 0) REC_TRACE(t, 2);         // first operand chunk landed
           tc_fence_after();
-          const uint32_t sb = smem_u32(sH + c * 2048);
+          const uint32_t sb = smem_u32(sH + c * CHUNK_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)     // accumulator k: the tensor pipe sees a dependent MMA only every 4th issue
-            umma_bf16_ts(tmem_d + k * REC_BG, tmem_base + (c * 4 + k) * 8, umma_smem_desc(sb + k * 32, 16, 1024), idesc, c != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ts(tmem_d, tmem_base + (c * 4 + k) * 8, umma_smem_desc(sb + k * 32, 16, 1024), idesc, (c | k) != 0 ? 1u : 0u);
         }
         umma_commit(bar_d);
         REC_TRACE(t, 3);                       // all MMAs issued
       }
     }
   } else {
-    // ---------------- epilogue: 128 threads; thread e owns trial b0 + e/8 and units j0 + 4*(e%8) .. +3
+    // ---------------- epilogue: thread e owns trial b0 + e/8 and units j0 + 4*(e%8) .. +3
     const int e = threadIdx.x - 64;
+    const int ew = e >> 5;                     // epilogue warp index
     const int q = warp & 3;                    // TMEM lane quarter: 0 -> r rows, 1 -> z, 2 -> n, 3 -> unused
+    const int chalf = ew >> 2;                 // which 16 accumulator columns this warp moves (BG = 32 has two halves)
     const int bl = e >> 3, u0 = (e & 7) * 4;
     const int b = b0 + bl, j = j0 + u0;
     float h[4], bh[3][4];
     {
-      const float4 hv = *reinterpret_cast<const float4*>(p.h_init + (size_t)b * p.H + j);
+      const float4 hv = *reinterpret_cast<const float4*>(p.h_state + (size_t)b * p.H + j);
       h[0] = hv.x; h[1] = hv.y; h[2] = hv.z; h[3] = hv.w;
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
@@ -187,40 +203,34 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
     }
     const bool train = p.R != nullptr;
     const float inv_keep = 1.0f / p.keep;
-    for (int t = 0; t < p.T; ++t) {
+    for (int t = p.t_begin; t < p.t_end; ++t) {
       const size_t row = (size_t)t * p.Bpad + b;
       // prefetch the input projection while the MMA runs
       float4 gxv[3];
 #pragma unroll
       for (int g = 0; g < 3; ++g) gxv[g] = __ldg(reinterpret_cast<const float4*>(p.gx + row * 3 * p.H + g * p.H + j));
 
-      mbar_wait(bar_d, t & 1);
+      mbar_wait(bar_d, (uint32_t)(t - p.t_begin) & 1u);
       if (e == 0) REC_TRACE(t, 4);             // accumulator complete
       tc_fence_after();
       if (q < 3) {
-        uint32_t v0[16], v1[16], v2[16], v3[16];
-        const uint32_t ta = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
-        tmem_ld16(ta, v0); tmem_ld16(ta + 16, v1); tmem_ld16(ta + 32, v2); tmem_ld16(ta + 48, v3);
+        uint32_t v[16];
+        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + chalf * 16, v);
         tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(sX + (q * 32 + lane) * REC_XPAD);
+        float4* dst = reinterpret_cast<float4*>(sX + (q * 32 + lane) * XP + chalf * 16);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float f[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            f[k] = (__uint_as_float(v0[4 * i + k]) + __uint_as_float(v1[4 * i + k])) + (__uint_as_float(v2[4 * i + k]) + __uint_as_float(v3[4 * i + k]));
-          dst[i] = make_float4(f[0], f[1], f[2], f[3]);
-        }
+        for (int i = 0; i < 4; ++i)
+          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
       }
       tc_fence_before();
-      epi_bar_sync();
+      epi_bar_sync<Cfg::kEpiThreads>();
       if (e == 0) REC_TRACE(t, 7);             // gates exchanged
       float hn[4], r[4], z[4], n[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float ar = sX[(0 * 32 + u0 + i) * REC_XPAD + bl];
-        const float az = sX[(1 * 32 + u0 + i) * REC_XPAD + bl];
-        const float an = sX[(2 * 32 + u0 + i) * REC_XPAD + bl];
+        const float ar = sX[(0 * 32 + u0 + i) * XP + bl];
+        const float az = sX[(1 * 32 + u0 + i) * XP + bl];
+        const float an = sX[(2 * 32 + u0 + i) * XP + bl];
         const float gr = (&gxv[0].x)[i], gz = (&gxv[1].x)[i], gn = (&gxv[2].x)[i];
         r[i] = sigmoid_f(gr + ar + bh[0][i]);
         z[i] = sigmoid_f(gz + az + bh[1][i]);
@@ -234,7 +244,7 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
       // publish h_t: every thread's store is ordered before the CTA barrier; the release by one thread is
       // cumulative over it (same pattern as a grid barrier).  The BPTT stash is written after the release,
       // off the critical path of the other CTAs.
-      epi_bar_sync();
+      epi_bar_sync<Cfg::kEpiThreads>();
       if (e == 0) {
         fence_proxy_async_all();
         red_release_add(&done[t], 1);
@@ -257,7 +267,7 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
         st_bf16x4(p.hdrop + off, d[0], d[1], d[2], d[3]);
       }
     }
-    if (p.h_final) *reinterpret_cast<float4*>(p.h_final + (size_t)b * p.H + j) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(p.h_state + (size_t)b * p.H + j) = make_float4(h[0], h[1], h[2], h[3]);
   }
 
   tc_fence_before();
@@ -276,17 +286,21 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
 //   dh_{t-1} = dh*z + dGh_t W_hh + dY_{t-1}
 // dW_ih/dW_hh are GEMMs over dGx/dGh afterwards; the bias gradients are accumulated here in registers.
 struct RecBwdParams {
-  int H, T, Bpad, n_slices;
+  int H, Bpad, n_slices;
+  int t_begin, t_end;               // this chunk processes t = t_end-1 ... t_begin
+  int T;                            // total steps (stride of `done`)
   const float* dY;                  // [T][Bpad][H] fp32 gradient wrt this layer's (dropped) output
   const __nv_bfloat16* hseq;        // [(T+1)][Bpad][H]
   const __nv_bfloat16 *R, *Z, *Nn, *HN;
   const __nv_bfloat16* whh;         // [3H][H] bf16
   __nv_bfloat16* dGx;               // [T][Bpad][3H]
   __nv_bfloat16* dGh;               // [T][Bpad][3H]
-  float* part;                      // [2][n_groups][n_slices(dest)][n_slices(src)][16][32] fp32 partial sums of dh
+  float* part;                      // [2][n_groups][n_slices(dest)][n_slices(src)][BG][32] fp32 partial sums of dh
   float* dbih;                      // [3H] (atomicAdd)
   float* dbhh;                      // [3H] (atomicAdd)
-  float* dh0;                       // [Bpad][H] gradient wrt the initial state (written)
+  float* dh_state;                  // [Bpad][H] fp32: recurrent part of dh_{t_end-1} on entry (ignored when first_chunk),
+                                    //                  recurrent part of dh_{t_begin-1} on exit (= grad wrt the initial state at t_begin = 0)
+  int first_chunk;                  // 1: t_end == T, no incoming recurrent gradient
   int* done;                        // [n_groups][T]
   int n_valid;                      // trials < n_valid contribute (pad trials are masked out)
   float keep;                       // dropout applied to this layer's output in forward (1 => none)
@@ -294,21 +308,26 @@ struct RecBwdParams {
   long long* trace;                 // optional [T][8] clock64 samples from CTA 0
 };
 
-__global__ void __launch_bounds__(REC_THREADS, 1)
+template <int BG>
+__global__ void __launch_bounds__(RecCfg<BG>::kThreads, 1)
 gru_rec_bwd_kernel(const RecBwdParams p) {
+  using Cfg = RecCfg<BG>;
+  constexpr int CHUNK_BYTES = BG * 128;
+  constexpr int A_PITCH = 48;                            // TMEM columns per 128-row block of W_slice^T (96 kk = 48 words)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sB = smem;                                    // 2 chunks x 2 KB: dG_t as K-major B operand [16 trials][128 kk] (kk = gate*32 + unit, 96 used)
-  uint64_t* bar_d = reinterpret_cast<uint64_t*>(sB + 4096);
+  uint8_t* sB = smem;                                    // 2 chunks: dG_t as K-major B operand [BG trials][128 kk] (kk = gate*32 + unit, 96 used)
+  uint64_t* bar_d = reinterpret_cast<uint64_t*>(sB + 2 * CHUNK_BYTES);
   uint64_t* bar_f = bar_d + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_f + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NS = p.n_slices, NG = gridDim.x / NS;
   const int slice = blockIdx.x % NS, grp = blockIdx.x / NS;
-  const int j0 = slice * REC_US, b0 = grp * REC_BG;
+  const int j0 = slice * REC_US, b0 = grp * BG;
   const int MB = (p.H + 127) / 128;                      // 128-row blocks of the output (all hidden units)
   int* done = p.done + (size_t)grp * p.T;
+  const int nsteps = p.t_end - p.t_begin;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_d, 1);
@@ -316,16 +335,16 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < 1024; i += REC_THREADS) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
+  for (int i = threadIdx.x; i < 2 * CHUNK_BYTES / 4; i += Cfg::kThreads) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d = tmem_base + REC_D_COL;
+  const uint32_t tmem_d = tmem_base + MB * A_PITCH;
 
   // ---- one-time: W_slice^T -> TMEM.  Block mb, lane m holds output unit k = mb*128+m; column w packs
-  //      kk = 2w, 2w+1 with kk = gate*32 + unit (48 words per block, block pitch 64 columns).
-  if (warp >= 2) {
+  //      kk = 2w, 2w+1 with kk = gate*32 + unit (48 words per block).
+  if (warp >= 2 && warp < 6) {
     const int q = warp & 3;
     for (int mb = 0; mb < MB; ++mb) {
       const int k = mb * 128 + q * 32 + lane;
@@ -342,7 +361,7 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
           }
           v[i] = lo | (hi << 16);
         }
-        tmem_st16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mb * 64 + w0, v);
+        tmem_st16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mb * A_PITCH + w0, v);
       }
     }
     tmem_st_wait();
@@ -351,23 +370,25 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
   __syncthreads();
   tc_fence_after();
 
-  // Steps are indexed s = 0..T-1 for t = T-1-s.  The partials published at step s feed dh of step s+1.
+  // Steps are indexed s = 0..nsteps-1 for t = t_end-1-s.  The partials published at step s feed dh of step s+1.
   if (warp == 0) {
     if (elect_one()) {
-      for (int s = 0; s < p.T; ++s) {                    // forward the "all partials of step s are visible" event to the CTA
-        wait_counter(&done[s], NS);
+      for (int s = 0; s < nsteps; ++s) {                 // forward the "all partials of step s are visible" event to the CTA
+        wait_counter(&done[p.t_end - 1 - s], NS);
         REC_TRACE(s, 0);
         mbar_arrive(bar_f);
       }
     }
   } else if (warp >= 2) {
     const int e = threadIdx.x - 64;
+    const int ew = e >> 5;
     const int q = warp & 3;
+    const int chalf = ew >> 2;
     const int bl = e >> 3, u0 = (e & 7) * 4;
     const int b = b0 + bl, j = j0 + u0;
     const bool valid = b < p.n_valid;
     const float inv_keep = 1.0f / p.keep;
-    constexpr uint32_t idesc = umma_idesc_bf16(128, REC_BG, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BG, 0, 0);
     float carry[4] = {0.f, 0.f, 0.f, 0.f};               // dh_{t+1} * z_{t+1}
     float accx[3][4], acch[4];                           // bias-gradient partial sums (dGh differs only in n)
 #pragma unroll
@@ -375,21 +396,21 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
 
     auto gather_partials = [&](int s_prev, float (&P)[4]) {
       // sum over the NS source CTAs of the partial for (trial bl, units u0..u0+3) published at step s_prev
-      const float* base = p.part + ((((size_t)(s_prev & 1) * NG + grp) * NS + slice) * NS) * 512 + bl * 32 + u0;
+      const float* base = p.part + ((((size_t)(s_prev & 1) * NG + grp) * NS + slice) * NS) * (BG * 32) + bl * 32 + u0;
       P[0] = P[1] = P[2] = P[3] = 0.f;
       for (int src = 0; src < NS; src += 4) {
         float4 v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (src + i < NS) v[i] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(src + i) * 512));
+          if (src + i < NS) v[i] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(src + i) * (BG * 32)));
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (src + i < NS) { P[0] += v[i].x; P[1] += v[i].y; P[2] += v[i].z; P[3] += v[i].w; }
       }
     };
 
-    for (int s = 0; s < p.T; ++s) {
-      const int t = p.T - 1 - s;
+    for (int s = 0; s < nsteps; ++s) {
+      const int t = p.t_end - 1 - s;
       const size_t row = (size_t)t * p.Bpad + b;
       const size_t off = row * p.H + j;
       float r[4], z[4], n[4], hn[4], hp[4];
@@ -411,6 +432,9 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
         gather_partials(s - 1, P);
 #pragma unroll
         for (int i = 0; i < 4; ++i) dh[i] = carry[i] + P[i] + dy[i];
+      } else if (!p.first_chunk) {                       // recurrent gradient handed over by the later chunk
+        const float4 c4 = *reinterpret_cast<const float4*>(p.dh_state + (size_t)b * p.H + j);
+        dh[0] = c4.x + dy[0]; dh[1] = c4.y + dy[1]; dh[2] = c4.z + dy[2]; dh[3] = c4.w + dy[3];
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) dh[i] = dy[i];
@@ -435,7 +459,7 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
         for (int g = 0; g < 3; ++g) {
           const int kk = g * 32 + u0;                    // 4 consecutive kk, 8 bytes
           const int chunk = kk >> 6, kl = kk & 63;
-          uint8_t* dst = sB + chunk * 2048 + bl * 128 + ((((kl >> 3) ^ (bl & 7)) & 7) << 4) + (kl & 7) * 2;
+          uint8_t* dst = sB + chunk * CHUNK_BYTES + bl * 128 + ((((kl >> 3) ^ (bl & 7)) & 7) << 4) + (kl & 7) * 2;
           __nv_bfloat162 lo = __floats2bfloat162_rn(gsel[g][0], gsel[g][1]), hi = __floats2bfloat162_rn(gsel[g][2], gsel[g][3]);
           uint2 u;
           u.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -445,15 +469,15 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       }
       fence_proxy_async_smem();                          // generic smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
-      epi_bar_sync();
+      epi_bar_sync<Cfg::kEpiThreads>();
       if (e == 0) {
         REC_TRACE(s, 2);
         tc_fence_after();
         const uint32_t sb = smem_u32(sB);
 #pragma unroll
         for (int ks = 0; ks < 6; ++ks) {                 // K = 96 = 6 x 16; the MB accumulators are independent chains
-          const uint64_t bdesc = umma_smem_desc(sb + (ks >> 2) * 2048 + (ks & 3) * 32, 16, 1024);
-          for (int mb = 0; mb < MB; ++mb) umma_bf16_ts(tmem_d + mb * 16, tmem_base + mb * 64 + ks * 8, bdesc, idesc, ks != 0 ? 1u : 0u);
+          const uint64_t bdesc = umma_smem_desc(sb + (ks >> 2) * CHUNK_BYTES + (ks & 3) * 32, 16, 1024);
+          for (int mb = 0; mb < MB; ++mb) umma_bf16_ts(tmem_d + mb * BG, tmem_base + mb * A_PITCH + ks * 8, bdesc, idesc, ks != 0 ? 1u : 0u);
         }
         umma_commit(bar_d);
         REC_TRACE(s, 3);
@@ -473,32 +497,32 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       // partial sums -> L2: lane = output unit within its 32-unit destination slice, one 128 B line per trial
       for (int mb = 0; mb < MB; ++mb) {
         uint32_t v[16];
-        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + mb * 16, v);
+        tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + mb * BG + chalf * 16, v);
         tmem_ld_wait();
         const int dest = mb * 4 + q;                     // destination slice = k / 32
         if (dest < NS) {
-          float* dst = p.part + ((((size_t)(s & 1) * NG + grp) * NS + dest) * NS + slice) * 512 + lane;
+          float* dst = p.part + ((((size_t)(s & 1) * NG + grp) * NS + dest) * NS + slice) * (BG * 32) + (chalf * 16) * 32 + lane;
 #pragma unroll
           for (int i = 0; i < 16; ++i) dst[i * 32] = __uint_as_float(v[i]);
         }
       }
       if (e == 0) REC_TRACE(s, 5);
       tc_fence_before();
-      epi_bar_sync();
+      epi_bar_sync<Cfg::kEpiThreads>();
       if (e == 0) {
-        red_release_add(&done[s], 1);
+        red_release_add(&done[t], 1);
         REC_TRACE(s, 6);
       }
     }
-    // gradient wrt the initial state: dh_{-1} = dh_0 * z_0 + dGh_0 W_hh
+    // recurrent gradient for the step before this chunk: dh_{t_begin-1} (rec) = dh_{t_begin} * z + dGh_{t_begin} W_hh
     {
-      mbar_wait(bar_f, (p.T - 1) & 1);
+      mbar_wait(bar_f, (nsteps - 1) & 1);
       float P[4];
-      gather_partials(p.T - 1, P);
+      gather_partials(nsteps - 1, P);
       float o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[i] = valid ? carry[i] + P[i] : 0.0f;
-      *reinterpret_cast<float4*>(p.dh0 + (size_t)b * p.H + j) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(p.dh_state + (size_t)b * p.H + j) = make_float4(o[0], o[1], o[2], o[3]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

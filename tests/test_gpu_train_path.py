@@ -86,8 +86,19 @@ def test_ctc_vs_golden(E, pkg, name):
     assert np.abs(got - rest["dlogits"]).max() < 1e-5 * max(1.0, np.abs(rest["dlogits"]).max() * 10)
 
 
+@pytest.fixture(params=["default", "chunks3_lanes2", "chunks2_lanes1"])
+def rec_schedule(request, monkeypatch):
+    """Recurrence schedules: default, and forced time-chunking / lane counts so that the chunk carry of h and dh and the
+    multi-stream wave-front are exercised on the small golden shapes too."""
+    if request.param == "chunks3_lanes2":
+        monkeypatch.setenv("B2T_REC_CHUNKS", "3"); monkeypatch.setenv("B2T_REC_LANES", "2")
+    elif request.param == "chunks2_lanes1":
+        monkeypatch.setenv("B2T_REC_CHUNKS", "2"); monkeypatch.setenv("B2T_REC_LANES", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("name", ["train_small.npz", "train_ragged.npz"])
-def test_train_step_vs_golden(E, name):
+def test_train_step_vs_golden(E, name, rec_schedule):
     """forward -> CTC -> backward -> clip+AdamW against the reference's own step (golden)."""
     import gru_ctc_oracle as O
     eng, cfg, params, grads, p1, rest = _engine_from_golden(E, name)
