@@ -147,6 +147,11 @@ int b2t_greedy_edit(b2t_engine* e, const int* labels, int Smax, const int* in_le
  * kernels records clock64() at eight points of every time step.  NULL disables. */
 int b2t_debug_set_trace(b2t_engine* e, long long* device_buf);
 
+/* Profiling aid: with enable != 0 every task of forward/backward/optimizer is bracketed by CUDA events (lane = side stream,
+ * 9 = caller's stream); b2t_debug_dump_timeline synchronises and writes "lane name start_us end_us" lines. */
+int b2t_debug_timeline(int enable);
+int b2t_debug_dump_timeline(char* buf, int cap);
+
 /* Number of kernels this library has launched on behalf of the calling process (bench accounting). */
 long long b2t_launch_count(void);
 

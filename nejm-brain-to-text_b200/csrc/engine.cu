@@ -158,14 +158,15 @@ struct b2t_engine {
   int BG = 16, n_tchunks = 1, n_lanes = 1;
   int tc_begin[MAX_CHUNKS + 1];
   bool plans_ok = false, use_unfold_copy = false;
-  GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw, p_in0, p_dx0;
-  std::vector<GemmPlan> p_dwih, p_dwhh;
+  GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw;
+  std::vector<GemmPlan> p_dwih, p_dwhh, p_dwih0;   // p_dwih0: layer-0 dW_ih per time chunk (accumulating)
   std::vector<std::vector<GemmPlan>> p_in, p_dx;     // [layer >= 1][chunk]
   std::vector<CUtensorMap> tm_h;
   // side streams / events of the wave-front
   cudaStream_t lane[MAX_LANES + 1] = {nullptr, nullptr, nullptr, nullptr};   // [MAX_LANES] = bulk stream (weight-gradient GEMMs)
   cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 1] = {nullptr, nullptr, nullptr, nullptr}, ev_top = nullptr;
   std::vector<cudaEvent_t> ev_r, ev_dx;              // [layer * MAX_CHUNKS + chunk]
+  cudaEvent_t ev_g0[MAX_CHUNKS] = {};                // layer-0 input projection chunks (issued ahead on the bulk stream)
   // state of the last forward
   bool have_fwd = false, have_dlogits = false, fwd_training = false;
   unsigned long long seed = 0;
@@ -173,6 +174,34 @@ struct b2t_engine {
   bool states_given = false;
   long long* trace = nullptr;   // optional device buffer [2][T'][8] for the recurrence cycle trace
 };
+
+// Optional timeline (B2T_TIMELINE=1): CUDA events around every task of a step, dumped by b2t_debug_dump_timeline.
+struct TlRec { std::string name; int lane; cudaEvent_t a, b; };
+static std::vector<TlRec> g_tl;
+static bool g_tl_on = false;
+struct TlScope {
+  cudaStream_t st; size_t idx; bool on;
+  TlScope(const char* name, int lane, cudaStream_t s) : st(s), idx(0), on(g_tl_on) {
+    if (!on) return;
+    TlRec r; r.name = name; r.lane = lane;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_tl.push_back(r); idx = g_tl.size() - 1;
+  }
+  ~TlScope() { if (on) cudaEventRecord(g_tl[idx].b, st); }
+};
+extern "C" int b2t_debug_timeline(int enable) { g_tl_on = enable != 0; for (auto& r : g_tl) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); } g_tl.clear(); return 0; }
+extern "C" int b2t_debug_dump_timeline(char* buf, int cap) {
+  cudaDeviceSynchronize();
+  int n = 0;
+  for (auto& r : g_tl) {
+    float t0 = 0, t1 = 0;
+    cudaEventElapsedTime(&t0, g_tl[0].a, r.a); cudaEventElapsedTime(&t1, g_tl[0].a, r.b);
+    n += snprintf(buf + n, cap - n > 0 ? cap - n : 0, "%d %s %.1f %.1f\n", r.lane, r.name.c_str(), t0 * 1e3, t1 * 1e3);
+    if (n >= cap) break;
+  }
+  return n;
+}
 
 static long long seg_off(const b2t_engine* e, const std::string& n) {
   for (auto& s : e->segs)
@@ -257,6 +286,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
   if (e->ev_top) cudaEventDestroy(e->ev_top);
   for (cudaEvent_t ev : e->ev_r) if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->ev_dx) if (ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : e->ev_g0) if (ev) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -291,6 +321,7 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
   for (size_t i = 0; i < e->ev_r.size() && ok; ++i)
     ok = cudaEventCreateWithFlags(&e->ev_r[i], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_dx[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < MAX_CHUNKS && ok; ++i) ok = cudaEventCreateWithFlags(&e->ev_g0[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { fail(B2T_ERR_CUDA, "stream/event creation failed"); b2t_engine_destroy(e); return nullptr; }
   if (training) {
     std::vector<Segment> hs;
@@ -369,25 +400,27 @@ static int build_plans(b2t_engine* e) {
     s.keep = 1.0f;
     if ((rc = gemm_plan_build(&e->p_day, s))) return fail(B2T_ERR_CUDA, "day-layer plan failed (%d)", rc);
   }
-  {  // layer-0 input projection over the whole sequence (does not depend on any recurrence)
+  // layer-0 input projection, one GEMM per time chunk so that the layer-0 recurrence can start after the first one
+  for (int c = 0; c < nch; ++c) {
+    const int t0 = e->tc_begin[c], nt = e->tc_begin[c + 1] - e->tc_begin[c];
     GemmSpec s;
     s.a_mn = 0; s.b_mn = 0; s.epi = EPI_STORE; s.out_bf16 = 0;
-    s.N = 3 * H; s.K = K0; s.ldb = K0; s.M = M;
+    s.N = 3 * H; s.K = K0; s.ldb = K0; s.M = (long long)nt * Bp;
     s.B = e->shadow + seg_off(e, "gru.weight_ih_l0");
-    s.C = e->lay[0].gx; s.ldc = 3 * H;
+    s.C = e->lay[0].gx + (size_t)t0 * Bp * 3 * H; s.ldc = 3 * H;
     s.bias = e->params + seg_off(e, "gru.bias_ih_l0");
     rc = -1;
     if (!e->use_unfold_copy) {   // strided patch view of xd (rnn_model.py:106-119), never materialised
-      s.A = e->xd; s.a_rin = Bp; s.a_rout = Tp; s.a_rin_stride = (long long)T * D; s.a_rout_stride = (long long)e->stride * D;
-      rc = gemm_plan_build(&e->p_in0, s);
+      s.A = e->xd + (size_t)t0 * e->stride * D; s.a_rin = Bp; s.a_rout = nt; s.a_rin_stride = (long long)T * D; s.a_rout_stride = (long long)e->stride * D;
+      rc = gemm_plan_build(&e->p_in[0][c], s);
       if (rc) {
         fprintf(stderr, "b2t: strided patch tensor map rejected (%d); falling back to a materialised unfold\n", rc);
         e->use_unfold_copy = true;
       }
     }
     if (e->use_unfold_copy) {
-      s.a_rin = 0; s.A = e->xu; s.lda = K0;
-      if ((rc = gemm_plan_build(&e->p_in0, s))) return fail(B2T_ERR_CUDA, "L0 input plan failed (%d)", rc);
+      s.a_rin = 0; s.A = e->xu + (size_t)t0 * Bp * K0; s.lda = K0;
+      if ((rc = gemm_plan_build(&e->p_in[0][c], s))) return fail(B2T_ERR_CUDA, "L0 input plan failed (%d)", rc);
     }
   }
   for (int l = 0; l < L; ++l) {
@@ -437,25 +470,32 @@ static int build_plans(b2t_engine* e) {
   }
   for (int l = 0; l < L; ++l) {
     const std::string sl = std::to_string(l);
-    {  // dW_ih = dGx^T X
+    if (l == 0) {   // dW_ih0 = sum over time chunks of dGx0[chunk]^T X_unf[chunk]: chunk GEMMs fill idle SMs while the last recurrences run
+      e->p_dwih0.assign(nch, GemmPlan());
+      for (int c = 0; c < nch; ++c) {
+        const int t0 = e->tc_begin[c], nt = e->tc_begin[c + 1] - e->tc_begin[c];
+        GemmSpec s;
+        s.a_mn = 1; s.b_mn = 1; s.epi = (c == nch - 1) ? EPI_STORE : EPI_ACCUM;    // the LAST time chunk is computed first and initialises the buffer
+        s.M = 3 * H; s.K = (long long)nt * Bp; s.N = K0; s.ldc = K0;
+        s.A = e->lay[0].dGx + (size_t)t0 * Bp * 3 * H; s.lda = 3 * H;
+        s.C = e->grads + seg_off(e, "gru.weight_ih_l0");
+        if (!e->use_unfold_copy) {
+          s.k_rin = Bp; s.k_rout = nt;
+          s.a_rin_stride = 3 * H; s.a_rout_stride = (long long)Bp * 3 * H;
+          s.B = e->xd + (size_t)t0 * e->stride * D; s.b_rin_stride = (long long)T * D; s.b_rout_stride = (long long)e->stride * D;
+        } else {
+          s.B = e->xu + (size_t)t0 * Bp * K0; s.ldb = K0;
+        }
+        if ((rc = gemm_plan_build(&e->p_dwih0[c], s))) return fail(B2T_ERR_CUDA, "dW_ih0 plan %d failed (%d)", c, rc);
+      }
+    } else {  // dW_ih = dGx^T X
       GemmSpec s;
       s.a_mn = 1; s.b_mn = 1; s.epi = EPI_STORE;
       s.M = 3 * H; s.K = M;
       s.A = e->lay[l].dGx; s.lda = 3 * H;
       s.C = e->grads + seg_off(e, "gru.weight_ih_l" + sl);
-      if (l == 0) {
-        s.N = K0; s.ldc = K0;
-        if (!e->use_unfold_copy) {
-          s.k_rin = Bp; s.k_rout = Tp;
-          s.a_rin_stride = 3 * H; s.a_rout_stride = (long long)Bp * 3 * H;
-          s.B = e->xd; s.b_rin_stride = (long long)T * D; s.b_rout_stride = (long long)e->stride * D;
-        } else {
-          s.B = e->xu; s.ldb = K0;
-        }
-      } else {
-        s.N = H; s.ldc = H; s.ldb = H;
-        s.B = e->lay[l - 1].hdrop ? e->lay[l - 1].hdrop : e->lay[l - 1].hseq + (size_t)Bp * H;
-      }
+      s.N = H; s.ldc = H; s.ldb = H;
+      s.B = e->lay[l - 1].hdrop ? e->lay[l - 1].hdrop : e->lay[l - 1].hseq + (size_t)Bp * H;
       if ((rc = gemm_plan_build(&e->p_dwih[l], s))) return fail(B2T_ERR_CUDA, "dW_ih plan %d failed (%d)", l, rc);
     }
     {  // dW_hh = dGh^T H_prev   (H_prev = hseq slots 0..T-1)
@@ -466,23 +506,15 @@ static int build_plans(b2t_engine* e) {
       s.C = e->grads + seg_off(e, "gru.weight_hh_l" + sl); s.ldc = H;
       if ((rc = gemm_plan_build(&e->p_dwhh[l], s))) return fail(B2T_ERR_CUDA, "dW_hh plan %d failed (%d)", l, rc);
     }
-    if (l == 0) {  // dX_unf = dGx W_ih (whole sequence), folded afterwards
+    for (int c = 0; c < nch; ++c) {   // data gradient per time chunk: dX_unf (l == 0, folded afterwards) or dY_{l-1} = dGx_l W_ih_l
+      const long long r0 = (long long)e->tc_begin[c] * Bp, rows = (long long)(e->tc_begin[c + 1] - e->tc_begin[c]) * Bp;
       GemmSpec s;
       s.a_mn = 0; s.b_mn = 1; s.epi = EPI_STORE;
-      s.M = M; s.K = 3 * H; s.A = e->lay[0].dGx; s.lda = 3 * H;
-      s.B = e->shadow + seg_off(e, "gru.weight_ih_l0");
-      s.N = K0; s.ldb = K0; s.out_bf16 = 1; s.C = e->dxu; s.ldc = K0;
-      if ((rc = gemm_plan_build(&e->p_dx0, s))) return fail(B2T_ERR_CUDA, "dX plan 0 failed (%d)", rc);
-    } else {
-      for (int c = 0; c < nch; ++c) {   // dY_{l-1}[chunk] = dGx_l[chunk] W_ih_l
-        const long long r0 = (long long)e->tc_begin[c] * Bp, rows = (long long)(e->tc_begin[c + 1] - e->tc_begin[c]) * Bp;
-        GemmSpec s;
-        s.a_mn = 0; s.b_mn = 1; s.epi = EPI_STORE;
-        s.M = rows; s.K = 3 * H; s.A = e->lay[l].dGx + r0 * 3 * H; s.lda = 3 * H;
-        s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
-        s.N = H; s.ldb = H; s.out_bf16 = 0; s.C = e->lay[l - 1].dY + r0 * H; s.ldc = H;
-        if ((rc = gemm_plan_build(&e->p_dx[l][c], s))) return fail(B2T_ERR_CUDA, "dX plan %d/%d failed (%d)", l, c, rc);
-      }
+      s.M = rows; s.K = 3 * H; s.A = e->lay[l].dGx + r0 * 3 * H; s.lda = 3 * H;
+      s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
+      if (l == 0) { s.N = K0; s.ldb = K0; s.out_bf16 = 1; s.C = e->dxu + r0 * K0; s.ldc = K0; }
+      else { s.N = H; s.ldb = H; s.out_bf16 = 0; s.C = e->lay[l - 1].dY + r0 * H; s.ldc = H; }
+      if ((rc = gemm_plan_build(&e->p_dx[l][c], s))) return fail(B2T_ERR_CUDA, "dX plan %d/%d failed (%d)", l, c, rc);
     }
   }
   {  // dW_day[day_b] += xs[b]^T dpre[b]
@@ -605,16 +637,16 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
   pp.seed = a->seed; pp.rng_offset = 0;
   {
     dim3 g((a->T + PRE_TT - 1) / PRE_TT, Bp);
+    TlScope tl("pre", 9, st);
     pre_smooth_kernel<<<g, D / 4, 0, st>>>(pp);
     CK(LAUNCHED());
   }
   e->p_day.p.keep = keep_in; e->p_day.p.seed = a->seed; e->p_day.p.rng_offset = 0;
-  CK(gemm_run(e->p_day, st)); ++g_launches;
+  { TlScope tl("day", 9, st); CK(gemm_run(e->p_day, st)); ++g_launches; }
   if (e->use_unfold_copy) {
     unfold_kernel<<<num_sms() * 4, 256, 0, st>>>(e->xd, e->xu, Bp, a->T, D, Tp, e->patch, e->stride);
     CK(LAUNCHED());
   }
-  CK(gemm_run(e->p_in0, st)); ++g_launches;
   CK(cudaMemsetAsync(e->done_all, 0, e->done_elems * sizeof(int), st));
   for (int l = 0; l < L; ++l) {
     init_state_kernel<<<(Bp * H + 255) / 256, 256, 0, st>>>(e->params + seg_off(e, "h0"), a->states ? a->states + (size_t)l * a->B * H : nullptr,
@@ -622,19 +654,38 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
     CK(LAUNCHED());
   }
   CK(cudaEventRecord(e->ev_start, st));
-  for (int i = 0; i < NL; ++i) CK(cudaStreamWaitEvent(e->lane[i], e->ev_start, 0));
+  for (int i = 0; i <= MAX_LANES; ++i) CK(cudaStreamWaitEvent(e->lane[i], e->ev_start, 0));
+  // layer-0 input projection: all chunks up front on the bulk stream (they depend on no recurrence)
+  for (int c = 0; c < nch; ++c) {
+    TlScope tl(("G0." + std::to_string(c)).c_str(), 3, e->lane[MAX_LANES]);
+    CK(gemm_run(e->p_in[0][c], e->lane[MAX_LANES])); ++g_launches;
+    CK(cudaEventRecord(e->ev_g0[c], e->lane[MAX_LANES]));
+  }
 
-  // 4. GRU stack, wave-front over (layer, chunk)
+  // 4. GRU stack: wave-front over (layer, chunk).  Task (l, c) = input projection of chunk c (l > 0: needs chunk c of the layer
+  //    below) + recurrence over chunk c (needs chunk c-1 of the same layer).  Tasks are list-scheduled onto the lane that
+  //    frees first (estimated durations), dependencies are CUDA events, issue order is diagonal by diagonal.
   const bool save = a->training != 0;
+  double lane_free[MAX_LANES] = {0, 0, 0};
+  std::vector<double> t_end((size_t)L * MAX_CHUNKS, 0.0);
+  const double dur_g = 40.0, dur_r = 135.0;
   for (int d = 0; d < nch + L - 1; ++d) {
     for (int l = 0; l < L; ++l) {
       const int c = d - l;
       if (c < 0 || c >= nch) continue;
-      cudaStream_t ls = e->lane[l % NL];
-      if (l > 0) {
-        CK(cudaStreamWaitEvent(ls, e->ev_r[(size_t)(l - 1) * MAX_CHUNKS + c], 0));
-        CK(gemm_run(e->p_in[l][c], ls)); ++g_launches;
-      }
+      double ready = 0.0;
+      if (l > 0) ready = std::max(ready, t_end[(size_t)(l - 1) * MAX_CHUNKS + c]);
+      if (c > 0) ready = std::max(ready, t_end[(size_t)l * MAX_CHUNKS + c - 1]);
+      int li = 0;
+      for (int i = 1; i < NL; ++i)
+        if (std::max(lane_free[i], ready) < std::max(lane_free[li], ready) - 1e-9) li = i;
+      const double start = std::max(lane_free[li], ready);
+      lane_free[li] = t_end[(size_t)l * MAX_CHUNKS + c] = start + (l == 0 ? 0.0 : dur_g) + dur_r;
+      cudaStream_t ls = e->lane[li];
+      if (l > 0) CK(cudaStreamWaitEvent(ls, e->ev_r[(size_t)(l - 1) * MAX_CHUNKS + c], 0));
+      if (c > 0) CK(cudaStreamWaitEvent(ls, e->ev_r[(size_t)l * MAX_CHUNKS + c - 1], 0));
+      if (l == 0) CK(cudaStreamWaitEvent(ls, e->ev_g0[c], 0));
+      else { TlScope tl(("G" + std::to_string(l) + "." + std::to_string(c)).c_str(), li, ls); CK(gemm_run(e->p_in[l][c], ls)); ++g_launches; }
       RecFwdParams rp;
       rp.H = H; rp.Bpad = Bp; rp.t_begin = e->tc_begin[c]; rp.t_end = e->tc_begin[c + 1]; rp.T = Tp; rp.n_slices = H / 32;
       rp.gx = e->lay[l].gx; rp.bhh = e->params + seg_off(e, "gru.bias_hh_l" + std::to_string(l));
@@ -647,17 +698,18 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
       rp.trace = (l == 0) ? e->trace : nullptr;
       // eval-mode forward through a training engine: the next layer reads hdrop if it exists, so keep it in sync
       if (!save && e->lay[l].hdrop) { rp.hdrop = e->lay[l].hdrop; rp.keep = 1.0f; }
-      CK(launch_rec_fwd(BG, e->tm_h[l], rp, grid, ls));
+      { TlScope tl(("R" + std::to_string(l) + "." + std::to_string(c)).c_str(), li, ls); CK(launch_rec_fwd(BG, e->tm_h[l], rp, grid, ls)); }
       CK(cudaEventRecord(e->ev_r[(size_t)l * MAX_CHUNKS + c], ls));
     }
   }
   // join: the user stream continues after the top layer's last chunk (which transitively follows everything else)
-  for (int i = 0; i < NL; ++i) {
+  for (int i = 0; i <= MAX_LANES; ++i) {
+    if (i < MAX_LANES && i >= NL) continue;
     CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
     CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));
   }
   // 5. head
-  CK(gemm_run(e->p_head, st)); ++g_launches;
+  { TlScope tl("head", 9, st); CK(gemm_run(e->p_head, st)); ++g_launches; }
   if (a->logits_out) {
     gather_logits_kernel<<<num_sms() * 2, 256, 0, st>>>(e->logits, Tp, a->B, Bp, LDL, e->C, a->logits_out);
     CK(LAUNCHED());
@@ -720,7 +772,8 @@ extern "C" int b2t_ctc_loss(b2t_engine* e, const int* labels, int Smax, const in
     CK(cudaMemsetAsync(e->dlog16, 0, (size_t)e->M * LDL * sizeof(__nv_bfloat16), st));
     CK(cudaMemsetAsync(e->dlog32, 0, (size_t)e->M * LDL * sizeof(float), st));
   }
-  int rc = run_ctc(cp, e->B, st);
+  int rc;
+  { TlScope tl("ctc", 9, st); rc = run_ctc(cp, e->B, st); }
   if (rc) return rc;
   if (want_grad) e->have_dlogits = true;
   return 0;
@@ -776,21 +829,34 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   // head
   colsum_kernel<<<64, 64, 0, st>>>(e->dlog32, (size_t)e->M, LDL, e->C, e->grads + seg_off(e, "out.bias"));
   CK(LAUNCHED());
-  CK(gemm_run(e->p_dwout, st)); ++g_launches;
-  CK(gemm_run(e->p_dytop, st)); ++g_launches;
+  { TlScope tl("dWout", 9, st); CK(gemm_run(e->p_dwout, st)); ++g_launches; }
+  { TlScope tl("dYtop", 9, st); CK(gemm_run(e->p_dytop, st)); ++g_launches; }
   CK(cudaEventRecord(e->ev_top, st));
   for (int i = 0; i < NL; ++i) CK(cudaStreamWaitEvent(e->lane[i], e->ev_top, 0));
   CK(cudaStreamWaitEvent(e->lane[MAX_LANES], e->ev_top, 0));
 
-  // wave-front over (layer descending, time chunk descending); k counts chunks from the end of the sequence
+  // wave-front over (layer descending, time chunk descending); k counts chunks from the end of the sequence.
+  // Task (l, c) = recurrence over chunk c (needs chunk c+1 of the same layer and dY_l[chunk c] from the layer above)
+  // followed by the data-gradient GEMM for the layer below.  Same list scheduling as in forward.
+  double lane_free[MAX_LANES] = {0, 0, 0};
+  std::vector<double> t_end((size_t)L * MAX_CHUNKS, 0.0);
+  const double dur_rb = 215.0, dur_dx = 25.0;
   for (int d = 0; d < nch + L - 1; ++d) {
     for (int l = L - 1; l >= 0; --l) {
       const int k = d - (L - 1 - l);
       if (k < 0 || k >= nch) continue;
       const int c = nch - 1 - k;
       const std::string sl = std::to_string(l);
-      cudaStream_t ls = e->lane[l % NL];
+      double ready = 0.0;
+      if (l < L - 1) ready = std::max(ready, t_end[(size_t)(l + 1) * MAX_CHUNKS + c]);
+      if (c < nch - 1) ready = std::max(ready, t_end[(size_t)l * MAX_CHUNKS + c + 1]);
+      int li = 0;
+      for (int i = 1; i < NL; ++i)
+        if (std::max(lane_free[i], ready) < std::max(lane_free[li], ready) - 1e-9) li = i;
+      lane_free[li] = t_end[(size_t)l * MAX_CHUNKS + c] = std::max(lane_free[li], ready) + dur_rb + (l > 0 ? dur_dx : 0.0);
+      cudaStream_t ls = e->lane[li];
       if (l < L - 1) CK(cudaStreamWaitEvent(ls, e->ev_dx[(size_t)(l + 1) * MAX_CHUNKS + c], 0));   // dY_l[chunk c] is ready
+      if (c < nch - 1) CK(cudaStreamWaitEvent(ls, e->ev_dx[(size_t)l * MAX_CHUNKS + c + 1], 0));    // chunk c+1 of this layer is done
       RecBwdParams bp;
       bp.H = H; bp.Bpad = Bp; bp.n_slices = H / 32; bp.T = Tp;
       bp.t_begin = e->tc_begin[c]; bp.t_end = e->tc_begin[c + 1]; bp.first_chunk = (c == nch - 1);
@@ -804,31 +870,33 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       bp.keep = (l < L - 1) ? keep_rnn : 1.0f;
       bp.seed = e->seed; bp.rng_offset = (unsigned long long)(l + 1) << 40;
       bp.trace = (l == L - 1 && c == nch - 1 && e->trace) ? e->trace + (size_t)Tp * 8 : nullptr;
-      CK(launch_rec_bwd(BG, bp, grid, ls));
-      if (l > 0) {
-        CK(gemm_run(e->p_dx[l][c], ls)); ++g_launches;
-        CK(cudaEventRecord(e->ev_dx[(size_t)l * MAX_CHUNKS + c], ls));
+      { TlScope tl(("RB" + sl + "." + std::to_string(c)).c_str(), li, ls); CK(launch_rec_bwd(BG, bp, grid, ls)); }
+      if (l > 0) { TlScope tl(("DX" + sl + "." + std::to_string(c)).c_str(), li, ls); CK(gemm_run(e->p_dx[l][c], ls)); ++g_launches; }
+      CK(cudaEventRecord(e->ev_dx[(size_t)l * MAX_CHUNKS + c], ls));
+      if (l == 0) {   // layer 0: data gradient (to be folded) and weight gradient of this chunk fill idle SMs on the bulk stream
+        cudaStream_t bs = e->lane[MAX_LANES];
+        CK(cudaStreamWaitEvent(bs, e->ev_dx[(size_t)c], 0));
+        { TlScope tl(("DX0." + std::to_string(c)).c_str(), 3, bs); CK(gemm_run(e->p_dx[0][c], bs)); ++g_launches; }
+        { TlScope tl(("dWih0." + std::to_string(c)).c_str(), 3, bs); CK(gemm_run(e->p_dwih0[c], bs)); ++g_launches; }
       }
       if (c == 0) {   // the layer's recurrence is complete: weight gradients over the whole sequence, on the bulk stream
         cudaStream_t bs = e->lane[MAX_LANES];
         CK(cudaEventRecord(e->ev_r[(size_t)l * MAX_CHUNKS], ls));
         CK(cudaStreamWaitEvent(bs, e->ev_r[(size_t)l * MAX_CHUNKS], 0));
-        CK(gemm_run(e->p_dwih[l], bs)); ++g_launches;
-        CK(gemm_run(e->p_dwhh[l], bs)); ++g_launches;
+        if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 3, bs); CK(gemm_run(e->p_dwih[l], bs)); ++g_launches; }
+        { TlScope tl(("dWhh" + sl).c_str(), 3, bs); CK(gemm_run(e->p_dwhh[l], bs)); ++g_launches; }
         if (!e->states_given) {
           reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bs>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
           CK(LAUNCHED());
         }
         if (l == 0) {   // patch fold + day layer
-          CK(gemm_run(e->p_dx0, bs)); ++g_launches;
           FoldParams fp;
           fp.dxu = e->dxu; fp.xd = e->xd; fp.dpre = e->dpre; fp.dbias_day = e->grads + seg_off(e, "day_biases.0"); fp.bias_pitch = (int)r64(D);
           fp.day_idx = e->day_idx; fp.B = e->B; fp.Bpad = Bp; fp.T_alloc = e->T_in; fp.T_valid = e->T_out; fp.D = D; fp.Tp = Tp;
           fp.patch = e->patch; fp.stride = e->stride; fp.keep = keep_in; fp.seed = e->seed; fp.rng_offset = 0;
           dim3 g((e->T_in + FOLD_TT - 1) / FOLD_TT, Bp);
-          fold_dpre_kernel<<<g, D / 4, 0, bs>>>(fp);
-          CK(LAUNCHED());
-          CK(gemm_run(e->p_daydw, bs)); ++g_launches;
+          { TlScope tl("fold", 3, bs); fold_dpre_kernel<<<g, D / 4, 0, bs>>>(fp); CK(LAUNCHED()); }
+          { TlScope tl("daydW", 3, bs); CK(gemm_run(e->p_daydw, bs)); ++g_launches; }
         }
       }
     }
@@ -856,6 +924,7 @@ extern "C" int b2t_optimizer_step(b2t_engine* e, const b2t_adamw_args* a, float*
   ap.sumsq = e->sumsq; ap.stats = e->stats; ap.max_norm = a->max_grad_norm;
   for (int i = 0; i < 3; ++i) { ap.lr[i] = a->lr[i]; ap.wd[i] = a->weight_decay[i]; }
   ap.beta1 = a->beta1; ap.beta2 = a->beta2; ap.eps = a->eps;
+  TlScope tl_adam("adamw", 9, st);
   clip_adamw_kernel<<<e->n_chunks, 256, 0, st>>>(ap);
   CK(LAUNCHED());
   bump_steps_kernel<<<((int)e->segs.size() + 127) / 128, 128, 0, st>>>(e->d_segs, (int)e->segs.size(), e->touched, e->steps);

@@ -42,6 +42,7 @@ cudaError_t gemm_run(const GemmPlan& pl, cudaStream_t st) {
     case 2 | (EPI_DAY << 2) | 16: return launch_variant<false, true, EPI_DAY, __nv_bfloat16>(pl, st);
     case 3 | (EPI_STORE << 2): return launch_variant<true, true, EPI_STORE, float>(pl, st);
     case 3 | (EPI_ATOMIC << 2): return launch_variant<true, true, EPI_ATOMIC, float>(pl, st);
+    case 3 | (EPI_ACCUM << 2): return launch_variant<true, true, EPI_ACCUM, float>(pl, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -230,6 +230,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
+          if (EPI == EPI_ACCUM) {
+            float* cf = reinterpret_cast<float*>(crow) + n0;
+            if (ncols >= 32 && vec_ok) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 o = reinterpret_cast<const float4*>(cf)[i];
+                f[4 * i] += o.x; f[4 * i + 1] += o.y; f[4 * i + 2] += o.z; f[4 * i + 3] += o.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < ncols) f[i] += cf[i];
+            }
+          }
           if (EPI == EPI_ATOMIC) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)

@@ -2,7 +2,7 @@
 #pragma once
 namespace b2t {
 
-enum { EPI_STORE = 0, EPI_DAY = 1, EPI_ATOMIC = 2 };
+enum { EPI_STORE = 0, EPI_DAY = 1, EPI_ATOMIC = 2, EPI_ACCUM = 3 };   // ACCUM: C += A*B (each tile owned by one CTA)
 
 struct GemmParams {
   int M, N;                 // output extent per problem (M only used for MN-major A)

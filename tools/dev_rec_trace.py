@@ -7,12 +7,12 @@ import b2t_pkg, bench
 E = b2t_pkg.submodule("engine"); N = b2t_pkg.load()._native
 from torch_cpu_port import PortModel
 torch.manual_seed(0)
+os.environ.setdefault("B2T_REC_CHUNKS", "1")
 cfg = E.make_config(**bench.CFG)
 flat = E.flat_from_state_dict(cfg, PortModel(**bench.CFG).state_dict()).cuda()
 eng = E.Engine(cfg, flat, max_batch=64, max_T=400, max_label_len=64, training=True)
 hb = {k: v.cuda() for k, v in bench.synth_batches(1, 1)[0].items()}
 in_len = torch.full((64,), 97, dtype=torch.int32)
-os.environ.setdefault("B2T_REC_CHUNKS", "1")
 Tp = 97
 trace = torch.zeros(2 * Tp * 8, dtype=torch.int64, device="cuda")
 N.check(N.lib.b2t_debug_set_trace(eng.handle, trace.data_ptr()), "trace")
