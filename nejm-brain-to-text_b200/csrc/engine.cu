@@ -131,7 +131,7 @@ constexpr int MAX_LANES = 3;   // concurrent recurrence launches (side streams)
 struct LayerBuf {
   __nv_bfloat16 *hseq, *hdrop, *R, *Z, *Nn, *HN, *dGx, *dGh;
   float *gx, *dY, *part, *h_state, *dh_state;
-  int *done_f, *done_b;
+  int gen = 0;                                       // backward partial-exchange generation (mod 8), advanced per launch
 };
 
 struct b2t_engine {
@@ -146,8 +146,8 @@ struct b2t_engine {
   __nv_bfloat16 *xs, *xd, *xu, *dxu, *dpre, *dlog16;
   float *logits, *dlog32, *alpha;
   std::vector<LayerBuf> lay;
-  int *done_all, *steps, *greedy_scratch;
-  size_t done_elems = 0;
+  int *steps, *greedy_scratch;
+  int part_geom = -1;
   float *sumsq, *stats;
   Segment* d_segs;
   ChunkRef* d_chunks;
@@ -222,8 +222,6 @@ static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
   e->xd = c.take<__nv_bfloat16>((size_t)Bp * T * D);
   e->xu = c.take<__nv_bfloat16>(M * e->K0);
   e->lay.resize(L);
-  e->done_elems = (size_t)2 * L * NG * Tq;
-  e->done_all = c.take<int>(e->done_elems + 16);
   for (int l = 0; l < L; ++l) {
     LayerBuf& b = e->lay[l];
     b.gx = c.take<float>(M * 3 * H);
@@ -234,8 +232,6 @@ static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
     b.Nn = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
     b.HN = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
     b.h_state = c.take<float>((size_t)Bp * H);
-    b.done_f = dry ? nullptr : e->done_all + (size_t)(2 * l) * NG * Tq;
-    b.done_b = dry ? nullptr : e->done_all + (size_t)(2 * l + 1) * NG * Tq;
     b.dGx = b.dGh = nullptr; b.dY = b.part = b.dh_state = nullptr;
     if (tr) {
       b.dGx = c.take<__nv_bfloat16>(M * 3 * H);
@@ -565,12 +561,13 @@ extern "C" int b2t_output_frames(const b2t_config* cfg, int T, int smooth_mode, 
 // co-resident (they spin on each other's flags).
 constexpr size_t REC_SMEM_BYTES = 120 * 1024;
 template <int BG>
-static cudaError_t launch_rec_fwd_t(const CUtensorMap& tm, const RecFwdParams& p, int grid, cudaStream_t st) {
-  cudaError_t err = cudaFuncSetAttribute(gru_rec_fwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM_BYTES);
+static cudaError_t launch_rec_fwd_t(const RecFwdParams& p, int grid, cudaStream_t st) {
+  const size_t smem = std::max(REC_SMEM_BYTES, RecCfg<BG>::fwd_smem_bytes(p.H));
+  cudaError_t err = cudaFuncSetAttribute(gru_rec_fwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  void* args[2] = {(void*)&tm, (void*)&p};
+  void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_rec_fwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kThreads), args, REC_SMEM_BYTES, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_rec_fwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kFwdThreads), args, smem, st);
 }
 template <int BG>
 static cudaError_t launch_rec_bwd_t(const RecBwdParams& p, int grid, cudaStream_t st) {
@@ -578,10 +575,10 @@ static cudaError_t launch_rec_bwd_t(const RecBwdParams& p, int grid, cudaStream_
   if (err != cudaSuccess) return err;
   void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kThreads), args, REC_SMEM_BYTES, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kBwdThreads), args, REC_SMEM_BYTES, st);
 }
-static cudaError_t launch_rec_fwd(int BG, const CUtensorMap& tm, const RecFwdParams& p, int grid, cudaStream_t st) {
-  return BG == 32 ? launch_rec_fwd_t<32>(tm, p, grid, st) : launch_rec_fwd_t<16>(tm, p, grid, st);
+static cudaError_t launch_rec_fwd(int BG, const RecFwdParams& p, int grid, cudaStream_t st) {
+  return BG == 32 ? launch_rec_fwd_t<32>(p, grid, st) : launch_rec_fwd_t<16>(p, grid, st);
 }
 static cudaError_t launch_rec_bwd(int BG, const RecBwdParams& p, int grid, cudaStream_t st) {
   return BG == 32 ? launch_rec_bwd_t<32>(p, grid, st) : launch_rec_bwd_t<16>(p, grid, st);
@@ -647,8 +644,9 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
     unfold_kernel<<<num_sms() * 4, 256, 0, st>>>(e->xd, e->xu, Bp, a->T, D, Tp, e->patch, e->stride);
     CK(LAUNCHED());
   }
-  CK(cudaMemsetAsync(e->done_all, 0, e->done_elems * sizeof(int), st));
   for (int l = 0; l < L; ++l) {
+    // "not written yet" sentinel for the recurrence's data-as-signal exchange (gru_rec.cuh); slot 0 is the initial state
+    CK(cudaMemsetAsync(e->lay[l].hseq + (size_t)Bp * H, 0xFF, (size_t)Tp * Bp * H * sizeof(__nv_bfloat16), st));
     init_state_kernel<<<(Bp * H + 255) / 256, 256, 0, st>>>(e->params + seg_off(e, "h0"), a->states ? a->states + (size_t)l * a->B * H : nullptr,
                                                              a->B, Bp, H, e->lay[l].hseq, e->lay[l].h_state);
     CK(LAUNCHED());
@@ -694,11 +692,11 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
       rp.hdrop = save ? e->lay[l].hdrop : nullptr;
       rp.R = save ? e->lay[l].R : nullptr; rp.Z = save ? e->lay[l].Z : nullptr;
       rp.Nn = save ? e->lay[l].Nn : nullptr; rp.HN = save ? e->lay[l].HN : nullptr;
-      rp.done = e->lay[l].done_f; rp.keep = keep_rnn; rp.seed = a->seed; rp.rng_offset = (unsigned long long)(l + 1) << 40;
+      rp.keep = keep_rnn; rp.seed = a->seed; rp.rng_offset = (unsigned long long)(l + 1) << 40;
       rp.trace = (l == 0) ? e->trace : nullptr;
       // eval-mode forward through a training engine: the next layer reads hdrop if it exists, so keep it in sync
       if (!save && e->lay[l].hdrop) { rp.hdrop = e->lay[l].hdrop; rp.keep = 1.0f; }
-      { TlScope tl(("R" + std::to_string(l) + "." + std::to_string(c)).c_str(), li, ls); CK(launch_rec_fwd(BG, e->tm_h[l], rp, grid, ls)); }
+      { TlScope tl(("R" + std::to_string(l) + "." + std::to_string(c)).c_str(), li, ls); CK(launch_rec_fwd(BG, rp, grid, ls)); }
       CK(cudaEventRecord(e->ev_r[(size_t)l * MAX_CHUNKS + c], ls));
     }
   }
@@ -824,7 +822,13 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   for (int l = 0; l < L; ++l)
     CK(cudaMemsetAsync(e->grads + seg_off(e, "gru.bias_ih_l" + std::to_string(l)), 0, (size_t)2 * r64(3 * H) * sizeof(float), st));
   CK(cudaMemsetAsync(e->grads + seg_off(e, "out.bias"), 0, (size_t)(r64(e->C) + r64(H)) * sizeof(float), st));
-  CK(cudaMemsetAsync(e->done_all, 0, e->done_elems * sizeof(int), st));
+  if (e->part_geom != Bp * 64 + BG) {   // partial-exchange buffers: (re)start the generation tags (gru_rec.cuh) for this geometry
+    for (int l = 0; l < L; ++l) {
+      CK(cudaMemsetAsync(e->lay[l].part, 0xFF, (size_t)2 * Bp * (H / 32) * (H / 32) * 32 * sizeof(float), st));
+      e->lay[l].gen = 0;
+    }
+    e->part_geom = Bp * 64 + BG;
+  }
 
   // head
   colsum_kernel<<<64, 64, 0, st>>>(e->dlog32, (size_t)e->M, LDL, e->C, e->grads + seg_off(e, "out.bias"));
@@ -866,7 +870,8 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       bp.dGx = e->lay[l].dGx; bp.dGh = e->lay[l].dGh; bp.part = e->lay[l].part;
       bp.dbih = e->grads + seg_off(e, "gru.bias_ih_l" + sl); bp.dbhh = e->grads + seg_off(e, "gru.bias_hh_l" + sl);
       bp.dh_state = e->lay[l].dh_state;
-      bp.done = e->lay[l].done_b; bp.n_valid = e->B;
+      bp.n_valid = e->B;
+      bp.gen_base = e->lay[l].gen; e->lay[l].gen = (e->lay[l].gen + (bp.t_end - bp.t_begin)) & 7;
       bp.keep = (l < L - 1) ? keep_rnn : 1.0f;
       bp.seed = e->seed; bp.rng_offset = (unsigned long long)(l + 1) << 40;
       bp.trace = (l == L - 1 && c == nch - 1 && e->trace) ? e->trace + (size_t)Tp * 8 : nullptr;

@@ -20,12 +20,21 @@
 //             group exchange fp32 partials through L2 (reduce-scatter) once per step.
 //
 // Measured on B200 (profiles/r1_mma_dispatch_microbench.md): a tcgen05.mma with N <= 64 costs a fixed ~50 cycles,
-// so the step is bound by the NUMBER of MMAs (48 forward, 36 backward) and by the publish/acquire round trip through
+// so the step is bound by the NUMBER of MMAs (48 forward, 36 backward) and by the exchange round trip through
 // L2, not by N.  BG = 32 therefore costs the same per step as BG = 16 but needs half the CTAs (48 for H = 768,
 // B = 64), which lets the engine run the chunks of up to three layers concurrently (wave-front over layers and
 // time chunks, see engine.cu).  A chunk [t_begin, t_end) carries its state in fp32 (h / dh) between launches.
-// Trials are independent, so only the H/32 CTAs of one batch group synchronise per step, through a
-// release/acquire counter in global memory (cooperative launch guarantees co-residency).
+//
+// Per-step exchange.  Trials are independent, so only the H/32 CTAs of one batch group exchange data.  There is no
+// flag and no fence on that path: the DATA is the signal.  Every 32-bit word is written by one relaxed gpu-scope
+// store and polled with relaxed gpu-scope loads (each word is single-copy atomic, the consumer only uses words it
+// has itself observed as valid, and what it does with them is data-dependent on those loads):
+//   forward : hseq slots are pre-filled with the bf16 pair 0xFFFF'FFFF (a NaN pattern cvt.rn never produces) by the
+//             engine; loader warps poll the BG x H block of h_{t-1} until no word is the sentinel and stage it in
+//             shared memory (manual 128B swizzle) as the B operand.
+//   backward: the two low mantissa bits of every fp32 partial carry a generation tag ((step >> 1) & 3; the buffer is
+//             double-buffered on step & 1), so a stale word is never mistaken for a fresh one and nothing is reset.
+// Cooperative launch guarantees that the CTAs polling each other are co-resident.
 #pragma once
 #include "sm100.cuh"
 
@@ -37,8 +46,12 @@ constexpr int REC_TMEM_COLS = 512;
 template <int BG> struct RecCfg {
   static constexpr int kEpiWarps = BG / 4;            // 4 (BG=16) or 8 (BG=32): one thread per (trial, 4 units)
   static constexpr int kEpiThreads = 32 * kEpiWarps;
-  static constexpr int kThreads = 64 + kEpiThreads;   // warp0 producer/poller, warp1 MMA + TMEM owner
+  static constexpr int kLoadWarps = 8;                // forward: warp 0 + the last 7 warps poll/stage h_{t-1} (one 16 B unit per chunk each)
+  static constexpr int kLoadThreads = 32 * kLoadWarps;
+  static constexpr int kFwdThreads = 64 + kEpiThreads + 32 * (kLoadWarps - 1);   // warp1 = MMA issuer + TMEM owner
+  static constexpr int kBwdThreads = 64 + kEpiThreads;                          // warp0 idle, warp1 = TMEM owner
   static constexpr int kXPitch = BG + 4;              // exchange row pitch (floats)
+  static constexpr size_t fwd_smem_bytes(int H) { return (size_t)2 * (H / 64) * BG * 128 + (size_t)3 * 32 * kXPitch * 4 + 512 + 1024; }
 };
 
 struct RecFwdParams {
@@ -52,8 +65,7 @@ struct RecFwdParams {
   float* h_state;                 // [Bpad][H] fp32: h_{t_begin-1} on entry, h_{t_end-1} on exit (chunk carry / final state)
   __nv_bfloat16* hdrop;           // [T][Bpad][H] dropout(h_t) for the next layer (nullable => not written)
   __nv_bfloat16 *R, *Z, *Nn, *HN; // [T][Bpad][H] stash for BPTT (nullable when not training)
-  int* done;                      // [n_groups][T] arrival counters, zeroed before the first chunk
-  int T;                          // total steps (stride of `done`)
+  int T;                          // total steps
   float keep;                     // dropout keep prob for hdrop
   unsigned long long seed, rng_offset;
   long long* trace;               // optional [T][8] clock64 samples from CTA 0 (profiling aid)
@@ -64,11 +76,25 @@ struct RecFwdParams {
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
-__device__ __forceinline__ void wait_counter(const int* ctr, int target) {
-  uint32_t spins = 0;
-  while (ld_acquire_gpu(ctr) < target) {
-    if (++spins > (1u << 26)) __trap();
-  }
+constexpr uint32_t REC_SENTINEL = 0xFFFFFFFFu;       // "not written yet" marker of an hseq word (two bf16)
+constexpr uint32_t REC_MAX_SPINS = 1u << 24;           // bounded polling: a lost peer traps instead of hanging the GPU
+
+__device__ __forceinline__ uint4 ld_relaxed_v4(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_v2(void* ptr, uint32_t a, uint32_t b) {
+  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1,%2};" ::"l"(ptr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_v4(void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ bool has_sentinel(const uint4& v) {
+  return v.x == REC_SENTINEL || v.y == REC_SENTINEL || v.z == REC_SENTINEL || v.w == REC_SENTINEL;
+}
+__device__ __forceinline__ bool tags_match(const uint4& v, uint32_t tag) {
+  return (((v.x ^ tag) | (v.y ^ tag) | (v.z ^ tag) | (v.w ^ tag)) & 3u) == 0u;
 }
 
 // A operand from TMEM, B operand from shared memory.
@@ -95,31 +121,30 @@ __device__ __forceinline__ uint4 rec_dropout_bits(unsigned long long seed, unsig
   return philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x6a7eu, 0), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 
-// tmap_h : hseq bf16   dims (H, (T+1)*Bpad)  box (64, BG)
 template <int BG>
-__global__ void __launch_bounds__(RecCfg<BG>::kThreads, 1)
-gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParams p) {
+__global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads, 1)
+gru_rec_fwd_kernel(const RecFwdParams p) {
   using Cfg = RecCfg<BG>;
   constexpr int XP = Cfg::kXPitch;
   constexpr int CHUNK_BYTES = BG * 128;                  // BG rows x 64 bf16
+  constexpr int UNITS = BG * 8;                          // 16-byte units per chunk (<= kLoadThreads)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int KC = p.H / 64;                               // 64-wide contraction chunks
-  uint8_t* sH = smem;                                    // KC x CHUNK_BYTES (SWIZZLE_128B)
-  float* sX = reinterpret_cast<float*>(sH + KC * CHUNK_BYTES);   // [3][32][XP]
-  uint64_t* bar_h = reinterpret_cast<uint64_t*>(sX + 3 * 32 * XP);   // [KC] (<= 16)
-  uint64_t* bar_d = bar_h + 16;
+  const int KC = p.H / 64;                               // 64-wide contraction chunks (<= 16)
+  uint8_t* sH = smem;                                    // [2 buffers][KC] x CHUNK_BYTES, K-major, 128B swizzle
+  float* sX = reinterpret_cast<float*>(sH + 2 * KC * CHUNK_BYTES);   // [3][32][XP]
+  uint64_t* bar_h = reinterpret_cast<uint64_t*>(sX + 3 * 32 * XP);   // [2][16]
+  uint64_t* bar_d = bar_h + 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % p.n_slices, grp = blockIdx.x / p.n_slices;
   const int j0 = slice * REC_US, b0 = grp * BG;
-  int* done = p.done + (size_t)grp * p.T;
   const int a_cols = p.H / 2;                            // TMEM columns of the A operand; accumulator follows
+  const bool is_loader = warp == 0 || warp >= 2 + Cfg::kEpiWarps;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmap_h);
-    for (int c = 0; c < KC; ++c) mbar_init(&bar_h[c], 1);
+    for (int c = 0; c < 32; ++c) mbar_init(&bar_h[c], Cfg::kLoadWarps);
     mbar_init(bar_d, 1);
     fence_mbar_init();
   }
@@ -150,31 +175,60 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
   __syncthreads();
   tc_fence_after();
 
-  if (warp == 0) {
-    if (elect_one()) {
-      for (int t = p.t_begin; t < p.t_end; ++t) {
-        if (t > p.t_begin) {
-          wait_counter(&done[t - 1], p.n_slices);
-          fence_proxy_async_all();             // order the acquired generic-proxy writes before async-proxy reads
+  if (is_loader) {
+    // ---------------- loaders: poll h_{t-1} (all units of this batch group) out of L2 and stage it as the B operand.
+    // Thread lt owns the 16-byte unit (row = lt / 8, segment = lt % 8) of every 64-column chunk.  Double-buffered:
+    // the peers' h_t can land while this CTA's MMA of step t still reads h_{t-1}.
+    const int lw = warp == 0 ? 0 : warp - (1 + Cfg::kEpiWarps);
+    const int lt = lw * 32 + lane;
+    const bool active = lt < UNITS;
+    const int row = lt >> 3, seg = lt & 7;
+    const uint32_t soff = row * 128 + ((seg ^ (row & 7)) << 4);
+    for (int t = p.t_begin; t < p.t_end; ++t) {
+      const int step = t - p.t_begin, buf = step & 1;
+      // h_{t-1} cannot exist before this CTA's own accumulator of step t-1 is complete: do not load L2 before that
+      if (step > 0) mbar_wait(bar_d, (uint32_t)(step - 1) & 1u);
+      const uint8_t* g = reinterpret_cast<const uint8_t*>(p.hseq + ((size_t)t * p.Bpad + b0 + row) * p.H) + seg * 16;   // slot t = h_{t-1}
+      uint8_t* sdst = sH + (size_t)buf * KC * CHUNK_BYTES + soff;
+      uint4 v[16];
+      uint32_t pending = (1u << KC) - 1u;                  // warp-uniform: chunks not staged yet
+      uint32_t spins = 0;
+      while (pending) {
+        // one polling round: every pending chunk is (re)loaded with all loads in flight together
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (((pending >> c) & 1u) && active) v[c] = ld_relaxed_v4(g + c * 128);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          if ((pending >> c) & 1u) {
+            const bool ok = !active || !has_sentinel(v[c]);
+            if (__all_sync(0xffffffffu, ok)) {
+              if (active) {
+                *reinterpret_cast<uint4*>(sdst + c * CHUNK_BYTES) = v[c];
+                fence_proxy_async_smem();          // generic smem write -> visible to the tensor-core (async) proxy
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&bar_h[buf * 16 + c]);
+              if (lt == 0 && c == 0) REC_TRACE(t, 0);      // first chunk of h_{t-1} staged
+              pending &= ~(1u << c);
+            }
+          }
         }
-        REC_TRACE(t, 0);                       // flags acquired
-        for (int c = 0; c < KC; ++c) {
-          mbar_arrive_expect_tx(&bar_h[c], CHUNK_BYTES);
-          tma_load_2d(sH + c * CHUNK_BYTES, &tmap_h, &bar_h[c], c * 64, t * p.Bpad + b0);   // slot t = h_{t-1}
-        }
-        REC_TRACE(t, 1);                       // TMA issued
+        if (++spins > REC_MAX_SPINS) __trap();
       }
+      if (lt == 0) REC_TRACE(t, 1);                        // all chunks staged
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BG, 0, 0);
       for (int t = p.t_begin; t < p.t_end; ++t) {
-        const uint32_t par = (uint32_t)(t - p.t_begin) & 1u;
+        const int step = t - p.t_begin, buf = step & 1;
+        const uint32_t par = (uint32_t)(step >> 1) & 1u;
         for (int c = 0; c < KC; ++c) {
-          mbar_wait(&bar_h[c], par);
+          mbar_wait(&bar_h[buf * 16 + c], par);
           if (c == 0) REC_TRACE(t, 2);         // first operand chunk landed
           tc_fence_after();
-          const uint32_t sb = smem_u32(sH + c * CHUNK_BYTES);
+          const uint32_t sb = smem_u32(sH + ((size_t)buf * KC + c) * CHUNK_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_ts(tmem_d, tmem_base + (c * 4 + k) * 8, umma_smem_desc(sb + k * 32, 16, 1024), idesc, (c | k) != 0 ? 1u : 0u);
@@ -223,6 +277,8 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
           dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
       }
       tc_fence_before();
+      // The only CTA barrier of the step.  sX and the accumulator are not overwritten before every thread here has
+      // stored its part of h_t: the next accumulator needs all of h_t, including this CTA's own slice.
       epi_bar_sync<Cfg::kEpiThreads>();
       if (e == 0) REC_TRACE(t, 7);             // gates exchanged
       float hn[4], r[4], z[4], n[4];
@@ -239,17 +295,11 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
         h[i] = (1.0f - z[i]) * n[i] + z[i] * h[i];
       }
       const size_t off = row * p.H + j;
-      st_bf16x4(p.hseq + ((size_t)(t + 1) * p.Bpad + b) * p.H + j, h[0], h[1], h[2], h[3]);
-      if (e == 0) REC_TRACE(t, 5);             // h_t stored
-      // publish h_t: every thread's store is ordered before the CTA barrier; the release by one thread is
-      // cumulative over it (same pattern as a grid barrier).  The BPTT stash is written after the release,
-      // off the critical path of the other CTAs.
-      epi_bar_sync<Cfg::kEpiThreads>();
-      if (e == 0) {
-        fence_proxy_async_all();
-        red_release_add(&done[t], 1);
-        REC_TRACE(t, 6);                       // published
+      {  // publish h_t: the data is the signal (see the header); the BPTT stash below is off the peers' critical path
+        __nv_bfloat162 lo = __floats2bfloat162_rn(h[0], h[1]), hi = __floats2bfloat162_rn(h[2], h[3]);
+        st_relaxed_v2(p.hseq + ((size_t)(t + 1) * p.Bpad + b) * p.H + j, *reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
       }
+      if (e == 0) REC_TRACE(t, 5);             // h_t stored
       if (train) {
         st_bf16x4(p.R + off, r[0], r[1], r[2], r[3]);
         st_bf16x4(p.Z + off, z[0], z[1], z[2], z[3]);
@@ -288,7 +338,8 @@ gru_rec_fwd_kernel(const __grid_constant__ CUtensorMap tmap_h, const RecFwdParam
 struct RecBwdParams {
   int H, Bpad, n_slices;
   int t_begin, t_end;               // this chunk processes t = t_end-1 ... t_begin
-  int T;                            // total steps (stride of `done`)
+  int T;                            // total steps
+  int gen_base;                     // generation of this launch's first step (see the header): buffer = gen & 1, tag = (gen >> 1) & 3
   const float* dY;                  // [T][Bpad][H] fp32 gradient wrt this layer's (dropped) output
   const __nv_bfloat16* hseq;        // [(T+1)][Bpad][H]
   const __nv_bfloat16 *R, *Z, *Nn, *HN;
@@ -301,7 +352,6 @@ struct RecBwdParams {
   float* dh_state;                  // [Bpad][H] fp32: recurrent part of dh_{t_end-1} on entry (ignored when first_chunk),
                                     //                  recurrent part of dh_{t_begin-1} on exit (= grad wrt the initial state at t_begin = 0)
   int first_chunk;                  // 1: t_end == T, no incoming recurrent gradient
-  int* done;                        // [n_groups][T]
   int n_valid;                      // trials < n_valid contribute (pad trials are masked out)
   float keep;                       // dropout applied to this layer's output in forward (1 => none)
   unsigned long long seed, rng_offset;
@@ -309,7 +359,7 @@ struct RecBwdParams {
 };
 
 template <int BG>
-__global__ void __launch_bounds__(RecCfg<BG>::kThreads, 1)
+__global__ void __launch_bounds__(RecCfg<BG>::kBwdThreads, 1)
 gru_rec_bwd_kernel(const RecBwdParams p) {
   using Cfg = RecCfg<BG>;
   constexpr int CHUNK_BYTES = BG * 128;
@@ -318,24 +368,21 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                                    // 2 chunks: dG_t as K-major B operand [BG trials][128 kk] (kk = gate*32 + unit, 96 used)
   uint64_t* bar_d = reinterpret_cast<uint64_t*>(sB + 2 * CHUNK_BYTES);
-  uint64_t* bar_f = bar_d + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_f + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NS = p.n_slices, NG = gridDim.x / NS;
   const int slice = blockIdx.x % NS, grp = blockIdx.x / NS;
   const int j0 = slice * REC_US, b0 = grp * BG;
   const int MB = (p.H + 127) / 128;                      // 128-row blocks of the output (all hidden units)
-  int* done = p.done + (size_t)grp * p.T;
   const int nsteps = p.t_end - p.t_begin;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_d, 1);
-    mbar_init(bar_f, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < 2 * CHUNK_BYTES / 4; i += Cfg::kThreads) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
+  for (int i = threadIdx.x; i < 2 * CHUNK_BYTES / 4; i += Cfg::kBwdThreads) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -371,15 +418,7 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
   tc_fence_after();
 
   // Steps are indexed s = 0..nsteps-1 for t = t_end-1-s.  The partials published at step s feed dh of step s+1.
-  if (warp == 0) {
-    if (elect_one()) {
-      for (int s = 0; s < nsteps; ++s) {                 // forward the "all partials of step s are visible" event to the CTA
-        wait_counter(&done[p.t_end - 1 - s], NS);
-        REC_TRACE(s, 0);
-        mbar_arrive(bar_f);
-      }
-    }
-  } else if (warp >= 2) {
+  if (warp >= 2) {
     const int e = threadIdx.x - 64;
     const int ew = e >> 5;
     const int q = warp & 3;
@@ -394,18 +433,47 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { accx[0][i] = accx[1][i] = accx[2][i] = 0.f; acch[i] = 0.f; }
 
-    auto gather_partials = [&](int s_prev, float (&P)[4]) {
-      // sum over the NS source CTAs of the partial for (trial bl, units u0..u0+3) published at step s_prev
-      const float* base = p.part + ((((size_t)(s_prev & 1) * NG + grp) * NS + slice) * NS) * (BG * 32) + bl * 32 + u0;
-      P[0] = P[1] = P[2] = P[3] = 0.f;
-      for (int src = 0; src < NS; src += 4) {
-        float4 v[4];
+    // Partial block layout (one per (buffer, group, destination slice, source slice)): 16-byte granules
+    // [trial quad tq][unit 0..31][4 trials], so that the producer (one TMEM lane = one unit, consecutive trials in its
+    // registers) and the consumer (warp ew = trial quad ew, lane = unit) both move 512 contiguous bytes per warp access.
+    auto gather_partials = [&](int gen, float (&P)[4]) {
+      // sum over the NS source CTAs; a word is valid once its two low bits carry the generation tag
+      const uint32_t tag = (uint32_t)(gen >> 1) & 3u;
+      const float* base = p.part + ((((size_t)(gen & 1) * NG + grp) * NS + slice) * NS) * (BG * 32) + (ew * 32 + lane) * 4;
+      float G[4] = {0.f, 0.f, 0.f, 0.f};                  // (unit = lane, trials 4*ew .. 4*ew+3)
+      constexpr int NB = 24;
+      for (int src0 = 0; src0 < NS; src0 += NB) {
+        uint4 v[NB];
+        uint32_t pending = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (src + i < NS) v[i] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(src + i) * (BG * 32)));
+        for (int i = 0; i < NB; ++i)
+          if (src0 + i < NS) pending |= 1u << i;
+        uint32_t spins = 0;
+        while (true) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (src + i < NS) { P[0] += v[i].x; P[1] += v[i].y; P[2] += v[i].z; P[3] += v[i].w; }
+          for (int i = 0; i < NB; ++i)
+            if ((pending >> i) & 1u) v[i] = ld_relaxed_v4(base + (size_t)(src0 + i) * (BG * 32));
+#pragma unroll
+          for (int i = 0; i < NB; ++i)
+            if (((pending >> i) & 1u) && tags_match(v[i], tag)) pending &= ~(1u << i);
+          if (!pending) break;
+          if (++spins > REC_MAX_SPINS) __trap();
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i)                       // fixed summation order: results do not depend on arrival order
+          if (src0 + i < NS) {
+            G[0] += __uint_as_float(v[i].x & ~3u); G[1] += __uint_as_float(v[i].y & ~3u);
+            G[2] += __uint_as_float(v[i].z & ~3u); G[3] += __uint_as_float(v[i].w & ~3u);
+          }
+      }
+      // transpose inside the warp: this thread needs trial k = lane/8 of units 4*(lane%8) + i
+      const int k = lane >> 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int sl = 4 * (lane & 7) + i;
+        const float a0 = __shfl_sync(0xffffffffu, G[0], sl), a1 = __shfl_sync(0xffffffffu, G[1], sl);
+        const float a2 = __shfl_sync(0xffffffffu, G[2], sl), a3 = __shfl_sync(0xffffffffu, G[3], sl);
+        P[i] = k == 0 ? a0 : (k == 1 ? a1 : (k == 2 ? a2 : a3));
       }
     };
 
@@ -417,19 +485,22 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       ld_bf16x4(p.R + off, r); ld_bf16x4(p.Z + off, z); ld_bf16x4(p.Nn + off, n); ld_bf16x4(p.HN + off, hn);
       ld_bf16x4(p.hseq + off, hp);                       // slot t = h_{t-1}
       float4 dyv = __ldg(reinterpret_cast<const float4*>(p.dY + off));
-      float dy[4] = {dyv.x, dyv.y, dyv.z, dyv.w};
+      float dmask[4] = {1.0f, 1.0f, 1.0f, 1.0f};         // dropout of this layer's output (same Philox stream as forward)
       if (p.keep < 1.0f) {
         const uint4 rnd = rec_dropout_bits(p.seed, p.rng_offset, off >> 2);
         const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dy[i] = (u32_to_unit(rr[i]) < p.keep) ? dy[i] * inv_keep : 0.0f;
+        for (int i = 0; i < 4; ++i) dmask[i] = (u32_to_unit(rr[i]) < p.keep) ? inv_keep : 0.0f;
       }
+      float P[4] = {0.f, 0.f, 0.f, 0.f};
+      if (s > 0) {
+        if (e == 0) REC_TRACE(s, 0);
+        gather_partials(p.gen_base + s - 1, P);          // polls until the partials of step s-1 from every CTA of the group are there
+        if (e == 0) REC_TRACE(s, 1);
+      }
+      const float dy[4] = {dyv.x * dmask[0], dyv.y * dmask[1], dyv.z * dmask[2], dyv.w * dmask[3]};
       float dh[4];
       if (s > 0) {
-        mbar_wait(bar_f, (s - 1) & 1);                   // partials of step s-1 from every CTA of the group are visible
-        if (e == 0) REC_TRACE(s, 1);
-        float P[4];
-        gather_partials(s - 1, P);
 #pragma unroll
         for (int i = 0; i < 4; ++i) dh[i] = carry[i] + P[i] + dy[i];
       } else if (!p.first_chunk) {                       // recurrent gradient handed over by the later chunk
@@ -495,30 +566,30 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       if (e == 0) REC_TRACE(s, 4);
       tc_fence_after();
       // partial sums -> L2: lane = output unit within its 32-unit destination slice, one 128 B line per trial
+      const int gen = p.gen_base + s;
+      const uint32_t tag = (uint32_t)(gen >> 1) & 3u;
       for (int mb = 0; mb < MB; ++mb) {
         uint32_t v[16];
         tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + mb * BG + chalf * 16, v);
         tmem_ld_wait();
         const int dest = mb * 4 + q;                     // destination slice = k / 32
         if (dest < NS) {
-          float* dst = p.part + ((((size_t)(s & 1) * NG + grp) * NS + dest) * NS + slice) * (BG * 32) + (chalf * 16) * 32 + lane;
+          float* dst = p.part + ((((size_t)(gen & 1) * NG + grp) * NS + dest) * NS + slice) * (BG * 32) + ((chalf * 4) * 32 + lane) * 4;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dst[i * 32] = __uint_as_float(v[i]);
+          for (int g4 = 0; g4 < 4; ++g4)
+            st_relaxed_v4(dst + g4 * 128, (v[4 * g4] & ~3u) | tag, (v[4 * g4 + 1] & ~3u) | tag, (v[4 * g4 + 2] & ~3u) | tag, (v[4 * g4 + 3] & ~3u) | tag);
         }
       }
       if (e == 0) REC_TRACE(s, 5);
+      // No barrier here: sB is rewritten only after this thread has gathered the partials of step s from every CTA
+      // (so MMA(s) is long complete), and MMA(s+1) is issued behind the CTA barrier above, after every warp has
+      // drained the accumulators of step s.
       tc_fence_before();
-      epi_bar_sync<Cfg::kEpiThreads>();
-      if (e == 0) {
-        red_release_add(&done[t], 1);
-        REC_TRACE(s, 6);
-      }
     }
     // recurrent gradient for the step before this chunk: dh_{t_begin-1} (rec) = dh_{t_begin} * z + dGh_{t_begin} W_hh
     {
-      mbar_wait(bar_f, (nsteps - 1) & 1);
       float P[4];
-      gather_partials(nsteps - 1, P);
+      gather_partials(p.gen_base + nsteps - 1, P);
       float o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[i] = valid ? carry[i] + P[i] : 0.0f;

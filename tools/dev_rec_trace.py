@@ -22,15 +22,18 @@ for i in range(3):
     eng.backward()
 torch.cuda.synchronize()
 tr = trace.cpu().numpy().reshape(2, Tp, 8)
-names = ["flags acquired", "TMA issued|partials gathered-start", "first chunk landed|B written", "MMAs issued", "accumulator done", "stored", "published", "gates exchanged"]
-for which, lab in ((0, "FWD layer 0"), (1, "BWD top layer")):
+fw = ["h chunk 0 staged", "all chunks staged", "MMA saw chunk 0", "MMAs issued", "accumulator done", "h_t stored", "-", "gates exchanged"]
+bw = ["gather start", "partials gathered", "B operand written", "MMAs issued", "accumulator done", "partials stored"]
+for which, lab, names, seq in ((0, "FWD layer 0", fw, (0, 2, 3, 4, 7, 5)), (1, "BWD top layer", bw, (0, 1, 2, 3, 4, 5))):
     t = tr[which].astype(np.float64)
     print(lab)
     steps = range(10, 90)
-    per = np.mean([t[s + 1, 0] - t[s, 0] for s in steps if t[s + 1, 0] and t[s, 0]])
-    print(f"  cycles per step (flag-to-flag): {per:.0f}")
-    for a, b in (((0, 1), (1, 2), (2, 3), (3, 4), (4, 7), (7, 5), (5, 6)) if which == 0 else ((0, 1), (1, 2), (2, 3), (3, 4), (4, 5), (5, 6))):
+    per = np.mean([t[s + 1, seq[0]] - t[s, seq[0]] for s in steps])
+    print(f"  cycles per step: {per:.0f}")
+    for a, b in zip(seq[:-1], seq[1:]):
         d = np.mean([t[s, b] - t[s, a] for s in steps])
         print(f"  {names[a]:>20s} -> {names[b]:<20s}: {d:8.0f} cyc")
-    d = np.mean([t[s + 1, 0] - t[s, 6] for s in steps])
-    print(f"  {'published':>20s} -> {'next flags acquired':<20s}: {d:8.0f} cyc")
+    d = np.mean([t[s + 1, seq[0]] - t[s, seq[-1]] for s in steps])
+    print(f"  {names[seq[-1]]:>20s} -> next {names[seq[0]]:<20s}: {d:8.0f} cyc")
+    if which == 0:
+        print(f"  (all chunks staged - chunk 0 staged: {np.mean([t[s, 1] - t[s, 0] for s in steps]):.0f} cyc)")
