@@ -28,6 +28,7 @@ struct CtcParams {
   const int* in_len;        // [B]
   const int* tgt_len;       // [B]
   float* alpha;             // scratch [B][T][Lmax], Lmax = 2*Smax+1 (row-normalised alpha)
+  float* beta;              // scratch, same shape (row-normalised beta; used by the CTA-per-trial parallel kernel)
   float* loss;              // [B]
   float* dlogits;           // fp32, same layout as logits (nullable => loss only)
   __nv_bfloat16* dlogits_bf16;  // bf16 copy for the tensor-core GEMMs (nullable)
@@ -377,6 +378,206 @@ ctc_loss_grad_warp_kernel(const CtcParams p) {
     for (int c = lane; c < p.C && k < 2; c += 32, ++k) atomicAdd(p.dbias + c, dbacc[k]);
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-per-trial variant for 2*Smax+1 <= 32*CPL: the three phases of the warp kernel, de-serialised.
+//   1. log-softmax: one warp per frame, all warps;
+//   2. warp 0 runs the alpha recursion (t ascending) WHILE warp 1 runs the beta recursion (t descending); both keep the
+//      lattice row in registers (neighbours by shuffle) and stream the normalised rows to L2 scratch;
+//   3. gradient: one warp per frame, all warps, from alpha + beta + the accumulated shifts.
+// The serial chain is max(alpha, beta) steps instead of log-softmax + alpha + (beta + gradient) steps, and neither
+// recursion has memory loads, atomics or stores-with-consumers on its dependency chain.  Arithmetic is the same as in
+// the kernels above (row-normalised fp32 recursions, shifts in double).
+constexpr int CTC_PAR_WARPS = 8;
+
+template <int CPL>
+__global__ void __launch_bounds__(32 * CTC_PAR_WARPS)
+ctc_loss_grad_par_kernel(const CtcParams p) {
+  extern __shared__ double ctc_smem_d[];
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Lmax = 2 * p.Smax + 1;
+  double* shiftA = ctc_smem_d;                                // [T] cumulative alpha shift up to and including frame t
+  double* shiftB = shiftA + p.T;                              // [T] cumulative beta shift from the last frame down to t
+  float* lp = reinterpret_cast<float*>(shiftB + p.T);         // [T][C]
+  float* occ_all = lp + (size_t)p.T * p.C;                    // [warps][C]
+  float* dbsum = occ_all + CTC_PAR_WARPS * p.C;               // [C]
+  __shared__ double s_ll;
+  int Tb = p.in_len[b];
+  Tb = Tb < 0 ? 0 : (Tb > p.T ? p.T : Tb);
+  const int S = p.tgt_len[b];
+  const int L = 2 * S + 1;
+  const float NINF = -CUDART_INF_F;
+  const unsigned FULL = 0xffffffffu;
+
+  int ext[CPL];
+  bool skip[CPL], skipf[CPL];                                 // may come from s-2 / may go to s+2
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) {
+    const int s = lane * CPL + j;
+    auto lab = [&](int q) { return (q & 1) ? p.labels[(size_t)b * p.Smax + (q >> 1)] : p.blank; };
+    ext[j] = s < L ? lab(s) : p.blank;
+    skip[j] = s < L && s >= 2 && ext[j] != p.blank && ext[j] != lab(s - 2);
+    skipf[j] = s + 2 < L && lab(s + 2) != p.blank && lab(s + 2) != ext[j];
+  }
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) dbsum[c] = 0.f;
+
+  // ---- 1. log-softmax rows
+  for (int t = warp; t < Tb; t += CTC_PAR_WARPS) {
+    const float* row = p.logits + ((size_t)t * p.Bpad + b) * p.ldl;
+    float m = NINF;
+    for (int c = lane; c < p.C; c += 32) m = fmaxf(m, row[c]);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    float sum = 0.f;
+    for (int c = lane; c < p.C; c += 32) sum += expf(row[c] - m);
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    const float lz = m + logf(sum);
+    for (int c = lane; c < p.C; c += 32) lp[t * p.C + c] = row[c] - lz;
+  }
+  __syncthreads();
+
+  // ---- 2. the two recursions, concurrently
+  float* alpha = p.alpha + (size_t)b * p.T * Lmax;
+  float* beta = p.beta + (size_t)b * p.T * Lmax;
+  if (warp == 0) {
+    float a[CPL];
+    double accA = 0.0;
+    for (int t = 0; t < Tb; ++t) {
+      float na[CPL];
+      if (t == 0) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int s = lane * CPL + j;
+          na[j] = (s == 0) ? lp[p.blank] : ((s == 1 && s < L) ? lp[ext[j]] : NINF);
+        }
+      } else {
+        float l1 = __shfl_up_sync(FULL, a[CPL - 1], 1);
+        float l2 = CPL >= 2 ? __shfl_up_sync(FULL, a[CPL >= 2 ? CPL - 2 : 0], 1) : __shfl_up_sync(FULL, a[0], 2);
+        if (lane == 0) { l1 = NINF; l2 = NINF; }
+        if (CPL == 1 && lane == 1) l2 = NINF;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int s = lane * CPL + j;
+          const float a1 = j >= 1 ? a[j >= 1 ? j - 1 : 0] : l1;
+          const float a2 = j >= 2 ? a[j >= 2 ? j - 2 : 0] : (j == 1 ? l1 : l2);
+          na[j] = s < L ? lse3(a[j], a1, skip[j] ? a2 : NINF) + lp[t * p.C + ext[j]] : NINF;
+        }
+      }
+      float m = na[0];
+#pragma unroll
+      for (int j = 1; j < CPL; ++j) m = fmaxf(m, na[j]);
+      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+      const float sh = (m == NINF) ? 0.f : m;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        a[j] = na[j] - sh;
+        const int s = lane * CPL + j;
+        if (s < L) alpha[(size_t)t * Lmax + s] = a[j];
+      }
+      accA += (double)sh;
+      if (lane == 0) shiftA[t] = accA;
+    }
+    float last = NINF, last2 = NINF;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int s = lane * CPL + j;
+      if (Tb > 0 && s == L - 1) last = a[j];
+      if (Tb > 0 && s == L - 2) last2 = a[j];
+    }
+    for (int o = 16; o; o >>= 1) { last = fmaxf(last, __shfl_xor_sync(FULL, last, o)); last2 = fmaxf(last2, __shfl_xor_sync(FULL, last2, o)); }
+    double ll;
+    if (Tb > 0) ll = (double)lse2(last, last2) + accA;
+    else ll = (S == 0) ? 0.0 : -(double)CUDART_INF_F;
+    if (lane == 0) { s_ll = ll; p.loss[b] = (float)(-ll); }
+  } else if (warp == 1 && (p.dlogits || p.dlogits_bf16)) {
+    float bt[CPL];
+    double accB = 0.0;
+    for (int t = Tb - 1; t >= 0; --t) {
+      float nb[CPL];
+      if (t == Tb - 1) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int s = lane * CPL + j;
+          nb[j] = (s < L && (s == L - 1 || s == L - 2)) ? lp[t * p.C + ext[j]] : NINF;
+        }
+      } else {
+        float r1 = __shfl_down_sync(FULL, bt[0], 1);
+        float r2 = CPL >= 2 ? __shfl_down_sync(FULL, bt[CPL >= 2 ? 1 : 0], 1) : __shfl_down_sync(FULL, bt[0], 2);
+        if (lane == 31) { r1 = NINF; r2 = NINF; }
+        if (CPL == 1 && lane == 30) r2 = NINF;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int s = lane * CPL + j;
+          const float b1 = j + 1 < CPL ? bt[j + 1 < CPL ? j + 1 : 0] : r1;
+          const float b2 = j + 2 < CPL ? bt[j + 2 < CPL ? j + 2 : 0] : (j + 1 < CPL ? r1 : r2);
+          nb[j] = s < L ? lse3(bt[j], s + 1 < L ? b1 : NINF, skipf[j] ? b2 : NINF) + lp[t * p.C + ext[j]] : NINF;
+        }
+      }
+      float m = nb[0];
+#pragma unroll
+      for (int j = 1; j < CPL; ++j) m = fmaxf(m, nb[j]);
+      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+      const float sh = (m == NINF) ? 0.f : m;
+      accB += (double)sh;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        bt[j] = nb[j] - sh;
+        const int s = lane * CPL + j;
+        if (s < L) beta[(size_t)t * Lmax + s] = bt[j];
+      }
+      if (lane == 0) shiftB[t] = accB;
+    }
+  }
+  __syncthreads();                                            // also makes this CTA's alpha/beta rows (global) visible to all its warps
+  if (!p.dlogits && !p.dlogits_bf16) return;
+  const double ll = s_ll;
+
+  // ---- 3. gradient rows
+  float dbacc[2] = {0.f, 0.f};
+  float* occ = occ_all + warp * p.C;
+  for (int t = warp; t < p.T; t += CTC_PAR_WARPS) {
+    float* drow = p.dlogits ? p.dlogits + ((size_t)t * p.Bpad + b) * p.ldl : nullptr;
+    __nv_bfloat16* drow16 = p.dlogits_bf16 ? p.dlogits_bf16 + ((size_t)t * p.Bpad + b) * p.ldl : nullptr;
+    if (t >= Tb) {                                            // frames beyond the input length get zero gradient
+      for (int c = lane; c < p.ldl; c += 32) {
+        if (drow) drow[c] = 0.f;
+        if (drow16) drow16[c] = __float2bfloat16_rn(0.f);
+      }
+      continue;
+    }
+    const float base = (float)(shiftA[t] + shiftB[t] - ll);
+    for (int c = lane; c < p.C; c += 32) occ[c] = 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int s = lane * CPL + j;
+      if (s < L) {
+        const float ab = alpha[(size_t)t * Lmax + s] + beta[(size_t)t * Lmax + s] + base;   // log of the (doubly emitted) path mass through (t, s)
+        const float w = expf(ab - lp[t * p.C + ext[j]]);
+        if (w > 0.f) atomicAdd(&occ[ext[j]], w);
+      }
+    }
+    __syncwarp();
+    int k = 0;
+    for (int c = lane; c < p.ldl; c += 32, ++k) {
+      float g = 0.f;
+      if (c < p.C) {
+        g = (expf(lp[t * p.C + c]) - occ[c]) * p.grad_scale;
+        if (k < 2) dbacc[k] += g;
+      }
+      if (drow) drow[c] = g;
+      if (drow16) drow16[c] = __float2bfloat16_rn(g);
+    }
+    __syncwarp();
+  }
+  if (p.dbias) {
+    int k = 0;
+    for (int c = lane; c < p.C && k < 2; c += 32, ++k) atomicAdd(&dbsum[c], dbacc[k]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) atomicAdd(p.dbias + c, dbsum[c]);
+  }
+}
+
+inline size_t ctc_par_smem_bytes(int T, int C) { return (size_t)2 * T * sizeof(double) + ((size_t)T * C + (CTC_PAR_WARPS + 1) * C) * sizeof(float) + 16; }
 
 inline size_t ctc_warp_smem_bytes(int T, int C) { return (size_t)T * sizeof(double) + ((size_t)T * C + C) * sizeof(float) + 16; }
 

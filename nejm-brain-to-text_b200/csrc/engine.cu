@@ -144,10 +144,11 @@ struct b2t_engine {
   // carved buffers
   __nv_bfloat16* shadow;
   __nv_bfloat16 *xs, *xd, *xu, *dxu, *dpre, *dlog16;
-  float *logits, *dlog32, *alpha;
+  float *logits, *dlog32, *alpha, *beta;
   std::vector<LayerBuf> lay;
   int *steps, *greedy_scratch;
   int part_geom = -1;
+  int poll_delay = 0;
   float *sumsq, *stats;
   Segment* d_segs;
   ChunkRef* d_chunks;
@@ -245,6 +246,7 @@ static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
   e->dlog32 = c.take<float>(M * LDL);
   e->dlog16 = c.take<__nv_bfloat16>(M * LDL);
   e->alpha = c.take<float>((size_t)e->maxB * Tq * (2 * e->maxS + 1));
+  e->beta = c.take<float>((size_t)e->maxB * Tq * (2 * e->maxS + 1));
   e->greedy_scratch = c.take<int>((size_t)e->maxB * 2 * (e->maxS + 1));
   if (tr) {
     e->dxu = c.take<__nv_bfloat16>(M * e->K0);
@@ -366,6 +368,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 static int build_plans(b2t_engine* e) {
+  e->poll_delay = env_int("B2T_POLL_DELAY", 700);
   const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp, M = e->M, K0 = e->K0, T = e->T_in;
   const bool tr = e->training != 0;
   // ---- recurrence geometry: trials per CTA, concurrent launches, time chunks
@@ -692,7 +695,7 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
       rp.hdrop = save ? e->lay[l].hdrop : nullptr;
       rp.R = save ? e->lay[l].R : nullptr; rp.Z = save ? e->lay[l].Z : nullptr;
       rp.Nn = save ? e->lay[l].Nn : nullptr; rp.HN = save ? e->lay[l].HN : nullptr;
-      rp.keep = keep_rnn; rp.seed = a->seed; rp.rng_offset = (unsigned long long)(l + 1) << 40;
+      rp.poll_delay = e->poll_delay; rp.keep = keep_rnn; rp.seed = a->seed; rp.rng_offset = (unsigned long long)(l + 1) << 40;
       rp.trace = (l == 0) ? e->trace : nullptr;
       // eval-mode forward through a training engine: the next layer reads hdrop if it exists, so keep it in sync
       if (!save && e->lay[l].hdrop) { rp.hdrop = e->lay[l].hdrop; rp.keep = 1.0f; }
@@ -729,9 +732,28 @@ static int run_ctc_warp(const CtcParams& cp, int B, size_t smem, cudaStream_t st
   return 0;
 }
 
+template <int CPL>
+static int run_ctc_par(const CtcParams& cp, int B, size_t smem, cudaStream_t st) {
+  CK(cudaFuncSetAttribute(ctc_loss_grad_par_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctc_loss_grad_par_kernel<CPL><<<B, 32 * CTC_PAR_WARPS, smem, st>>>(cp);
+  CK(LAUNCHED());
+  return 0;
+}
+
 static int run_ctc(const CtcParams& cp, int B, cudaStream_t st) {
   if (cp.C > CTC_THREADS || cp.ldl > CTC_THREADS) return fail(B2T_ERR_UNSUPPORTED, "too many classes");
   const int Lmax = 2 * cp.Smax + 1;
+  const size_t psmem = ctc_par_smem_bytes(cp.T, cp.C);
+  static const bool force_warp = getenv("B2T_CTC_WARP") != nullptr;      // A/B switch for profiling
+  if (Lmax <= 128 && cp.C <= 64 && psmem <= 200 * 1024 && cp.beta && !force_warp) {   // CTA per trial, alpha and beta concurrently
+    const int cpl = (Lmax + 31) / 32;
+    switch (cpl) {
+      case 1: return run_ctc_par<1>(cp, B, psmem, st);
+      case 2: return run_ctc_par<2>(cp, B, psmem, st);
+      case 3: return run_ctc_par<3>(cp, B, psmem, st);
+      default: return run_ctc_par<4>(cp, B, psmem, st);
+    }
+  }
   const size_t wsmem = ctc_warp_smem_bytes(cp.T, cp.C);
   if (Lmax <= 128 && cp.C <= 64 && wsmem <= 200 * 1024) {     // warp-per-trial kernel: no block barriers
     const int cpl = (Lmax + 31) / 32;
@@ -759,7 +781,7 @@ extern "C" int b2t_ctc_loss(b2t_engine* e, const int* labels, int Smax, const in
   CtcParams cp;
   cp.logits = e->logits; cp.ldl = LDL; cp.Bpad = e->Bpad; cp.T = e->Tp; cp.C = e->C; cp.blank = 0;
   cp.labels = labels; cp.Smax = Smax; cp.in_len = in_len; cp.tgt_len = tgt_len;
-  cp.alpha = e->alpha; cp.loss = loss_out;
+  cp.alpha = e->alpha; cp.beta = e->beta; cp.loss = loss_out;
   cp.dlogits = want_grad ? e->dlog32 : nullptr;
   cp.dlogits_bf16 = want_grad ? e->dlog16 : nullptr;
   cp.dbias = nullptr;
@@ -777,7 +799,7 @@ extern "C" int b2t_ctc_loss(b2t_engine* e, const int* labels, int Smax, const in
   return 0;
 }
 
-extern "C" long long b2t_ctc_workspace_bytes(int T, int B, int Smax) { return (long long)T * B * (2 * Smax + 1) * 4 + 1024; }
+extern "C" long long b2t_ctc_workspace_bytes(int T, int B, int Smax) { return (long long)2 * T * B * (2 * Smax + 1) * 4 + 1024; }
 
 extern "C" int b2t_ctc_loss_tbc(const float* logits_tbc, int T, int B, int C, const int* labels, int Smax, const int* in_len, const int* tgt_len,
                                 float grad_scale, float* loss_out, float* dlogits_tbc, void* workspace, long long workspace_bytes, void* stream) {
@@ -786,7 +808,8 @@ extern "C" int b2t_ctc_loss_tbc(const float* logits_tbc, int T, int B, int C, co
   CtcParams cp;
   cp.logits = logits_tbc; cp.ldl = C; cp.Bpad = B; cp.T = T; cp.C = C; cp.blank = 0;
   cp.labels = labels; cp.Smax = Smax; cp.in_len = in_len; cp.tgt_len = tgt_len;
-  cp.alpha = reinterpret_cast<float*>(workspace); cp.loss = loss_out; cp.dlogits = dlogits_tbc; cp.dlogits_bf16 = nullptr; cp.dbias = nullptr;
+  cp.alpha = reinterpret_cast<float*>(workspace); cp.beta = cp.alpha + (size_t)T * B * (2 * Smax + 1);
+  cp.loss = loss_out; cp.dlogits = dlogits_tbc; cp.dlogits_bf16 = nullptr; cp.dbias = nullptr;
   cp.grad_scale = grad_scale;
   return run_ctc(cp, B, (cudaStream_t)stream);
 }

@@ -66,6 +66,7 @@ struct RecFwdParams {
   __nv_bfloat16* hdrop;           // [T][Bpad][H] dropout(h_t) for the next layer (nullable => not written)
   __nv_bfloat16 *R, *Z, *Nn, *HN; // [T][Bpad][H] stash for BPTT (nullable when not training)
   int T;                          // total steps
+  int poll_delay;                 // cycles between this CTA's own h_t store and the first polling round (tuning knob)
   float keep;                     // dropout keep prob for hdrop
   unsigned long long seed, rng_offset;
   long long* trace;               // optional [T][8] clock64 samples from CTA 0 (profiling aid)
@@ -82,6 +83,13 @@ constexpr uint32_t REC_MAX_SPINS = 1u << 24;           // bounded polling: a los
 __device__ __forceinline__ uint4 ld_relaxed_v4(const void* ptr) {
   uint4 v;
   asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
+// Poll load for the forward exchange: cache-global (L2 only, never L1), so every execution reads the point of
+// coherence; unlike ld.relaxed.gpu the 16-byte accesses of a warp are coalesced into full-line requests.
+__device__ __forceinline__ uint4 ld_l2_v4(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_relaxed_v2(void* ptr, uint32_t a, uint32_t b) {
@@ -135,7 +143,8 @@ gru_rec_fwd_kernel(const RecFwdParams p) {
   float* sX = reinterpret_cast<float*>(sH + 2 * KC * CHUNK_BYTES);   // [3][32][XP]
   uint64_t* bar_h = reinterpret_cast<uint64_t*>(sX + 3 * 32 * XP);   // [2][16]
   uint64_t* bar_d = bar_h + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
+  uint64_t* bar_s = bar_d + 1;                           // this CTA's epilogue warps have stored their part of h_t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % p.n_slices, grp = blockIdx.x / p.n_slices;
@@ -146,6 +155,7 @@ gru_rec_fwd_kernel(const RecFwdParams p) {
   if (threadIdx.x == 0) {
     for (int c = 0; c < 32; ++c) mbar_init(&bar_h[c], Cfg::kLoadWarps);
     mbar_init(bar_d, 1);
+    mbar_init(bar_s, Cfg::kEpiWarps);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
@@ -186,8 +196,15 @@ gru_rec_fwd_kernel(const RecFwdParams p) {
     const uint32_t soff = row * 128 + ((seg ^ (row & 7)) << 4);
     for (int t = p.t_begin; t < p.t_end; ++t) {
       const int step = t - p.t_begin, buf = step & 1;
-      // h_{t-1} cannot exist before this CTA's own accumulator of step t-1 is complete: do not load L2 before that
-      if (step > 0) mbar_wait(bar_d, (uint32_t)(step - 1) & 1u);
+      // The peers store their slices of h_{t-1} at about the time this CTA stores its own: start polling then
+      // (polling earlier only burns L2 bandwidth and de-phases the rounds from the arrival of the data).
+      if (step > 0) {
+        mbar_wait(bar_s, (uint32_t)(step - 1) & 1u);
+        if (p.poll_delay > 0) {
+          const long long t0 = clock64();
+          while (clock64() - t0 < p.poll_delay) {}
+        }
+      }
       const uint8_t* g = reinterpret_cast<const uint8_t*>(p.hseq + ((size_t)t * p.Bpad + b0 + row) * p.H) + seg * 16;   // slot t = h_{t-1}
       uint8_t* sdst = sH + (size_t)buf * KC * CHUNK_BYTES + soff;
       uint4 v[16];
@@ -197,7 +214,7 @@ gru_rec_fwd_kernel(const RecFwdParams p) {
         // one polling round: every pending chunk is (re)loaded with all loads in flight together
 #pragma unroll
         for (int c = 0; c < 16; ++c)
-          if (((pending >> c) & 1u) && active) v[c] = ld_relaxed_v4(g + c * 128);
+          if (((pending >> c) & 1u) && active) v[c] = ld_l2_v4(g + c * 128);
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           if ((pending >> c) & 1u) {
@@ -299,6 +316,8 @@ gru_rec_fwd_kernel(const RecFwdParams p) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(h[0], h[1]), hi = __floats2bfloat162_rn(h[2], h[3]);
         st_relaxed_v2(p.hseq + ((size_t)(t + 1) * p.Bpad + b) * p.H + j, *reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s);
       if (e == 0) REC_TRACE(t, 5);             // h_t stored
       if (train) {
         st_bf16x4(p.R + off, r[0], r[1], r[2], r[3]);
@@ -367,8 +386,8 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                                    // 2 chunks: dG_t as K-major B operand [BG trials][128 kk] (kk = gate*32 + unit, 96 used)
-  uint64_t* bar_d = reinterpret_cast<uint64_t*>(sB + 2 * CHUNK_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 1);
+  uint64_t* bar_d = reinterpret_cast<uint64_t*>(sB + 2 * CHUNK_BYTES);   // [8]: one per 128-row output block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NS = p.n_slices, NG = gridDim.x / NS;
@@ -378,7 +397,7 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
   const int nsteps = p.t_end - p.t_begin;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_d, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bar_d[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
@@ -545,12 +564,14 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
         REC_TRACE(s, 2);
         tc_fence_after();
         const uint32_t sb = smem_u32(sB);
+        for (int mb = 0; mb < MB; ++mb) {                // block by block: the drain of block mb overlaps the MMAs of mb+1..
 #pragma unroll
-        for (int ks = 0; ks < 6; ++ks) {                 // K = 96 = 6 x 16; the MB accumulators are independent chains
-          const uint64_t bdesc = umma_smem_desc(sb + (ks >> 2) * CHUNK_BYTES + (ks & 3) * 32, 16, 1024);
-          for (int mb = 0; mb < MB; ++mb) umma_bf16_ts(tmem_d + mb * BG, tmem_base + mb * A_PITCH + ks * 8, bdesc, idesc, ks != 0 ? 1u : 0u);
+          for (int ks = 0; ks < 6; ++ks) {               // K = 96 = 6 x 16
+            const uint64_t bdesc = umma_smem_desc(sb + (ks >> 2) * CHUNK_BYTES + (ks & 3) * 32, 16, 1024);
+            umma_bf16_ts(tmem_d + mb * BG, tmem_base + mb * A_PITCH + ks * 8, bdesc, idesc, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(&bar_d[mb]);
         }
-        umma_commit(bar_d);
         REC_TRACE(s, 3);
       }
       // off the critical path: gate gradients for the weight-gradient GEMMs
@@ -562,13 +583,13 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       st_bf16x4(p.dGx + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
       st_bf16x4(p.dGx + goff + 2 * p.H, gn[0], gn[1], gn[2], gn[3]);
 
-      mbar_wait(bar_d, s & 1);
-      if (e == 0) REC_TRACE(s, 4);
-      tc_fence_after();
-      // partial sums -> L2: lane = output unit within its 32-unit destination slice, one 128 B line per trial
+      // partial sums -> L2 (granule layout above): lane = output unit within its 32-unit destination slice
       const int gen = p.gen_base + s;
       const uint32_t tag = (uint32_t)(gen >> 1) & 3u;
       for (int mb = 0; mb < MB; ++mb) {
+        mbar_wait(&bar_d[mb], s & 1);
+        if (e == 0 && mb == 0) REC_TRACE(s, 4);
+        tc_fence_after();
         uint32_t v[16];
         tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + mb * BG + chalf * 16, v);
         tmem_ld_wait();
