@@ -56,42 +56,67 @@ def synth_batches(seed, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+    NVML is polled from a thread every ~2 ms (the timed region is ~0.1 s, too short for `nvidia-smi -lms`);
+    nvidia-smi is only the fallback when the NVML binding is missing."""
+    _REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.mx, self.reasons, self.power = index, [], 0, set(), 0.0
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self._stop.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in self._REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            try:
+                self.power = max(self.power, nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _smi_loop(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout
+                f = [c.strip() for c in out.strip().split(",")]
+                self.sm.append(float(f[0])); self.mx = max(self.mx, float(f[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                return
+
+    def _loop(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
+        time.sleep(0.01)                                      # let NVML initialise before the timed region opens
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            f = [c.strip() for c in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=15)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx or None, "reasons": sorted(self.reasons),
+                "samples": len(sm), "power_w_max": self.power or None}
 
 
 def run_ours(args):
@@ -128,12 +153,29 @@ def run_ours(args):
     gscale = 1.0 / (B * world)
     loss_host = torch.empty(B, pin_memory=True)
     stage = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def step(i, from_host):
-        if from_host:
-            hb, d = host[i % N_ROT], stage[i % 2]
+    def prefetch(i):
+        """Host -> device copy of step i's batch (pinned memory) on the copy stream, into the staging buffer the step
+        before last has finished with (every e2e step ends with a stream synchronize)."""
+        hb, d = host[i % N_ROT], stage[i % 2]
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
             for k in hb:
                 d[k].copy_(hb[k], non_blocking=True)
+            copied[i % 2].record(copy_stream)
+
+    def step(i, from_host, last=False):
+        if from_host:
+            # double-buffered input pipeline: batch i was issued during step i-1 (or just now for the first step); batch i+1 is
+            # issued here and overlaps this step's compute.  Every step copies exactly one batch inside the timed region.
+            if i == 0:
+                prefetch(0)
+            if not last:
+                prefetch(i + 1)
+            d = stage[i % 2]
+            torch.cuda.current_stream().wait_event(copied[i % 2])
         else:
             d = res[i % N_ROT]
         eng.forward(d["x"], d["days"], training=True, smooth_mode=1, cut=i % 3, white_noise_std=1.0, offset_noise_std=0.2,
@@ -159,7 +201,7 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n):
-            step(i, from_host)
+            step(i, from_host, last=(i == n - 1))
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -175,7 +217,7 @@ def run_ours(args):
         step(i, False)
     ms, launches, clocks = timed(args.steps, False, sample_clocks=True)
     for i in range(2):
-        step(i, True)
+        step(i, True, last=(i == 1))
     ms_e2e, _, _ = timed(args.steps, True)
     final_loss = float(step(0, False).mean().item())
 
@@ -194,6 +236,43 @@ def run_ours(args):
         kms = e0.elapsed_time(e1) / 10
         kern = {"name": "gemm_bf16_kernel<K,K> 6208x2304x7168 (layer-0 input projection)", "ms": kms,
                 "tflops": 2.0 * M * K * Nn / kms / 1e9}
+
+    # per-kernel view of one more step (CUDA events around every task on its own stream, engine timeline facility): where the
+    # step's time goes and what each kernel class achieves against the share of the chip it occupies
+    kernels = None
+    if rank == 0:
+        import ctypes
+        torch.cuda.synchronize()
+        N.lib.b2t_debug_timeline(1)
+        step(3, False)
+        buf = ctypes.create_string_buffer(1 << 16)
+        N.lib.b2t_debug_dump_timeline(buf, 1 << 16)
+        N.lib.b2t_debug_timeline(0)
+        H, Tp = CFG["n_units"], 97
+        agg = {}
+        for line in buf.value.decode().strip().split("\n"):
+            f = line.split()
+            if len(f) != 4:
+                continue
+            name, dur = f[1], float(f[3]) - float(f[2])
+            key = ("gru_rec_bwd_kernel" if name.startswith("RB") else "gru_rec_fwd_kernel" if name.startswith("R") else
+                   "gemm_bf16_kernel (L0 input projection, time chunks)" if name.startswith("G0.") else
+                   "gemm_bf16_kernel (other)" if name[0] in "GDd" or name in ("day", "head") else name)
+            a = agg.setdefault(key, {"launches": 0, "us": 0.0})
+            a["launches"] += 1; a["us"] += dur
+        rec_flop = 2.0 * B * 3 * H * H * Tp * CFG["n_layers"]              # all layers, all steps, one direction
+        kernels = []
+        for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+            e = {"name": key, "launches": a["launches"], "sum_us": round(a["us"], 1)}
+            if key.startswith("gru_rec"):
+                e["flop"] = rec_flop
+                e["tflops_per_launch_avg"] = rec_flop / a["us"] / 1e6
+                e["note"] = "48 CTAs per launch, up to 3 launches concurrent; latency-bound serial chain (97 steps x 5 layers)"
+            if key.startswith("gemm_bf16_kernel (L0"):
+                e["flop"] = 2.0 * Tp * B * 7168 * 2304
+                e["tflops_per_launch_avg"] = e["flop"] / a["us"] / 1e6
+                e["note"] = "runs concurrently with recurrence launches, i.e. on a share of the SMs"
+            kernels.append(e)
 
     if rank != 0:
         if world > 1:
@@ -216,9 +295,10 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": None, "peak_source": src + " (bf16_tflops_sustained)",
-                     "note": "whole-step GRU-GEMM FLOPs (18.88 GFLOP/trial, BASELINE.md) / step time, per GPU",
-                     "dominant_kernel": kern},
+                     "traffic": 169.5e6, "traffic_note": "dram bytes read+write of ONE launch of the dominant GEMM below (ncu --set full, profiles/r1_ncu_full_summary.md); algorithmic 179 MB",
+                     "peak_source": src + " (bf16_tflops_sustained)",
+                     "note": "achieved = whole-step GRU-GEMM FLOPs (18.88 GFLOP/trial, BASELINE.md) / step time, per GPU: the fraction of the GRU-GEMM roofline north_star asks for",
+                     "dominant_kernel": kern, "kernels": kernels},
         "cpu_baseline": cpu,
     }
     print(json.dumps(out))

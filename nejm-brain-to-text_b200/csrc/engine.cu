@@ -111,6 +111,11 @@ extern "C" long long b2t_grad_elems(const b2t_config* cfg) {
 }
 
 // ------------------------------------------------------------------------------------ engine
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 struct Carver {
   uint8_t* base;
   size_t off, cap;
@@ -126,7 +131,7 @@ struct Carver {
 
 constexpr int LDL = 64;        // pitch (elements) of logits / dlogits rows: 128 B in bf16, TMA friendly
 constexpr int MAX_CHUNKS = 8;  // time chunks of the layer wave-front
-constexpr int MAX_LANES = 3;   // concurrent recurrence launches (side streams)
+constexpr int MAX_LANES = 5;   // concurrent recurrence launches (side streams)
 
 struct LayerBuf {
   __nv_bfloat16 *hseq, *hdrop, *R, *Z, *Nn, *HN, *dGx, *dGh;
@@ -156,16 +161,15 @@ struct b2t_engine {
   float* touched;             // tail of the gradient buffer: [n_days]
   // current shape + plans
   int B = 0, Bpad = 0, T_in = 0, T_out = 0, Tp = 0, M = 0;
-  int BG = 16, n_tchunks = 1, n_lanes = 1;
+  int BG = 16, BGb = 16, n_tchunks = 1, n_lanes = 1, n_lanes_b = 1;   // forward / backward trials per CTA and concurrent launches
   int tc_begin[MAX_CHUNKS + 1];
   bool plans_ok = false, use_unfold_copy = false;
   GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw;
   std::vector<GemmPlan> p_dwih, p_dwhh, p_dwih0;   // p_dwih0: layer-0 dW_ih per time chunk (accumulating)
   std::vector<std::vector<GemmPlan>> p_in, p_dx;     // [layer >= 1][chunk]
-  std::vector<CUtensorMap> tm_h;
   // side streams / events of the wave-front
-  cudaStream_t lane[MAX_LANES + 1] = {nullptr, nullptr, nullptr, nullptr};   // [MAX_LANES] = bulk stream (weight-gradient GEMMs)
-  cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 1] = {nullptr, nullptr, nullptr, nullptr}, ev_top = nullptr;
+  cudaStream_t lane[MAX_LANES + 1] = {};   // [MAX_LANES] = bulk stream (weight-gradient GEMMs)
+  cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 1] = {}, ev_top = nullptr;
   std::vector<cudaEvent_t> ev_r, ev_dx;              // [layer * MAX_CHUNKS + chunk]
   cudaEvent_t ev_g0[MAX_CHUNKS] = {};                // layer-0 input projection chunks (issued ahead on the bulk stream)
   // state of the last forward
@@ -311,8 +315,11 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
   e->touched = grads ? grads + e->n_params : nullptr;
   bool ok = cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_top, cudaEventDisableTiming) == cudaSuccess;
+  // recurrence lanes outrank the bulk stream: when SMs free up, the latency-critical cooperative launches are placed first
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   for (int i = 0; i <= MAX_LANES && ok; ++i)
-    ok = cudaStreamCreateWithFlags(&e->lane[i], cudaStreamNonBlocking) == cudaSuccess &&
+    ok = cudaStreamCreateWithPriority(&e->lane[i], cudaStreamNonBlocking, (i < MAX_LANES) != (env_int("B2T_BULK_PRIO", 0) != 0) ? prio_hi : prio_lo) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_lane_end[i], cudaEventDisableTiming) == cudaSuccess;
   e->ev_r.assign((size_t)e->L * MAX_CHUNKS, nullptr);
   e->ev_dx.assign((size_t)e->L * MAX_CHUNKS, nullptr);
@@ -362,22 +369,33 @@ static int make_2d(CUtensorMap* tm, const void* p, uint64_t inner, uint64_t rows
   return make_tmap_bf16_4d(tm, p, dims, str, box);
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
-
 static int build_plans(b2t_engine* e) {
   e->poll_delay = env_int("B2T_POLL_DELAY", 700);
   const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp, M = e->M, K0 = e->K0, T = e->T_in;
   const bool tr = e->training != 0;
-  // ---- recurrence geometry: trials per CTA, concurrent launches, time chunks
-  e->BG = (Bp % 32 == 0) ? 32 : 16;
-  const int ctas = (H / 32) * (Bp / e->BG);
-  e->n_lanes = std::max(1, std::min(MAX_LANES, num_sms() / std::max(ctas, 1)));
-  e->n_lanes = std::max(1, std::min(e->n_lanes, env_int("B2T_REC_LANES", MAX_LANES)));
+  // ---- recurrence geometry: trials per CTA, concurrent launches, time chunks.  A tcgen05.mma costs the same for every
+  //      N <= 64 (profiles/r1_mma_dispatch_microbench.md), so wider batch groups need fewer CTAs for the same MMA time.
+  auto pick_bg = [&](const char* env) {
+    // BG = 64 halves the CTAs but doubles what each CTA moves through L2 per step; measured on B200 the step then takes
+    // 1.7-1.9x as long (the exchange is bound per SM), so 32 is the default and 64 stays an opt-in.
+    int bg = (Bp % 64 == 0) ? 64 : (Bp % 32 == 0) ? 32 : 16;
+    const int cap = env_int(env, 32);
+    while (bg > 16 && bg > cap) bg /= 2;
+    while (bg < 64 && Bp % (2 * bg) == 0 && (H / 32) * (Bp / bg) > num_sms()) bg *= 2;   // large batches: all CTAs must be co-resident
+    return bg;
+  };
+  e->BG = pick_bg("B2T_REC_BG_FWD");
+  e->BGb = pick_bg("B2T_REC_BG_BWD");
+  auto pick_lanes = [&](int bg, const char* env) {
+    const int ctas = (H / 32) * (Bp / bg);
+    int n = std::max(1, std::min(MAX_LANES, num_sms() / std::max(ctas, 1)));
+    n = std::min(n, L);
+    return std::max(1, std::min(n, env_int(env, MAX_LANES)));
+  };
+  e->n_lanes = pick_lanes(e->BG, "B2T_REC_LANES_FWD");
+  e->n_lanes_b = pick_lanes(e->BGb, "B2T_REC_LANES_BWD");
   int nch = env_int("B2T_REC_CHUNKS", 0);
-  if (nch <= 0) nch = (e->n_lanes > 1 && Tp >= 48) ? 4 : 1;
+  if (nch <= 0) nch = (std::max(e->n_lanes, e->n_lanes_b) > 1 && Tp >= 48) ? (std::max(e->n_lanes, e->n_lanes_b) >= 5 ? 6 : 3) : 1;
   nch = std::max(1, std::min(std::min(nch, MAX_CHUNKS), Tp));
   e->n_tchunks = nch;
   for (int c = 0; c <= nch; ++c) e->tc_begin[c] = (int)((long long)c * Tp / nch);
@@ -385,7 +403,6 @@ static int build_plans(b2t_engine* e) {
   e->p_dwhh.assign(L, GemmPlan());
   e->p_in.assign(L, std::vector<GemmPlan>(nch));
   e->p_dx.assign(L, std::vector<GemmPlan>(nch));
-  e->tm_h.assign(L, CUtensorMap());
   int rc;
   {  // day layer: xd[b] = softsign(xs[b] @ W_day[day_b] + b_day[day_b]) (+dropout)      rnn_model.py:95-103
     GemmSpec s;
@@ -438,7 +455,6 @@ static int build_plans(b2t_engine* e) {
         if ((rc = gemm_plan_build(&e->p_in[l][c], s))) return fail(B2T_ERR_CUDA, "input plan %d/%d failed (%d)", l, c, rc);
       }
     }
-    if (make_2d(&e->tm_h[l], e->lay[l].hseq, H, (uint64_t)(Tp + 1) * Bp, H, e->BG)) return fail(B2T_ERR_CUDA, "hseq map failed");
   }
   {  // head: logits = top @ W_out^T + b_out                                       rnn_model.py:129
     GemmSpec s;
@@ -574,17 +590,18 @@ static cudaError_t launch_rec_fwd_t(const RecFwdParams& p, int grid, cudaStream_
 }
 template <int BG>
 static cudaError_t launch_rec_bwd_t(const RecBwdParams& p, int grid, cudaStream_t st) {
-  cudaError_t err = cudaFuncSetAttribute(gru_rec_bwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REC_SMEM_BYTES);
+  const size_t smem = std::max(REC_SMEM_BYTES, RecCfg<BG>::bwd_smem_bytes(p.H));
+  cudaError_t err = cudaFuncSetAttribute(gru_rec_bwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kBwdThreads), args, REC_SMEM_BYTES, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kBwdThreads), args, smem, st);
 }
 static cudaError_t launch_rec_fwd(int BG, const RecFwdParams& p, int grid, cudaStream_t st) {
-  return BG == 32 ? launch_rec_fwd_t<32>(p, grid, st) : launch_rec_fwd_t<16>(p, grid, st);
+  return BG == 64 ? launch_rec_fwd_t<64>(p, grid, st) : BG == 32 ? launch_rec_fwd_t<32>(p, grid, st) : launch_rec_fwd_t<16>(p, grid, st);
 }
 static cudaError_t launch_rec_bwd(int BG, const RecBwdParams& p, int grid, cudaStream_t st) {
-  return BG == 32 ? launch_rec_bwd_t<32>(p, grid, st) : launch_rec_bwd_t<16>(p, grid, st);
+  return BG == 64 ? launch_rec_bwd_t<64>(p, grid, st) : BG == 32 ? launch_rec_bwd_t<32>(p, grid, st) : launch_rec_bwd_t<16>(p, grid, st);
 }
 
 // ------------------------------------------------------------------------------------ forward
@@ -610,7 +627,7 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
   const int Tp = b2t_output_frames(&e->cfg, a->T, a->smooth_mode, ntaps, cut);
   if (Tp < 1) return fail(B2T_ERR_ARG, "input too short: T=%d gives no output frame", a->T);
   const int Bp = r16(a->B);
-  if ((H / 32) * (Bp / ((Bp % 32 == 0) ? 32 : 16)) > num_sms())
+  if ((H / 32) * (Bp / ((Bp % 64 == 0) ? 64 : (Bp % 32 == 0) ? 32 : 16)) > num_sms())
     return fail(B2T_ERR_UNSUPPORTED, "batch %d needs more co-resident CTAs than the %d SMs; split the batch", a->B, num_sms());
   if (!e->plans_ok || e->B != a->B || e->T_in != a->T || e->Tp != Tp || e->T_out != T_out || e->day_idx != a->day_idx) {
     e->B = a->B; e->Bpad = Bp; e->T_in = a->T; e->T_out = T_out; e->Tp = Tp; e->M = Tp * Bp; e->day_idx = a->day_idx;
@@ -658,7 +675,7 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
   for (int i = 0; i <= MAX_LANES; ++i) CK(cudaStreamWaitEvent(e->lane[i], e->ev_start, 0));
   // layer-0 input projection: all chunks up front on the bulk stream (they depend on no recurrence)
   for (int c = 0; c < nch; ++c) {
-    TlScope tl(("G0." + std::to_string(c)).c_str(), 3, e->lane[MAX_LANES]);
+    TlScope tl(("G0." + std::to_string(c)).c_str(), 8, e->lane[MAX_LANES]);
     CK(gemm_run(e->p_in[0][c], e->lane[MAX_LANES])); ++g_launches;
     CK(cudaEventRecord(e->ev_g0[c], e->lane[MAX_LANES]));
   }
@@ -667,7 +684,7 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
   //    below) + recurrence over chunk c (needs chunk c-1 of the same layer).  Tasks are list-scheduled onto the lane that
   //    frees first (estimated durations), dependencies are CUDA events, issue order is diagonal by diagonal.
   const bool save = a->training != 0;
-  double lane_free[MAX_LANES] = {0, 0, 0};
+  double lane_free[MAX_LANES] = {};
   std::vector<double> t_end((size_t)L * MAX_CHUNKS, 0.0);
   const double dur_g = 40.0, dur_r = 135.0;
   for (int d = 0; d < nch + L - 1; ++d) {
@@ -833,7 +850,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp;
   const float keep_in = e->cfg.input_dropout > 0.f ? 1.0f - e->cfg.input_dropout : 1.0f;
   const float keep_rnn = e->cfg.rnn_dropout > 0.f ? 1.0f - e->cfg.rnn_dropout : 1.0f;
-  const int BG = e->BG, nch = e->n_tchunks, NL = e->n_lanes;
+  const int BG = e->BGb, nch = e->n_tchunks, NL = e->n_lanes_b;
   const int n_groups = Bp / BG, grid = (H / 32) * n_groups;
   // zero what is accumulated with atomics: biases, h0, day params, touched flags
   CK(cudaMemsetAsync(e->touched, 0, r64(e->cfg.n_days) * sizeof(float), st));
@@ -865,7 +882,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   // wave-front over (layer descending, time chunk descending); k counts chunks from the end of the sequence.
   // Task (l, c) = recurrence over chunk c (needs chunk c+1 of the same layer and dY_l[chunk c] from the layer above)
   // followed by the data-gradient GEMM for the layer below.  Same list scheduling as in forward.
-  double lane_free[MAX_LANES] = {0, 0, 0};
+  double lane_free[MAX_LANES] = {};
   std::vector<double> t_end((size_t)L * MAX_CHUNKS, 0.0);
   const double dur_rb = 215.0, dur_dx = 25.0;
   for (int d = 0; d < nch + L - 1; ++d) {
@@ -904,15 +921,15 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       if (l == 0) {   // layer 0: data gradient (to be folded) and weight gradient of this chunk fill idle SMs on the bulk stream
         cudaStream_t bs = e->lane[MAX_LANES];
         CK(cudaStreamWaitEvent(bs, e->ev_dx[(size_t)c], 0));
-        { TlScope tl(("DX0." + std::to_string(c)).c_str(), 3, bs); CK(gemm_run(e->p_dx[0][c], bs)); ++g_launches; }
-        { TlScope tl(("dWih0." + std::to_string(c)).c_str(), 3, bs); CK(gemm_run(e->p_dwih0[c], bs)); ++g_launches; }
+        { TlScope tl(("DX0." + std::to_string(c)).c_str(), 8, bs); CK(gemm_run(e->p_dx[0][c], bs)); ++g_launches; }
+        { TlScope tl(("dWih0." + std::to_string(c)).c_str(), 8, bs); CK(gemm_run(e->p_dwih0[c], bs)); ++g_launches; }
       }
       if (c == 0) {   // the layer's recurrence is complete: weight gradients over the whole sequence, on the bulk stream
         cudaStream_t bs = e->lane[MAX_LANES];
         CK(cudaEventRecord(e->ev_r[(size_t)l * MAX_CHUNKS], ls));
         CK(cudaStreamWaitEvent(bs, e->ev_r[(size_t)l * MAX_CHUNKS], 0));
-        if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 3, bs); CK(gemm_run(e->p_dwih[l], bs)); ++g_launches; }
-        { TlScope tl(("dWhh" + sl).c_str(), 3, bs); CK(gemm_run(e->p_dwhh[l], bs)); ++g_launches; }
+        if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 8, bs); CK(gemm_run(e->p_dwih[l], bs)); ++g_launches; }
+        { TlScope tl(("dWhh" + sl).c_str(), 8, bs); CK(gemm_run(e->p_dwhh[l], bs)); ++g_launches; }
         if (!e->states_given) {
           reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bs>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
           CK(LAUNCHED());
@@ -923,8 +940,8 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
           fp.day_idx = e->day_idx; fp.B = e->B; fp.Bpad = Bp; fp.T_alloc = e->T_in; fp.T_valid = e->T_out; fp.D = D; fp.Tp = Tp;
           fp.patch = e->patch; fp.stride = e->stride; fp.keep = keep_in; fp.seed = e->seed; fp.rng_offset = 0;
           dim3 g((e->T_in + FOLD_TT - 1) / FOLD_TT, Bp);
-          { TlScope tl("fold", 3, bs); fold_dpre_kernel<<<g, D / 4, 0, bs>>>(fp); CK(LAUNCHED()); }
-          { TlScope tl("daydW", 3, bs); CK(gemm_run(e->p_daydw, bs)); ++g_launches; }
+          { TlScope tl("fold", 8, bs); fold_dpre_kernel<<<g, D / 4, 0, bs>>>(fp); CK(LAUNCHED()); }
+          { TlScope tl("daydW", 8, bs); CK(gemm_run(e->p_daydw, bs)); ++g_launches; }
         }
       }
     }

@@ -44,14 +44,19 @@ constexpr int REC_US = 32;        // hidden units per CTA
 constexpr int REC_TMEM_COLS = 512;
 
 template <int BG> struct RecCfg {
-  static constexpr int kEpiWarps = BG / 4;            // 4 (BG=16) or 8 (BG=32): one thread per (trial, 4 units)
+  static constexpr int kEpiWarps = BG / 4;            // 4 / 8 / 16 (BG = 16 / 32 / 64): one thread per (trial, 4 units)
   static constexpr int kEpiThreads = 32 * kEpiWarps;
-  static constexpr int kLoadWarps = 8;                // forward: warp 0 + the last 7 warps poll/stage h_{t-1} (one 16 B unit per chunk each)
+  static constexpr int kLoadWarps = 8;                // forward: warp 0 + the last 7 warps poll/stage h_{t-1}
   static constexpr int kLoadThreads = 32 * kLoadWarps;
+  static constexpr int kUnitsPerThread = (BG * 8 + kLoadThreads - 1) / kLoadThreads;   // 16 B units per loader thread and 64-column chunk (2 for BG = 64)
+  static constexpr int kPollChunks = kUnitsPerThread == 1 ? 16 : 6;                    // chunks polled together (bounds the registers of a polling round)
   static constexpr int kFwdThreads = 64 + kEpiThreads + 32 * (kLoadWarps - 1);   // warp1 = MMA issuer + TMEM owner
-  static constexpr int kBwdThreads = 64 + kEpiThreads;                          // warp0 idle, warp1 = TMEM owner
+  static constexpr int kBwdThreads = kEpiThreads;                               // every warp is an epilogue warp (warp 0 also owns the TMEM allocation)
+  static constexpr int kGatherBatch = BG == 64 ? 12 : 24;                       // backward: partial blocks polled together (register budget)
   static constexpr int kXPitch = BG + 4;              // exchange row pitch (floats)
   static constexpr size_t fwd_smem_bytes(int H) { return (size_t)2 * (H / 64) * BG * 128 + (size_t)3 * 32 * kXPitch * 4 + 512 + 1024; }
+  // backward: W_slice^T as the K-major A operand (2 chunks of 64 kk) + dG_t as the B operand (2 chunks) + barriers
+  static constexpr size_t bwd_smem_bytes(int H) { return (size_t)2 * ((H + 127) / 128) * 128 * 128 + (size_t)2 * BG * 128 + 256 + 1024; }
 };
 
 struct RecFwdParams {
@@ -191,9 +196,12 @@ gru_rec_fwd_kernel(const RecFwdParams p) {
     // the peers' h_t can land while this CTA's MMA of step t still reads h_{t-1}.
     const int lw = warp == 0 ? 0 : warp - (1 + Cfg::kEpiWarps);
     const int lt = lw * 32 + lane;
-    const bool active = lt < UNITS;
+    constexpr int UPT = Cfg::kUnitsPerThread, PC = Cfg::kPollChunks;
+    constexpr int ROWS_PER_PASS = Cfg::kLoadThreads / 8;   // unit u of a thread is row (lt / 8) + u * ROWS_PER_PASS
+    const bool active = lt < UNITS / UPT;
     const int row = lt >> 3, seg = lt & 7;
-    const uint32_t soff = row * 128 + ((seg ^ (row & 7)) << 4);
+    const uint32_t soff = row * 128 + ((seg ^ (row & 7)) << 4);      // ROWS_PER_PASS is a multiple of 8: same swizzle phase for every unit
+    const size_t g_unit = (size_t)ROWS_PER_PASS * p.H * sizeof(__nv_bfloat16);
     for (int t = p.t_begin; t < p.t_end; ++t) {
       const int step = t - p.t_begin, buf = step & 1;
       // The peers store their slices of h_{t-1} at about the time this CTA stores its own: start polling then
@@ -207,31 +215,43 @@ gru_rec_fwd_kernel(const RecFwdParams p) {
       }
       const uint8_t* g = reinterpret_cast<const uint8_t*>(p.hseq + ((size_t)t * p.Bpad + b0 + row) * p.H) + seg * 16;   // slot t = h_{t-1}
       uint8_t* sdst = sH + (size_t)buf * KC * CHUNK_BYTES + soff;
-      uint4 v[16];
-      uint32_t pending = (1u << KC) - 1u;                  // warp-uniform: chunks not staged yet
-      uint32_t spins = 0;
-      while (pending) {
-        // one polling round: every pending chunk is (re)loaded with all loads in flight together
+      for (int c0 = 0; c0 < KC; c0 += PC) {                  // chunk groups in the order the MMA consumes them
+        uint4 v[PC][UPT];
+        const int nc = KC - c0 < PC ? KC - c0 : PC;
+        uint32_t pending = (1u << nc) - 1u;                  // warp-uniform: chunks of this group not staged yet
+        uint32_t spins = 0;
+        while (pending) {
+          // one polling round: every pending chunk is (re)loaded with all loads in flight together
 #pragma unroll
-        for (int c = 0; c < 16; ++c)
-          if (((pending >> c) & 1u) && active) v[c] = ld_l2_v4(g + c * 128);
+          for (int c = 0; c < PC; ++c)
+            if (((pending >> c) & 1u) && active) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          if ((pending >> c) & 1u) {
-            const bool ok = !active || !has_sentinel(v[c]);
-            if (__all_sync(0xffffffffu, ok)) {
+              for (int u = 0; u < UPT; ++u) v[c][u] = ld_l2_v4(g + (c0 + c) * 128 + u * g_unit);
+            }
+#pragma unroll
+          for (int c = 0; c < PC; ++c) {
+            if ((pending >> c) & 1u) {
+              bool ok = true;
               if (active) {
-                *reinterpret_cast<uint4*>(sdst + c * CHUNK_BYTES) = v[c];
-                fence_proxy_async_smem();          // generic smem write -> visible to the tensor-core (async) proxy
+#pragma unroll
+                for (int u = 0; u < UPT; ++u) ok = ok && !has_sentinel(v[c][u]);
               }
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&bar_h[buf * 16 + c]);
-              if (lt == 0 && c == 0) REC_TRACE(t, 0);      // first chunk of h_{t-1} staged
-              pending &= ~(1u << c);
+              if (__all_sync(0xffffffffu, ok)) {
+                if (active) {
+#pragma unroll
+                  for (int u = 0; u < UPT; ++u)
+                    *reinterpret_cast<uint4*>(sdst + (c0 + c) * CHUNK_BYTES + u * (ROWS_PER_PASS * 128)) = v[c][u];
+                  fence_proxy_async_smem();          // generic smem write -> visible to the tensor-core (async) proxy
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_h[buf * 16 + c0 + c]);
+                if (lt == 0 && c0 + c == 0) REC_TRACE(t, 0);      // first chunk of h_{t-1} staged
+                pending &= ~(1u << c);
+              }
             }
           }
+          if (++spins > REC_MAX_SPINS) __trap();
         }
-        if (++spins > REC_MAX_SPINS) __trap();
       }
       if (lt == 0) REC_TRACE(t, 1);                        // all chunks staged
     }
@@ -382,10 +402,12 @@ __global__ void __launch_bounds__(RecCfg<BG>::kBwdThreads, 1)
 gru_rec_bwd_kernel(const RecBwdParams p) {
   using Cfg = RecCfg<BG>;
   constexpr int CHUNK_BYTES = BG * 128;
-  constexpr int A_PITCH = 48;                            // TMEM columns per 128-row block of W_slice^T (96 kk = 48 words)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sB = smem;                                    // 2 chunks: dG_t as K-major B operand [BG trials][128 kk] (kk = gate*32 + unit, 96 used)
+  const int MB = (p.H + 127) / 128;                      // 128-row blocks of the output (all hidden units)
+  const int A_CHUNK = MB * 128 * 128;                    // bytes of one 64-kk chunk of the A operand
+  uint8_t* sA = smem;                                    // W_slice^T, K-major A operand: [2 chunks of 64 kk][MB*128 rows k][128 B], 128B swizzle
+  uint8_t* sB = sA + 2 * A_CHUNK;                        // 2 chunks: dG_t as K-major B operand [BG trials][128 kk] (kk = gate*32 + unit, 96 used)
   uint64_t* bar_d = reinterpret_cast<uint64_t*>(sB + 2 * CHUNK_BYTES);   // [8]: one per 128-row output block
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 8);
 
@@ -393,54 +415,54 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
   const int NS = p.n_slices, NG = gridDim.x / NS;
   const int slice = blockIdx.x % NS, grp = blockIdx.x / NS;
   const int j0 = slice * REC_US, b0 = grp * BG;
-  const int MB = (p.H + 127) / 128;                      // 128-row blocks of the output (all hidden units)
   const int nsteps = p.t_end - p.t_begin;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(&bar_d[i], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
+  if (warp == 0) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
   for (int i = threadIdx.x; i < 2 * CHUNK_BYTES / 4; i += Cfg::kBwdThreads) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
+
+  // ---- one-time: W_slice^T -> shared memory (the accumulators of all MB output blocks need the whole TMEM for BG = 64,
+  //      and an A operand read from shared memory dispatches faster than one read from TMEM for N <= 64, see
+  //      profiles/r1_mma_dispatch_microbench.md).  Row k (output unit), column kk = gate*32 + unit; one item = two
+  //      adjacent kk (same gate, units u and u+1) x 8 consecutive k: two 16 B global loads, eight 4 B smem stores.
+  //      Consecutive lanes take consecutive kk pairs: the stores of a warp fall into one 128 B row (conflict free).
+  {
+    const int K8 = (MB * 128) / 8;
+    for (int it = threadIdx.x; it < K8 * 48; it += Cfg::kBwdThreads) {
+      const int pr = it % 48, k8 = it / 48;
+      const int kk = 2 * pr, k = k8 * 8;
+      uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+      if (k < p.H) {
+        const __nv_bfloat16* src = p.whh + ((size_t)(kk >> 5) * p.H + j0 + (kk & 31)) * p.H + k;
+        lo = __ldg(reinterpret_cast<const uint4*>(src));
+        hi = __ldg(reinterpret_cast<const uint4*>(src + p.H));      // kk+1 is the next unit of the same gate
+      }
+      const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w}, h[4] = {hi.x, hi.y, hi.z, hi.w};
+      uint8_t* base = sA + (kk >> 6) * A_CHUNK + (kk & 7) * 2;
+      const int ku = (kk & 63) >> 3;                         // 16 B unit of the row
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t a = (l[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu, b = (h[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+        const int kr = k + i;
+        *reinterpret_cast<uint32_t*>(base + kr * 128 + ((ku ^ (kr & 7)) << 4)) = a | (b << 16);
+      }
+    }
+  }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d = tmem_base + MB * A_PITCH;
-
-  // ---- one-time: W_slice^T -> TMEM.  Block mb, lane m holds output unit k = mb*128+m; column w packs
-  //      kk = 2w, 2w+1 with kk = gate*32 + unit (48 words per block).
-  if (warp >= 2 && warp < 6) {
-    const int q = warp & 3;
-    for (int mb = 0; mb < MB; ++mb) {
-      const int k = mb * 128 + q * 32 + lane;
-      for (int w0 = 0; w0 < 48; w0 += 16) {
-        uint32_t v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int kk = 2 * (w0 + i);
-          uint32_t lo = 0, hi = 0;
-          if (k < p.H) {
-            const size_t r0 = ((size_t)(kk >> 5) * p.H + j0 + (kk & 31)) * p.H + k;
-            lo = __bfloat16_as_ushort(p.whh[r0]);
-            hi = __bfloat16_as_ushort(p.whh[r0 + p.H]);   // kk+1 is the next unit of the same gate
-          }
-          v[i] = lo | (hi << 16);
-        }
-        tmem_st16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mb * A_PITCH + w0, v);
-      }
-    }
-    tmem_st_wait();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  const uint32_t tmem_d = tmem_base;
 
   // Steps are indexed s = 0..nsteps-1 for t = t_end-1-s.  The partials published at step s feed dh of step s+1.
-  if (warp >= 2) {
-    const int e = threadIdx.x - 64;
-    const int ew = e >> 5;
-    const int q = warp & 3;
+  {
+    const int e = threadIdx.x;
+    const int ew = warp;
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read
     const int chalf = ew >> 2;
     const int bl = e >> 3, u0 = (e & 7) * 4;
     const int b = b0 + bl, j = j0 + u0;
@@ -460,7 +482,7 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       const uint32_t tag = (uint32_t)(gen >> 1) & 3u;
       const float* base = p.part + ((((size_t)(gen & 1) * NG + grp) * NS + slice) * NS) * (BG * 32) + (ew * 32 + lane) * 4;
       float G[4] = {0.f, 0.f, 0.f, 0.f};                  // (unit = lane, trials 4*ew .. 4*ew+3)
-      constexpr int NB = 24;
+      constexpr int NB = Cfg::kGatherBatch;
       for (int src0 = 0; src0 < NS; src0 += NB) {
         uint4 v[NB];
         uint32_t pending = 0;
@@ -563,12 +585,13 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       if (e == 0) {
         REC_TRACE(s, 2);
         tc_fence_after();
-        const uint32_t sb = smem_u32(sB);
+        const uint32_t sa = smem_u32(sA), sb = smem_u32(sB);
         for (int mb = 0; mb < MB; ++mb) {                // block by block: the drain of block mb overlaps the MMAs of mb+1..
 #pragma unroll
           for (int ks = 0; ks < 6; ++ks) {               // K = 96 = 6 x 16
+            const uint64_t adesc = umma_smem_desc(sa + (ks >> 2) * A_CHUNK + mb * (128 * 128) + (ks & 3) * 32, 16, 1024);
             const uint64_t bdesc = umma_smem_desc(sb + (ks >> 2) * CHUNK_BYTES + (ks & 3) * 32, 16, 1024);
-            umma_bf16_ts(tmem_d + mb * BG, tmem_base + mb * A_PITCH + ks * 8, bdesc, idesc, ks != 0 ? 1u : 0u);
+            umma_bf16(tmem_d + mb * BG, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
           }
           umma_commit(&bar_d[mb]);
         }
@@ -629,7 +652,7 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<REC_TMEM_COLS>(tmem_base);
   }

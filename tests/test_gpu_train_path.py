@@ -91,9 +91,9 @@ def rec_schedule(request, monkeypatch):
     """Recurrence schedules: default, and forced time-chunking / lane counts so that the chunk carry of h and dh and the
     multi-stream wave-front are exercised on the small golden shapes too."""
     if request.param == "chunks3_lanes2":
-        monkeypatch.setenv("B2T_REC_CHUNKS", "3"); monkeypatch.setenv("B2T_REC_LANES", "2")
+        monkeypatch.setenv("B2T_REC_CHUNKS", "3"); monkeypatch.setenv("B2T_REC_LANES_FWD", "2"); monkeypatch.setenv("B2T_REC_LANES_BWD", "2")
     elif request.param == "chunks2_lanes1":
-        monkeypatch.setenv("B2T_REC_CHUNKS", "2"); monkeypatch.setenv("B2T_REC_LANES", "1")
+        monkeypatch.setenv("B2T_REC_CHUNKS", "2"); monkeypatch.setenv("B2T_REC_LANES_FWD", "1"); monkeypatch.setenv("B2T_REC_LANES_BWD", "1")
     return request.param
 
 
@@ -147,3 +147,65 @@ def test_greedy_edit_bit_exact(E):
         want = O.greedy_decode(lg[b], int(in_len[b]))                    # same logits -> integer pipeline must be identical
         assert dec[b, :dlen[b]].cpu().tolist() == want
         assert int(ed[b]) == O.edit_distance(want, rest["labels"][b][:rest["lens"][b]])
+
+
+def _random_params(E, cfg, seed):
+    rng = np.random.RandomState(seed)
+    params = {}
+    for name, off, rows, cols in E.param_layout(cfg):
+        if name.startswith("day_weights"):
+            v = np.eye(rows, cols) + 0.05 * rng.randn(rows, cols)
+        elif "bias" in name or name == "h0":
+            v = 0.1 * rng.randn(rows, cols)
+        else:
+            v = rng.randn(rows, cols) / np.sqrt(cols)
+        params[name] = v.astype(np.float32)
+    return params
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,bg_cap,chunks", [(64, 64, 3), (64, 32, 2), (64, 16, 1), (32, 64, 2), (128, 64, 3), (40, 64, 2)])
+def test_wide_batch_train_step_vs_oracle(E, monkeypatch, B, bg_cap, chunks):
+    """Batch-group widths 16 / 32 / 64 of the recurrence kernels (forward: trials per CTA = MMA N; backward: partial
+    exchange geometry), with H = 192 (two 128-row output blocks, the second one partial) and several time chunks,
+    against the numpy oracle evaluated on the same inputs."""
+    import gru_ctc_oracle as O
+    monkeypatch.setenv("B2T_REC_BG_FWD", str(bg_cap)); monkeypatch.setenv("B2T_REC_BG_BWD", str(bg_cap))
+    monkeypatch.setenv("B2T_REC_CHUNKS", str(chunks))
+    D, H, L, n_days, T = 32, 192, 3, 4, 74
+    cfg = E.make_config(D, H, L, n_days, 41, 14, 4, 0.0, 0.0)
+    params = _random_params(E, cfg, 7)
+    shapes = {"h0": (1, 1, H)}
+    P = O.Params({k: (v.reshape(shapes[k]) if k in shapes else (v.reshape(-1) if "bias" in k and not k.startswith("day") else v))
+                  for k, v in params.items()})
+    rng = np.random.RandomState(11)
+    x = rng.randn(B, T, D).astype(np.float32)
+    n_steps = rng.randint(60, T + 1, size=B); n_steps[0] = T
+    for b in range(B):
+        x[b, n_steps[b]:] = 0
+    lens = rng.randint(2, 6, size=B)
+    labels = np.zeros((B, 8), dtype=np.int64)
+    for b in range(B):
+        labels[b, :lens[b]] = rng.randint(1, 41, size=lens[b])
+    days = rng.randint(0, n_days - 1, size=B)                    # day n_days-1 stays untouched
+    eng = E.Engine(cfg, util.flat_from_params(E, cfg, params, "cuda"), max_batch=B, max_T=T, max_label_len=8, training=True)
+    logits, _ = eng.forward(torch.from_numpy(x).cuda(), torch.from_numpy(days.astype(np.int32)), training=True, smooth_mode=1)
+    in_len = O.adjusted_lens(n_steps)
+    loss = eng.ctc_loss(torch.from_numpy(labels.astype(np.int32)), torch.from_numpy(in_len.astype(np.int32)),
+                        torch.from_numpy(lens.astype(np.int32)), grad_scale=1.0 / B)
+    eng.backward()
+    torch.cuda.synchronize()
+    xs, _ = O.transform_data(x, n_steps, mode="val")
+    ref_logits, _, cache = O.forward(P, xs, days, keep_cache=True)
+    assert np.abs(logits.cpu().numpy() - ref_logits).max() < 5e-2
+    ref_loss, dlog = O.ctc_loss_and_grad(ref_logits, labels, in_len, lens)
+    assert util.rel_err(loss.cpu().numpy(), ref_loss) < 2e-2
+    ref_g = O.backward(P, cache, dlog, days)          # dlog already carries the 1/B of the batch mean
+    got = util.unflatten(E, cfg, eng.grads[:eng.n_params])
+    bad = {}
+    for k, g in ref_g.items():
+        r = util.rel_err(got[k].reshape(np.asarray(g).shape), g)
+        if r >= 6e-2:
+            bad[k] = round(r, 4)
+    assert not bad, bad
+    assert np.abs(got[f"day_weights.{n_days - 1}"]).max() == 0.0
