@@ -240,11 +240,13 @@ def run_ours(args):
     # per-kernel view of one more step (CUDA events around every task on its own stream, engine timeline facility): where the
     # step's time goes and what each kernel class achieves against the share of the chip it occupies
     kernels = None
+    torch.cuda.synchronize()
+    if rank == 0:
+        N.lib.b2t_debug_timeline(1)
+    step(3, False)                                           # every rank takes part (the step holds a collective when world > 1)
+    torch.cuda.synchronize()
     if rank == 0:
         import ctypes
-        torch.cuda.synchronize()
-        N.lib.b2t_debug_timeline(1)
-        step(3, False)
         buf = ctypes.create_string_buffer(1 << 16)
         N.lib.b2t_debug_dump_timeline(buf, 1 << 16)
         N.lib.b2t_debug_timeline(0)

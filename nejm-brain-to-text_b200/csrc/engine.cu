@@ -13,6 +13,7 @@
 #include "elementwise.cuh"
 #include "gemm.h"
 #include "gru_rec.cuh"
+#include "gru_rec_bwd2.cuh"
 #include "optim.cuh"
 #include "tmap.h"
 
@@ -153,7 +154,7 @@ struct b2t_engine {
   std::vector<LayerBuf> lay;
   int *steps, *greedy_scratch;
   int part_geom = -1;
-  int poll_delay = 0;
+  int poll_delay = 0, poll_delay_b = 0;
   float *sumsq, *stats;
   Segment* d_segs;
   ChunkRef* d_chunks;
@@ -161,7 +162,7 @@ struct b2t_engine {
   float* touched;             // tail of the gradient buffer: [n_days]
   // current shape + plans
   int B = 0, Bpad = 0, T_in = 0, T_out = 0, Tp = 0, M = 0;
-  int BG = 16, BGb = 16, n_tchunks = 1, n_lanes = 1, n_lanes_b = 1;   // forward / backward trials per CTA and concurrent launches
+  int BG = 16, BGb = 16, NSUBb = 1, bwd2 = 0, n_tchunks = 1, n_lanes = 1, n_lanes_b = 1;   // forward / backward trials per CTA and concurrent launches
   int tc_begin[MAX_CHUNKS + 1];
   bool plans_ok = false, use_unfold_copy = false;
   GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw;
@@ -371,6 +372,7 @@ static int make_2d(CUtensorMap* tm, const void* p, uint64_t inner, uint64_t rows
 
 static int build_plans(b2t_engine* e) {
   e->poll_delay = env_int("B2T_POLL_DELAY", 700);
+  e->poll_delay_b = env_int("B2T_POLL_DELAY_BWD", 300);
   const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp, M = e->M, K0 = e->K0, T = e->T_in;
   const bool tr = e->training != 0;
   // ---- recurrence geometry: trials per CTA, concurrent launches, time chunks.  A tcgen05.mma costs the same for every
@@ -386,6 +388,17 @@ static int build_plans(b2t_engine* e) {
   };
   e->BG = pick_bg("B2T_REC_BG_FWD");
   e->BGb = pick_bg("B2T_REC_BG_BWD");
+  // backward: a CTA can host NSUB independent batch groups (gru_rec.cuh).  Measured on B200: two groups of 16 take as long per
+  // step as one group of 32 (the step is a chain of latencies, not of bytes), so one group per CTA stays the default.
+  e->NSUBb = 1;
+  {
+    const int want = env_int("B2T_REC_NSUB_BWD", 0);
+    if (want > 0) e->NSUBb = want;
+    while (e->NSUBb > 1 && ((Bp / e->BGb) % e->NSUBb != 0 || !((e->BGb == 16 && (e->NSUBb == 2 || e->NSUBb == 4)) || (e->BGb == 32 && e->NSUBb == 2)))) e->NSUBb /= 2;
+  }
+  // backward kernel: the 2-D decomposition (4-way partial reduction + dG all-gather) needs H/4 to be a multiple of 64
+  e->bwd2 = (H % 256 == 0 && e->BGb <= 32 && env_int("B2T_REC_BWD2", 0) != 0) ? 1 : 0;
+  if (e->bwd2) e->NSUBb = 1;
   auto pick_lanes = [&](int bg, const char* env) {
     const int ctas = (H / 32) * (Bp / bg);
     int n = std::max(1, std::min(MAX_LANES, num_sms() / std::max(ctas, 1)));
@@ -393,7 +406,7 @@ static int build_plans(b2t_engine* e) {
     return std::max(1, std::min(n, env_int(env, MAX_LANES)));
   };
   e->n_lanes = pick_lanes(e->BG, "B2T_REC_LANES_FWD");
-  e->n_lanes_b = pick_lanes(e->BGb, "B2T_REC_LANES_BWD");
+  e->n_lanes_b = pick_lanes(e->BGb * e->NSUBb, "B2T_REC_LANES_BWD");
   int nch = env_int("B2T_REC_CHUNKS", 0);
   if (nch <= 0) nch = (std::max(e->n_lanes, e->n_lanes_b) > 1 && Tp >= 48) ? (std::max(e->n_lanes, e->n_lanes_b) >= 5 ? 6 : 3) : 1;
   nch = std::max(1, std::min(std::min(nch, MAX_CHUNKS), Tp));
@@ -588,20 +601,38 @@ static cudaError_t launch_rec_fwd_t(const RecFwdParams& p, int grid, cudaStream_
   ++g_launches;
   return cudaLaunchCooperativeKernel((const void*)gru_rec_fwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kFwdThreads), args, smem, st);
 }
-template <int BG>
+template <int BG, int NSUB>
 static cudaError_t launch_rec_bwd_t(const RecBwdParams& p, int grid, cudaStream_t st) {
-  const size_t smem = std::max(REC_SMEM_BYTES, RecCfg<BG>::bwd_smem_bytes(p.H));
-  cudaError_t err = cudaFuncSetAttribute(gru_rec_bwd_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = std::max(REC_SMEM_BYTES, RecCfg<BG>::bwd_smem_bytes(p.H, NSUB));
+  cudaError_t err = cudaFuncSetAttribute(gru_rec_bwd_kernel<BG, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd_kernel<BG>, dim3(grid), dim3(RecCfg<BG>::kBwdThreads), args, smem, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd_kernel<BG, NSUB>, dim3(grid), dim3((RecCfg<BG>::kBwdThreads + 32) * NSUB), args, smem, st);
 }
 static cudaError_t launch_rec_fwd(int BG, const RecFwdParams& p, int grid, cudaStream_t st) {
   return BG == 64 ? launch_rec_fwd_t<64>(p, grid, st) : BG == 32 ? launch_rec_fwd_t<32>(p, grid, st) : launch_rec_fwd_t<16>(p, grid, st);
 }
-static cudaError_t launch_rec_bwd(int BG, const RecBwdParams& p, int grid, cudaStream_t st) {
-  return BG == 64 ? launch_rec_bwd_t<64>(p, grid, st) : BG == 32 ? launch_rec_bwd_t<32>(p, grid, st) : launch_rec_bwd_t<16>(p, grid, st);
+template <int BG>
+static cudaError_t launch_rec_bwd2_t(const RecBwdParams& p, int grid, cudaStream_t st) {
+  const size_t smem = std::max(REC_SMEM_BYTES, RecBwd2Cfg<BG>::smem_bytes(p.H));
+  cudaError_t err = cudaFuncSetAttribute(gru_rec_bwd2_kernel<BG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  void* args[1] = {(void*)&p};
+  ++g_launches;
+  return cudaLaunchCooperativeKernel((const void*)gru_rec_bwd2_kernel<BG>, dim3(grid), dim3(RecBwd2Cfg<BG>::kThreads), args, smem, st);
+}
+// two-dimensional decomposition (gru_rec_bwd2.cuh): grid = H/32 CTAs per batch group
+static cudaError_t launch_rec_bwd2(int BG, const RecBwdParams& p, int grid, cudaStream_t st) {
+  return BG == 32 ? launch_rec_bwd2_t<32>(p, grid, st) : launch_rec_bwd2_t<16>(p, grid, st);
+}
+// backward: `nsub` batch groups of BG trials per CTA (grid = slices x groups / nsub)
+static cudaError_t launch_rec_bwd(int BG, int nsub, const RecBwdParams& p, int grid, cudaStream_t st) {
+  if (BG == 16 && nsub == 2) return launch_rec_bwd_t<16, 2>(p, grid, st);
+  if (BG == 16 && nsub == 4) return launch_rec_bwd_t<16, 4>(p, grid, st);
+  if (BG == 32 && nsub == 2) return launch_rec_bwd_t<32, 2>(p, grid, st);
+  if (nsub != 1) return cudaErrorInvalidValue;
+  return BG == 64 ? launch_rec_bwd_t<64, 1>(p, grid, st) : BG == 32 ? launch_rec_bwd_t<32, 1>(p, grid, st) : launch_rec_bwd_t<16, 1>(p, grid, st);
 }
 
 // ------------------------------------------------------------------------------------ forward
@@ -851,7 +882,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   const float keep_in = e->cfg.input_dropout > 0.f ? 1.0f - e->cfg.input_dropout : 1.0f;
   const float keep_rnn = e->cfg.rnn_dropout > 0.f ? 1.0f - e->cfg.rnn_dropout : 1.0f;
   const int BG = e->BGb, nch = e->n_tchunks, NL = e->n_lanes_b;
-  const int n_groups = Bp / BG, grid = (H / 32) * n_groups;
+  const int n_groups = Bp / BG, grid = (H / 32) * n_groups / e->NSUBb;
   // zero what is accumulated with atomics: biases, h0, day params, touched flags
   CK(cudaMemsetAsync(e->touched, 0, r64(e->cfg.n_days) * sizeof(float), st));
   mark_days_kernel<<<(e->B + 127) / 128, 128, 0, st>>>(e->day_idx, e->B, e->touched);
@@ -862,12 +893,15 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   for (int l = 0; l < L; ++l)
     CK(cudaMemsetAsync(e->grads + seg_off(e, "gru.bias_ih_l" + std::to_string(l)), 0, (size_t)2 * r64(3 * H) * sizeof(float), st));
   CK(cudaMemsetAsync(e->grads + seg_off(e, "out.bias"), 0, (size_t)(r64(e->C) + r64(H)) * sizeof(float), st));
-  if (e->part_geom != Bp * 64 + BG) {   // partial-exchange buffers: (re)start the generation tags (gru_rec.cuh) for this geometry
+  if (e->bwd2) {   // the dGh arrays double as the exchange medium of gru_rec_bwd2_kernel: "not written yet" sentinel
+    for (int l = 0; l < L; ++l) CK(cudaMemsetAsync(e->lay[l].dGh, 0xFF, (size_t)e->M * 3 * H * sizeof(__nv_bfloat16), st));
+  }
+  if (e->part_geom != (Bp * 64 + BG) * 2 + e->bwd2) {   // partial-exchange buffers: (re)start the generation tags (gru_rec.cuh) for this geometry
     for (int l = 0; l < L; ++l) {
       CK(cudaMemsetAsync(e->lay[l].part, 0xFF, (size_t)2 * Bp * (H / 32) * (H / 32) * 32 * sizeof(float), st));
       e->lay[l].gen = 0;
     }
-    e->part_geom = Bp * 64 + BG;
+    e->part_geom = (Bp * 64 + BG) * 2 + e->bwd2;
   }
 
   // head
@@ -915,7 +949,8 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       bp.keep = (l < L - 1) ? keep_rnn : 1.0f;
       bp.seed = e->seed; bp.rng_offset = (unsigned long long)(l + 1) << 40;
       bp.trace = (l == L - 1 && c == nch - 1 && e->trace) ? e->trace + (size_t)Tp * 8 : nullptr;
-      { TlScope tl(("RB" + sl + "." + std::to_string(c)).c_str(), li, ls); CK(launch_rec_bwd(BG, bp, grid, ls)); }
+      bp.poll_delay = e->poll_delay_b;
+      { TlScope tl(("RB" + sl + "." + std::to_string(c)).c_str(), li, ls); CK(e->bwd2 ? launch_rec_bwd2(BG, bp, grid, ls) : launch_rec_bwd(BG, e->NSUBb, bp, grid, ls)); }
       if (l > 0) { TlScope tl(("DX" + sl + "." + std::to_string(c)).c_str(), li, ls); CK(gemm_run(e->p_dx[l][c], ls)); ++g_launches; }
       CK(cudaEventRecord(e->ev_dx[(size_t)l * MAX_CHUNKS + c], ls));
       if (l == 0) {   // layer 0: data gradient (to be folded) and weight gradient of this chunk fill idle SMs on the bulk stream

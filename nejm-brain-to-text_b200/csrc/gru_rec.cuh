@@ -51,12 +51,11 @@ template <int BG> struct RecCfg {
   static constexpr int kUnitsPerThread = (BG * 8 + kLoadThreads - 1) / kLoadThreads;   // 16 B units per loader thread and 64-column chunk (2 for BG = 64)
   static constexpr int kPollChunks = kUnitsPerThread == 1 ? 16 : 6;                    // chunks polled together (bounds the registers of a polling round)
   static constexpr int kFwdThreads = 64 + kEpiThreads + 32 * (kLoadWarps - 1);   // warp1 = MMA issuer + TMEM owner
-  static constexpr int kBwdThreads = kEpiThreads;                               // every warp is an epilogue warp (warp 0 also owns the TMEM allocation)
-  static constexpr int kGatherBatch = BG == 64 ? 12 : 24;                       // backward: partial blocks polled together (register budget)
+  static constexpr int kBwdThreads = kEpiThreads;                               // epilogue threads per batch group (the kernel adds one MMA-issuing warp per group)
   static constexpr int kXPitch = BG + 4;              // exchange row pitch (floats)
   static constexpr size_t fwd_smem_bytes(int H) { return (size_t)2 * (H / 64) * BG * 128 + (size_t)3 * 32 * kXPitch * 4 + 512 + 1024; }
   // backward: W_slice^T as the K-major A operand (2 chunks of 64 kk) + dG_t as the B operand (2 chunks) + barriers
-  static constexpr size_t bwd_smem_bytes(int H) { return (size_t)2 * ((H + 127) / 128) * 128 * 128 + (size_t)2 * BG * 128 + 256 + 1024; }
+  static constexpr size_t bwd_smem_bytes(int H, int nsub) { return (size_t)2 * ((H + 127) / 128) * 128 * 128 + (size_t)nsub * (2 * BG * 128 + 64) + 64 + 1024; }
 };
 
 struct RecFwdParams {
@@ -78,6 +77,7 @@ struct RecFwdParams {
 };
 
 #define REC_TRACE(step, slot) do { if (p.trace && blockIdx.x == 0) p.trace[(step) * 8 + (slot)] = clock64(); } while (0)
+#define REC_TRACE_G0(step, slot) do { if (sub == 0) REC_TRACE(step, slot); } while (0)   // backward: group 0 of the CTA only
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
@@ -85,9 +85,18 @@ template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile(
 constexpr uint32_t REC_SENTINEL = 0xFFFFFFFFu;       // "not written yet" marker of an hseq word (two bf16)
 constexpr uint32_t REC_MAX_SPINS = 1u << 24;           // bounded polling: a lost peer traps instead of hanging the GPU
 
+#ifndef B2T_POLL_RELAXED
+#define B2T_POLL_RELAXED 0
+#endif
+// Poll load of the backward exchanges.  tools/ubench/l2_signal.cu: a ping-pong through L2 takes ~1200 cycles per round trip with
+// ld.relaxed.gpu polls and far less with ld.global.cg polls (L2 only, never L1), so the cache-global flavour is the default.
 __device__ __forceinline__ uint4 ld_relaxed_v4(const void* ptr) {
   uint4 v;
+#if B2T_POLL_RELAXED
   asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+#else
+  asm volatile("ld.global.cg.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+#endif
   return v;
 }
 // Poll load for the forward exchange: cache-global (L2 only, never L1), so every execution reads the point of
@@ -132,6 +141,47 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ uint4 rec_dropout_bits(unsigned long long seed, unsigned long long offset, unsigned long long elem4) {
   const unsigned long long c = elem4 + offset;
   return philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x6a7eu, 0), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+// One group of up to PC chunks of a K-major B operand: poll the 16-byte units this thread owns (UPT per chunk, g_unit bytes
+// apart in global memory, s_unit bytes apart in shared memory) until no word is the sentinel, stage them (the caller's sdst
+// already carries the swizzled offset of the thread's first unit) and report each chunk once the whole warp has staged it.
+// A polling round (re)loads every pending chunk with all loads in flight together.
+template <int PC, int UPT, typename AddrF, typename DoneF>
+__device__ __forceinline__ void poll_and_stage(int nc, bool active, AddrF gaddr, size_t g_unit, uint8_t* sdst, int s_chunk, int s_unit, DoneF done) {
+  uint4 v[PC * UPT];
+  uint32_t pending = (1u << nc) - 1u;                        // warp-uniform: chunks of this group not staged yet
+  uint32_t spins = 0;
+  while (pending) {
+#pragma unroll
+    for (int c = 0; c < PC; ++c)
+      if (((pending >> c) & 1u) && active) {
+        const uint8_t* src = gaddr(c);
+#pragma unroll
+        for (int u = 0; u < UPT; ++u) v[c * UPT + u] = ld_l2_v4(src + u * g_unit);
+      }
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      if ((pending >> c) & 1u) {
+        bool ok = true;
+        if (active) {
+#pragma unroll
+          for (int u = 0; u < UPT; ++u) ok = ok && !has_sentinel(v[c * UPT + u]);
+        }
+        if (__all_sync(0xffffffffu, ok)) {
+          if (active) {
+#pragma unroll
+            for (int u = 0; u < UPT; ++u) *reinterpret_cast<uint4*>(sdst + c * s_chunk + u * s_unit) = v[c * UPT + u];
+            fence_proxy_async_smem();                        // generic smem write -> visible to the tensor-core (async) proxy
+          }
+          __syncwarp();
+          done(c);
+          pending &= ~(1u << c);
+        }
+      }
+    }
+    if (++spins > REC_MAX_SPINS) __trap();
+  }
 }
 
 template <int BG>
@@ -215,42 +265,21 @@ gru_rec_fwd_kernel(const RecFwdParams p) {
       }
       const uint8_t* g = reinterpret_cast<const uint8_t*>(p.hseq + ((size_t)t * p.Bpad + b0 + row) * p.H) + seg * 16;   // slot t = h_{t-1}
       uint8_t* sdst = sH + (size_t)buf * KC * CHUNK_BYTES + soff;
-      for (int c0 = 0; c0 < KC; c0 += PC) {                  // chunk groups in the order the MMA consumes them
-        uint4 v[PC][UPT];
-        const int nc = KC - c0 < PC ? KC - c0 : PC;
-        uint32_t pending = (1u << nc) - 1u;                  // warp-uniform: chunks of this group not staged yet
-        uint32_t spins = 0;
-        while (pending) {
-          // one polling round: every pending chunk is (re)loaded with all loads in flight together
-#pragma unroll
-          for (int c = 0; c < PC; ++c)
-            if (((pending >> c) & 1u) && active) {
-#pragma unroll
-              for (int u = 0; u < UPT; ++u) v[c][u] = ld_l2_v4(g + (c0 + c) * 128 + u * g_unit);
-            }
-#pragma unroll
-          for (int c = 0; c < PC; ++c) {
-            if ((pending >> c) & 1u) {
-              bool ok = true;
-              if (active) {
-#pragma unroll
-                for (int u = 0; u < UPT; ++u) ok = ok && !has_sentinel(v[c][u]);
-              }
-              if (__all_sync(0xffffffffu, ok)) {
-                if (active) {
-#pragma unroll
-                  for (int u = 0; u < UPT; ++u)
-                    *reinterpret_cast<uint4*>(sdst + (c0 + c) * CHUNK_BYTES + u * (ROWS_PER_PASS * 128)) = v[c][u];
-                  fence_proxy_async_smem();          // generic smem write -> visible to the tensor-core (async) proxy
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_h[buf * 16 + c0 + c]);
-                if (lt == 0 && c0 + c == 0) REC_TRACE(t, 0);      // first chunk of h_{t-1} staged
-                pending &= ~(1u << c);
-              }
-            }
-          }
-          if (++spins > REC_MAX_SPINS) __trap();
+      if constexpr (PC >= 16) {                              // all chunks (KC <= 16) in one group: no group loop (it costs registers)
+        uint64_t* bars = &bar_h[buf * 16];
+        poll_and_stage<PC, UPT>(KC, active, [&](int c) { return g + c * 128; }, g_unit, sdst, CHUNK_BYTES, ROWS_PER_PASS * 128, [&](int c) {
+          if (lane == 0) mbar_arrive(&bars[c]);
+          if (lt == 0 && c == 0) REC_TRACE(t, 0);          // first chunk of h_{t-1} staged
+        });
+      } else {
+        for (int c0 = 0; c0 < KC; c0 += PC) {                // chunk groups in the order the MMA consumes them
+          const uint8_t* gg = g + c0 * 128;
+          uint64_t* bars = &bar_h[buf * 16 + c0];
+          poll_and_stage<PC, UPT>(KC - c0 < PC ? KC - c0 : PC, active, [&](int c) { return gg + c * 128; }, g_unit,
+                                  sdst + (size_t)c0 * CHUNK_BYTES, CHUNK_BYTES, ROWS_PER_PASS * 128, [&](int c) {
+                                    if (lane == 0) mbar_arrive(&bars[c]);
+                                    if (lt == 0 && c0 + c == 0) REC_TRACE(t, 0);
+                                  });
         }
       }
       if (lt == 0) REC_TRACE(t, 1);                        // all chunks staged
@@ -392,37 +421,47 @@ struct RecBwdParams {
                                     //                  recurrent part of dh_{t_begin-1} on exit (= grad wrt the initial state at t_begin = 0)
   int first_chunk;                  // 1: t_end == T, no incoming recurrent gradient
   int n_valid;                      // trials < n_valid contribute (pad trials are masked out)
+  int poll_delay;                   // gru_rec_bwd2_kernel: cycles between publishing dG_t and the first polling round
   float keep;                       // dropout applied to this layer's output in forward (1 => none)
   unsigned long long seed, rng_offset;
   long long* trace;                 // optional [T][8] clock64 samples from CTA 0
 };
 
-template <int BG>
-__global__ void __launch_bounds__(RecCfg<BG>::kBwdThreads, 1)
+// NSUB independent batch groups of BG trials share one CTA (and one copy of W_slice^T): each group has its own epilogue
+// warps, dG operand, accumulator columns, barriers and exchange blocks, and runs the step loop on its own.  A group's step is
+// a chain of latencies (gather partials through L2 -> gate math -> MMAs -> drain -> publish); with two groups per CTA the
+// chain of one overlaps the other's, which nearly doubles the trials a CTA advances per unit time.
+template <int BG, int NSUB>
+__global__ void __launch_bounds__((RecCfg<BG>::kBwdThreads + 32) * NSUB, 1)
 gru_rec_bwd_kernel(const RecBwdParams p) {
   using Cfg = RecCfg<BG>;
   constexpr int CHUNK_BYTES = BG * 128;
+  constexpr int NTHREADS = (Cfg::kBwdThreads + 32) * NSUB;  // per group: kBwdThreads epilogue threads, then (after all of those) one MMA-issuing warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int MB = (p.H + 127) / 128;                      // 128-row blocks of the output (all hidden units)
   const int A_CHUNK = MB * 128 * 128;                    // bytes of one 64-kk chunk of the A operand
+  const bool is_issuer = threadIdx.x >= Cfg::kBwdThreads * NSUB;
+  const int sub = is_issuer ? (threadIdx.x - Cfg::kBwdThreads * NSUB) >> 5 : threadIdx.x / Cfg::kBwdThreads;   // batch group within the CTA (warp-uniform)
   uint8_t* sA = smem;                                    // W_slice^T, K-major A operand: [2 chunks of 64 kk][MB*128 rows k][128 B], 128B swizzle
-  uint8_t* sB = sA + 2 * A_CHUNK;                        // 2 chunks: dG_t as K-major B operand [BG trials][128 kk] (kk = gate*32 + unit, 96 used)
-  uint64_t* bar_d = reinterpret_cast<uint64_t*>(sB + 2 * CHUNK_BYTES);   // [8]: one per 128-row output block
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d + 8);
+  uint8_t* sB_all = sA + 2 * A_CHUNK;                    // per group, 2 chunks: dG_t as K-major B operand [BG trials][128 kk] (kk = gate*32 + unit, 96 used)
+  uint8_t* sB = sB_all + sub * 2 * CHUNK_BYTES;
+  uint64_t* bar_all = reinterpret_cast<uint64_t*>(sB_all + NSUB * 2 * CHUNK_BYTES);
+  uint64_t* bar_d = bar_all + sub * 8;                   // [8] per group: one per 128-row output block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_all + NSUB * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NS = p.n_slices, NG = gridDim.x / NS;
-  const int slice = blockIdx.x % NS, grp = blockIdx.x / NS;
+  const int NS = p.n_slices, NG = (gridDim.x / NS) * NSUB;
+  const int slice = blockIdx.x % NS, grp = (blockIdx.x / NS) * NSUB + sub;
   const int j0 = slice * REC_US, b0 = grp * BG;
   const int nsteps = p.t_end - p.t_begin;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; ++i) mbar_init(&bar_d[i], 1);
+    for (int i = 0; i < 8 * NSUB; ++i) mbar_init(&bar_all[i], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < 2 * CHUNK_BYTES / 4; i += Cfg::kBwdThreads) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
+  for (int i = threadIdx.x; i < NSUB * 2 * CHUNK_BYTES / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(sB_all)[i] = 0u;
 
   // ---- one-time: W_slice^T -> shared memory (the accumulators of all MB output blocks need the whole TMEM for BG = 64,
   //      and an A operand read from shared memory dispatches faster than one read from TMEM for N <= 64, see
@@ -431,7 +470,7 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
   //      Consecutive lanes take consecutive kk pairs: the stores of a warp fall into one 128 B row (conflict free).
   {
     const int K8 = (MB * 128) / 8;
-    for (int it = threadIdx.x; it < K8 * 48; it += Cfg::kBwdThreads) {
+    for (int it = threadIdx.x; it < K8 * 48; it += NTHREADS) {
       const int pr = it % 48, k8 = it / 48;
       const int kk = 2 * pr, k = k8 * 8;
       uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
@@ -456,19 +495,41 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d = tmem_base;
+  const uint32_t tmem_d = tmem_base + sub * MB * BG;       // this group's accumulators: MB blocks of BG columns
 
   // Steps are indexed s = 0..nsteps-1 for t = t_end-1-s.  The partials published at step s feed dh of step s+1.
-  {
-    const int e = threadIdx.x;
-    const int ew = warp;
-    const int q = warp & 3;                                // TMEM lane quarter this warp may read
+  constexpr uint32_t idesc = umma_idesc_bf16(128, BG, 0, 0);
+  if (is_issuer) {
+    // ---------------- MMA issuer of this group: waits until the epilogue warps have written dG_t, then issues block by block
+    // (the drain of block mb by the epilogue warps overlaps the MMAs of blocks mb+1..)
+    const uint32_t sa = smem_u32(sA), sb = smem_u32(sB);
+    for (int s = 0; s < nsteps; ++s) {
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + sub), "n"(Cfg::kEpiThreads + 32) : "memory");
+      if (elect_one()) {
+        if (sub == 0) REC_TRACE(s, 2);
+        tc_fence_after();
+        for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+          for (int ks = 0; ks < 6; ++ks) {               // K = 96 = 6 x 16
+            const uint64_t adesc = umma_smem_desc(sa + (ks >> 2) * A_CHUNK + mb * (128 * 128) + (ks & 3) * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(sb + (ks >> 2) * CHUNK_BYTES + (ks & 3) * 32, 16, 1024);
+            umma_bf16(tmem_d + mb * BG, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
+          }
+          umma_commit(&bar_d[mb]);
+        }
+        if (sub == 0) REC_TRACE(s, 3);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int e = threadIdx.x - sub * Cfg::kBwdThreads;
+    const int ew = e >> 5;
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read (kEpiWarps is a multiple of 4)
     const int chalf = ew >> 2;
     const int bl = e >> 3, u0 = (e & 7) * 4;
     const int b = b0 + bl, j = j0 + u0;
     const bool valid = b < p.n_valid;
     const float inv_keep = 1.0f / p.keep;
-    constexpr uint32_t idesc = umma_idesc_bf16(128, BG, 0, 0);
     float carry[4] = {0.f, 0.f, 0.f, 0.f};               // dh_{t+1} * z_{t+1}
     float accx[3][4], acch[4];                           // bias-gradient partial sums (dGh differs only in n)
 #pragma unroll
@@ -482,7 +543,7 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       const uint32_t tag = (uint32_t)(gen >> 1) & 3u;
       const float* base = p.part + ((((size_t)(gen & 1) * NG + grp) * NS + slice) * NS) * (BG * 32) + (ew * 32 + lane) * 4;
       float G[4] = {0.f, 0.f, 0.f, 0.f};                  // (unit = lane, trials 4*ew .. 4*ew+3)
-      constexpr int NB = Cfg::kGatherBatch;
+      constexpr int NB = NTHREADS > 256 ? 12 : 24;          // partial blocks polled together (register budget: 128 regs at 512 threads)
       for (int src0 = 0; src0 < NS; src0 += NB) {
         uint4 v[NB];
         uint32_t pending = 0;
@@ -518,14 +579,28 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       }
     };
 
+    // BPTT stash of one step, kept as raw words: the loads for step s+1 are issued while step s drains its accumulators,
+    // so their latency never sits between two exchanges.
+    struct Stash { uint2 r, z, n, hn, hp; float4 dy; };
+    auto load_stash = [&](int t) {
+      const size_t off = ((size_t)t * p.Bpad + b) * p.H + j;
+      Stash st;
+      st.r = __ldg(reinterpret_cast<const uint2*>(p.R + off)); st.z = __ldg(reinterpret_cast<const uint2*>(p.Z + off));
+      st.n = __ldg(reinterpret_cast<const uint2*>(p.Nn + off)); st.hn = __ldg(reinterpret_cast<const uint2*>(p.HN + off));
+      st.hp = *reinterpret_cast<const uint2*>(p.hseq + off);             // slot t = h_{t-1}
+      st.dy = __ldg(reinterpret_cast<const float4*>(p.dY + off));
+      return st;
+    };
+    auto unpack = [](const uint2& u, float (&f)[4]) {
+      const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+      f[0] = __low2float(lo); f[1] = __high2float(lo); f[2] = __low2float(hi); f[3] = __high2float(hi);
+    };
+    Stash cur = load_stash(p.t_end - 1);
+
     for (int s = 0; s < nsteps; ++s) {
       const int t = p.t_end - 1 - s;
       const size_t row = (size_t)t * p.Bpad + b;
       const size_t off = row * p.H + j;
-      float r[4], z[4], n[4], hn[4], hp[4];
-      ld_bf16x4(p.R + off, r); ld_bf16x4(p.Z + off, z); ld_bf16x4(p.Nn + off, n); ld_bf16x4(p.HN + off, hn);
-      ld_bf16x4(p.hseq + off, hp);                       // slot t = h_{t-1}
-      float4 dyv = __ldg(reinterpret_cast<const float4*>(p.dY + off));
       float dmask[4] = {1.0f, 1.0f, 1.0f, 1.0f};         // dropout of this layer's output (same Philox stream as forward)
       if (p.keep < 1.0f) {
         const uint4 rnd = rec_dropout_bits(p.seed, p.rng_offset, off >> 2);
@@ -535,11 +610,13 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       }
       float P[4] = {0.f, 0.f, 0.f, 0.f};
       if (s > 0) {
-        if (e == 0) REC_TRACE(s, 0);
+        if (e == 0) REC_TRACE_G0(s, 0);
         gather_partials(p.gen_base + s - 1, P);          // polls until the partials of step s-1 from every CTA of the group are there
-        if (e == 0) REC_TRACE(s, 1);
+        if (e == 0) REC_TRACE_G0(s, 1);
       }
-      const float dy[4] = {dyv.x * dmask[0], dyv.y * dmask[1], dyv.z * dmask[2], dyv.w * dmask[3]};
+      float r[4], z[4], n[4], hn[4], hp[4];
+      unpack(cur.r, r); unpack(cur.z, z); unpack(cur.n, n); unpack(cur.hn, hn); unpack(cur.hp, hp);
+      const float dy[4] = {cur.dy.x * dmask[0], cur.dy.y * dmask[1], cur.dy.z * dmask[2], cur.dy.w * dmask[3]};
       float dh[4];
       if (s > 0) {
 #pragma unroll
@@ -581,37 +658,14 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
       }
       fence_proxy_async_smem();                          // generic smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
-      epi_bar_sync<Cfg::kEpiThreads>();
-      if (e == 0) {
-        REC_TRACE(s, 2);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(sA), sb = smem_u32(sB);
-        for (int mb = 0; mb < MB; ++mb) {                // block by block: the drain of block mb overlaps the MMAs of mb+1..
-#pragma unroll
-          for (int ks = 0; ks < 6; ++ks) {               // K = 96 = 6 x 16
-            const uint64_t adesc = umma_smem_desc(sa + (ks >> 2) * A_CHUNK + mb * (128 * 128) + (ks & 3) * 32, 16, 1024);
-            const uint64_t bdesc = umma_smem_desc(sb + (ks >> 2) * CHUNK_BYTES + (ks & 3) * 32, 16, 1024);
-            umma_bf16(tmem_d + mb * BG, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
-          }
-          umma_commit(&bar_d[mb]);
-        }
-        REC_TRACE(s, 3);
-      }
-      // off the critical path: gate gradients for the weight-gradient GEMMs
-      const size_t goff = row * 3 * p.H + j;
-      st_bf16x4(p.dGh + goff, gr[0], gr[1], gr[2], gr[3]);
-      st_bf16x4(p.dGh + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
-      st_bf16x4(p.dGh + goff + 2 * p.H, gnh[0], gnh[1], gnh[2], gnh[3]);
-      st_bf16x4(p.dGx + goff, gr[0], gr[1], gr[2], gr[3]);
-      st_bf16x4(p.dGx + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
-      st_bf16x4(p.dGx + goff + 2 * p.H, gn[0], gn[1], gn[2], gn[3]);
-
+      asm volatile("bar.arrive %0, %1;" ::"r"(1 + sub), "n"(Cfg::kEpiThreads + 32) : "memory");   // hand dG_t to the issuer warp
+      if (s + 1 < nsteps) cur = load_stash(t - 1);       // in flight during the drain below
       // partial sums -> L2 (granule layout above): lane = output unit within its 32-unit destination slice
       const int gen = p.gen_base + s;
       const uint32_t tag = (uint32_t)(gen >> 1) & 3u;
       for (int mb = 0; mb < MB; ++mb) {
         mbar_wait(&bar_d[mb], s & 1);
-        if (e == 0 && mb == 0) REC_TRACE(s, 4);
+        if (e == 0 && mb == 0) REC_TRACE_G0(s, 4);
         tc_fence_after();
         uint32_t v[16];
         tmem_ld16(tmem_d + (static_cast<uint32_t>(q * 32) << 16) + mb * BG + chalf * 16, v);
@@ -624,10 +678,19 @@ gru_rec_bwd_kernel(const RecBwdParams p) {
             st_relaxed_v4(dst + g4 * 128, (v[4 * g4] & ~3u) | tag, (v[4 * g4 + 1] & ~3u) | tag, (v[4 * g4 + 2] & ~3u) | tag, (v[4 * g4 + 3] & ~3u) | tag);
         }
       }
-      if (e == 0) REC_TRACE(s, 5);
+      // off the critical path: gate gradients for the weight-gradient GEMMs
+      const size_t goff = row * 3 * p.H + j;
+      st_bf16x4(p.dGh + goff, gr[0], gr[1], gr[2], gr[3]);
+      st_bf16x4(p.dGh + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
+      st_bf16x4(p.dGh + goff + 2 * p.H, gnh[0], gnh[1], gnh[2], gnh[3]);
+      st_bf16x4(p.dGx + goff, gr[0], gr[1], gr[2], gr[3]);
+      st_bf16x4(p.dGx + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
+      st_bf16x4(p.dGx + goff + 2 * p.H, gn[0], gn[1], gn[2], gn[3]);
+
+      if (e == 0) REC_TRACE_G0(s, 5);
       // No barrier here: sB is rewritten only after this thread has gathered the partials of step s from every CTA
-      // (so MMA(s) is long complete), and MMA(s+1) is issued behind the CTA barrier above, after every warp has
-      // drained the accumulators of step s.
+      // (so MMA(s) is long complete), and MMA(s+1) is issued behind the named barrier above, at which every epilogue
+      // warp arrives only after it has drained the accumulators of step s.
       tc_fence_before();
     }
     // recurrent gradient for the step before this chunk: dh_{t_begin-1} (rec) = dh_{t_begin} * z + dGh_{t_begin} W_hh

@@ -101,7 +101,7 @@ class Engine:
 
     def __del__(self):
         h = getattr(self, "handle", None)
-        if h:
+        if h and N is not None and getattr(N, "lib", None) is not None:     # module globals may already be gone at interpreter exit
             N.lib.b2t_engine_destroy(h)
             self.handle = None
 
