@@ -169,8 +169,8 @@ struct b2t_engine {
   std::vector<GemmPlan> p_dwih, p_dwhh, p_dwih0;   // p_dwih0: layer-0 dW_ih per time chunk (accumulating)
   std::vector<std::vector<GemmPlan>> p_in, p_dx;     // [layer >= 1][chunk]
   // side streams / events of the wave-front
-  cudaStream_t lane[MAX_LANES + 1] = {};   // [MAX_LANES] = bulk stream (weight-gradient GEMMs)
-  cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 1] = {}, ev_top = nullptr;
+  cudaStream_t lane[MAX_LANES + 2] = {};   // [MAX_LANES] = bulk stream (layer-0 projections / data gradients), [MAX_LANES + 1] = second bulk stream (weight gradients)
+  cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 2] = {}, ev_top = nullptr, ev_init = nullptr;
   std::vector<cudaEvent_t> ev_r, ev_dx;              // [layer * MAX_CHUNKS + chunk]
   cudaEvent_t ev_g0[MAX_CHUNKS] = {};                // layer-0 input projection chunks (issued ahead on the bulk stream)
   // state of the last forward
@@ -281,12 +281,13 @@ extern "C" long long b2t_workspace_bytes(const b2t_config* cfg, int max_batch, i
 
 extern "C" void b2t_engine_destroy(b2t_engine* e) {
   if (!e) return;
-  for (int i = 0; i <= MAX_LANES; ++i) {
+  for (int i = 0; i <= MAX_LANES + 1; ++i) {
     if (e->lane[i]) cudaStreamDestroy(e->lane[i]);
     if (e->ev_lane_end[i]) cudaEventDestroy(e->ev_lane_end[i]);
   }
   if (e->ev_start) cudaEventDestroy(e->ev_start);
   if (e->ev_top) cudaEventDestroy(e->ev_top);
+  if (e->ev_init) cudaEventDestroy(e->ev_init);
   for (cudaEvent_t ev : e->ev_r) if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->ev_dx) if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->ev_g0) if (ev) cudaEventDestroy(ev);
@@ -315,11 +316,12 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
   carve(e, workspace, (size_t)workspace_bytes, false);
   e->touched = grads ? grads + e->n_params : nullptr;
   bool ok = cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&e->ev_top, cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&e->ev_top, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_init, cudaEventDisableTiming) == cudaSuccess;
   // recurrence lanes outrank the bulk stream: when SMs free up, the latency-critical cooperative launches are placed first
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  for (int i = 0; i <= MAX_LANES && ok; ++i)
+  for (int i = 0; i <= MAX_LANES + 1 && ok; ++i)
     ok = cudaStreamCreateWithPriority(&e->lane[i], cudaStreamNonBlocking, (i < MAX_LANES) != (env_int("B2T_BULK_PRIO", 0) != 0) ? prio_hi : prio_lo) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_lane_end[i], cudaEventDisableTiming) == cudaSuccess;
   e->ev_r.assign((size_t)e->L * MAX_CHUNKS, nullptr);
@@ -635,6 +637,18 @@ static cudaError_t launch_rec_bwd(int BG, int nsub, const RecBwdParams& p, int g
   return BG == 64 ? launch_rec_bwd_t<64, 1>(p, grid, st) : BG == 32 ? launch_rec_bwd_t<32, 1>(p, grid, st) : launch_rec_bwd_t<16, 1>(p, grid, st);
 }
 
+// Gradient regions that backward accumulates into with atomics (biases, h0, day layers): cleared ahead of time.  GEMM-stored
+// gradients are fully overwritten.  Untouched day segments are cleared too -- cheap, and keeps the gradient-norm reduction free
+// of stale values.
+static int zero_accumulated_grads(b2t_engine* e, cudaStream_t st) {
+  const int H = e->H, L = e->L;
+  CK(cudaMemsetAsync(e->grads + seg_off(e, "day_weights.0"), 0, (size_t)(seg_off(e, "gru.weight_ih_l0") - seg_off(e, "day_weights.0")) * sizeof(float), st));
+  for (int l = 0; l < L; ++l)
+    CK(cudaMemsetAsync(e->grads + seg_off(e, "gru.bias_ih_l" + std::to_string(l)), 0, (size_t)2 * r64(3 * H) * sizeof(float), st));
+  CK(cudaMemsetAsync(e->grads + seg_off(e, "out.bias"), 0, (size_t)(r64(e->C) + r64(H)) * sizeof(float), st));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ forward
 // Wave-front schedule.  Layer l runs on side stream ("lane") l % n_lanes; its time chunk c needs chunk c of the layer
 // below (event) and its own chunk c-1 (stream order).  Tasks are issued diagonal by diagonal so that every lane's FIFO
@@ -677,6 +691,22 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
   const int n_groups = Bp / BG, grid = (H / 32) * n_groups;
 
   // 1. augmentation + smoothing -> xs (bf16); 2. day layer; 3. layer-0 input projection (whole sequence)
+  // Side work that does not depend on this step's input runs on the second bulk stream while augmentation and day layer run:
+  // sentinels + initial states of the recurrence and (training) the gradient regions that backward accumulates into.
+  {
+    cudaStream_t ss = e->lane[MAX_LANES + 1];
+    CK(cudaEventRecord(e->ev_top, st));
+    CK(cudaStreamWaitEvent(ss, e->ev_top, 0));
+    for (int l = 0; l < L; ++l) {
+      // "not written yet" sentinel for the recurrence's data-as-signal exchange (gru_rec.cuh); slot 0 is the initial state
+      CK(cudaMemsetAsync(e->lay[l].hseq + (size_t)Bp * H, 0xFF, (size_t)Tp * Bp * H * sizeof(__nv_bfloat16), ss));
+      init_state_kernel<<<(Bp * H + 255) / 256, 256, 0, ss>>>(e->params + seg_off(e, "h0"), a->states ? a->states + (size_t)l * a->B * H : nullptr,
+                                                               a->B, Bp, H, e->lay[l].hseq, e->lay[l].h_state);
+      CK(LAUNCHED());
+    }
+    if (a->training) { const int rc = zero_accumulated_grads(e, ss); if (rc) return rc; }
+    CK(cudaEventRecord(e->ev_init, ss));
+  }
   pp.x = a->x; pp.out = e->xs; pp.out_f32 = nullptr; pp.B = a->B; pp.Bpad = Bp; pp.T_in = a->T; pp.T_alloc = a->T; pp.D = D;
   pp.cut = cut; pp.ntaps = ntaps; pp.valid = a->smooth_mode == 2;
   pp.white_std = a->training ? a->white_noise_std : 0.f;
@@ -695,15 +725,12 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
     unfold_kernel<<<num_sms() * 4, 256, 0, st>>>(e->xd, e->xu, Bp, a->T, D, Tp, e->patch, e->stride);
     CK(LAUNCHED());
   }
-  for (int l = 0; l < L; ++l) {
-    // "not written yet" sentinel for the recurrence's data-as-signal exchange (gru_rec.cuh); slot 0 is the initial state
-    CK(cudaMemsetAsync(e->lay[l].hseq + (size_t)Bp * H, 0xFF, (size_t)Tp * Bp * H * sizeof(__nv_bfloat16), st));
-    init_state_kernel<<<(Bp * H + 255) / 256, 256, 0, st>>>(e->params + seg_off(e, "h0"), a->states ? a->states + (size_t)l * a->B * H : nullptr,
-                                                             a->B, Bp, H, e->lay[l].hseq, e->lay[l].h_state);
-    CK(LAUNCHED());
-  }
   CK(cudaEventRecord(e->ev_start, st));
-  for (int i = 0; i <= MAX_LANES; ++i) CK(cudaStreamWaitEvent(e->lane[i], e->ev_start, 0));
+  for (int i = 0; i <= MAX_LANES; ++i) {
+    CK(cudaStreamWaitEvent(e->lane[i], e->ev_start, 0));
+    CK(cudaStreamWaitEvent(e->lane[i], e->ev_init, 0));
+  }
+  CK(cudaStreamWaitEvent(st, e->ev_init, 0));
   // layer-0 input projection: all chunks up front on the bulk stream (they depend on no recurrence)
   for (int c = 0; c < nch; ++c) {
     TlScope tl(("G0." + std::to_string(c)).c_str(), 8, e->lane[MAX_LANES]);
@@ -883,16 +910,10 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   const float keep_rnn = e->cfg.rnn_dropout > 0.f ? 1.0f - e->cfg.rnn_dropout : 1.0f;
   const int BG = e->BGb, nch = e->n_tchunks, NL = e->n_lanes_b;
   const int n_groups = Bp / BG, grid = (H / 32) * n_groups / e->NSUBb;
-  // zero what is accumulated with atomics: biases, h0, day params, touched flags
+  // (the regions that are accumulated with atomics were cleared on a side stream during forward: zero_accumulated_grads)
   CK(cudaMemsetAsync(e->touched, 0, r64(e->cfg.n_days) * sizeof(float), st));
   mark_days_kernel<<<(e->B + 127) / 128, 128, 0, st>>>(e->day_idx, e->B, e->touched);
   CK(LAUNCHED());
-  // (GEMM-stored gradients are fully overwritten; day-weight / bias / h0 regions are cleared here.  Untouched
-  //  day segments are cleared too -- cheap, and keeps the gradient-norm reduction free of stale values.)
-  CK(cudaMemsetAsync(e->grads + seg_off(e, "day_weights.0"), 0, (size_t)(seg_off(e, "gru.weight_ih_l0") - seg_off(e, "day_weights.0")) * sizeof(float), st));
-  for (int l = 0; l < L; ++l)
-    CK(cudaMemsetAsync(e->grads + seg_off(e, "gru.bias_ih_l" + std::to_string(l)), 0, (size_t)2 * r64(3 * H) * sizeof(float), st));
-  CK(cudaMemsetAsync(e->grads + seg_off(e, "out.bias"), 0, (size_t)(r64(e->C) + r64(H)) * sizeof(float), st));
   if (e->bwd2) {   // the dGh arrays double as the exchange medium of gru_rec_bwd2_kernel: "not written yet" sentinel
     for (int l = 0; l < L; ++l) CK(cudaMemsetAsync(e->lay[l].dGh, 0xFF, (size_t)e->M * 3 * H * sizeof(__nv_bfloat16), st));
   }
@@ -912,6 +933,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   CK(cudaEventRecord(e->ev_top, st));
   for (int i = 0; i < NL; ++i) CK(cudaStreamWaitEvent(e->lane[i], e->ev_top, 0));
   CK(cudaStreamWaitEvent(e->lane[MAX_LANES], e->ev_top, 0));
+  CK(cudaStreamWaitEvent(e->lane[MAX_LANES + 1], e->ev_top, 0));
 
   // wave-front over (layer descending, time chunk descending); k counts chunks from the end of the sequence.
   // Task (l, c) = recurrence over chunk c (needs chunk c+1 of the same layer and dY_l[chunk c] from the layer above)
@@ -954,19 +976,23 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       if (l > 0) { TlScope tl(("DX" + sl + "." + std::to_string(c)).c_str(), li, ls); CK(gemm_run(e->p_dx[l][c], ls)); ++g_launches; }
       CK(cudaEventRecord(e->ev_dx[(size_t)l * MAX_CHUNKS + c], ls));
       if (l == 0) {   // layer 0: data gradient (to be folded) and weight gradient of this chunk fill idle SMs on the bulk stream
-        cudaStream_t bs = e->lane[MAX_LANES];
+        // the data gradient heads the chain dX -> fold -> day layer (first bulk stream); the weight gradient is off that chain
+        cudaStream_t bs = e->lane[MAX_LANES], bw = e->lane[MAX_LANES + 1];
         CK(cudaStreamWaitEvent(bs, e->ev_dx[(size_t)c], 0));
+        CK(cudaStreamWaitEvent(bw, e->ev_dx[(size_t)c], 0));
         { TlScope tl(("DX0." + std::to_string(c)).c_str(), 8, bs); CK(gemm_run(e->p_dx[0][c], bs)); ++g_launches; }
-        { TlScope tl(("dWih0." + std::to_string(c)).c_str(), 8, bs); CK(gemm_run(e->p_dwih0[c], bs)); ++g_launches; }
+        { TlScope tl(("dWih0." + std::to_string(c)).c_str(), 7, bw); CK(gemm_run(e->p_dwih0[c], bw)); ++g_launches; }
       }
       if (c == 0) {   // the layer's recurrence is complete: weight gradients over the whole sequence, on the bulk stream
-        cudaStream_t bs = e->lane[MAX_LANES];
+        cudaStream_t bs = e->lane[MAX_LANES + (l > 0 ? 1 : 0)];   // layer 0 ends the chain dX -> fold -> day layer: keep it in order on the first bulk stream
+        cudaStream_t bw = e->lane[MAX_LANES + 1];                // weight gradients of the hidden-to-hidden matrices and h0
         CK(cudaEventRecord(e->ev_r[(size_t)l * MAX_CHUNKS], ls));
+        if (l == 0) CK(cudaStreamWaitEvent(bw, e->ev_r[(size_t)l * MAX_CHUNKS], 0));
         CK(cudaStreamWaitEvent(bs, e->ev_r[(size_t)l * MAX_CHUNKS], 0));
-        if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 8, bs); CK(gemm_run(e->p_dwih[l], bs)); ++g_launches; }
-        { TlScope tl(("dWhh" + sl).c_str(), 8, bs); CK(gemm_run(e->p_dwhh[l], bs)); ++g_launches; }
+        if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 7, bs); CK(gemm_run(e->p_dwih[l], bs)); ++g_launches; }
+        { TlScope tl(("dWhh" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwhh[l], bw)); ++g_launches; }
         if (!e->states_given) {
-          reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bs>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
+          reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bw>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
           CK(LAUNCHED());
         }
         if (l == 0) {   // patch fold + day layer
@@ -981,7 +1007,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       }
     }
   }
-  for (int i = 0; i <= MAX_LANES; ++i) {
+  for (int i = 0; i <= MAX_LANES + 1; ++i) {
     if (i < MAX_LANES && i >= NL) continue;
     CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
     CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));
