@@ -23,6 +23,10 @@
 // The irregular once-per-sentence work (final-cost pruning, best path, n-best) runs on the host from the
 // token/link pools.
 #include <math.h>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -395,6 +399,168 @@ wfst_decode_kernel(const DecParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ lattice pruning on the GPU
+// FinalizeDecoding / PruneForwardLinksFinal / PruneForwardLinks / PruneTokensForFrame (lattice-faster-decoder.cc:632-647,
+// 379-465, 298-373, 485-506) for a finished utterance: per-token extra cost (cost of the best complete path through the token
+// minus the best path overall) by a backward sweep over the frame levels, links and tokens beyond lattice_beam dropped, the
+// survivors compacted in place (stable, so creation order -- which the host n-best uses for ties -- is preserved).
+// Only the survivors (a few per cent of the lattice at max_active = 7000) cross PCIe afterwards.
+//
+// Level f holds the tokens [ftok[f], ftok[f+1]).  Links are stored in creation order: range [flink[f], flink[f+1]) holds
+// the epsilon links inside level f preceded by the emitting links from level f-1 into level f.
+// The reference iterates extra costs from 0 upwards until nothing changes; the token lattice is acyclic, so the fixpoint is
+// unique and is reached here from above (atomicMin on the bit pattern of non-negative floats).
+struct PruneParams {
+  const float* fin;              // [nstates] final costs (inf = not final)
+  float lattice_beam;
+  int* tok_state; float* tok_cost; DLink* links;      // per-slot pools (compacted in place)
+  unsigned int* extra;           // [slots][tok_cap] scratch: extra cost bits
+  int* newidx;                   // [slots][tok_cap] scratch
+  const int* frame_tok_off; const int* frame_link_off; const int* counters;
+  int* c_ftok;                   // [slots][max_frames + 3] compacted level offsets
+  int* c_counts;                 // [slots][2] survivors: tokens, links
+  const int* slot_ids;
+  int tok_cap, link_cap, max_frames;
+};
+
+__device__ inline float link_extra(const float* cost, const unsigned int* extra, const DLink& k) {
+  // extra[dst] + ((cost[src] + ac + graph) - cost[dst]), same association as the reference
+  return __fadd_rn(__uint_as_float(extra[k.dst]), __fsub_rn(__fadd_rn(__fadd_rn(cost[k.src], k.ac), k.graph), cost[k.dst]));
+}
+
+// exclusive offsets of the set flags inside the block, in thread order; returns the block total
+__device__ int block_rank(bool flag, int* rank, int* s_warp) {
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = __popc(m & ((1u << lane) - 1u));
+  __syncthreads();
+  if (lane == 0) s_warp[w] = __popc(m);
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int i = 0; i < DEC_THREADS / 32; ++i) { if (i < w) base += s_warp[i]; total += s_warp[i]; }
+  *rank = base + r;
+  return total;
+}
+
+__global__ void __launch_bounds__(DEC_THREADS, 1)
+lattice_prune_kernel(const PruneParams p) {
+  __shared__ float sred[DEC_THREADS / 32];
+  __shared__ int s_warp[DEC_THREADS / 32];
+  __shared__ int s_flag;
+  const int slot = p.slot_ids[blockIdx.x];
+  int* tok_state = p.tok_state + (size_t)slot * p.tok_cap;
+  float* cost = p.tok_cost + (size_t)slot * p.tok_cap;
+  DLink* links = p.links + (size_t)slot * p.link_cap;
+  unsigned int* extra = p.extra + (size_t)slot * p.tok_cap;
+  int* newidx = p.newidx + (size_t)slot * p.tok_cap;
+  const int* ftok = p.frame_tok_off + (size_t)slot * (p.max_frames + 3);
+  const int* flink = p.frame_link_off + (size_t)slot * (p.max_frames + 3);
+  int* c_ftok = p.c_ftok + (size_t)slot * (p.max_frames + 3);
+  const int F = p.counters[slot * 4 + 2] + 1;             // levels
+  const float lb = p.lattice_beam;
+  const unsigned int INF_BITS = 0x7f800000u;
+
+  // ---- last level: final costs
+  const int fb = ftok[F - 1], fe = ftok[F];
+  float bf = INFINITY, bp = INFINITY;
+  for (int i = fb + threadIdx.x; i < fe; i += DEC_THREADS) {
+    const float fc = p.fin[tok_state[i]];
+    bp = fminf(bp, cost[i]);
+    bf = fminf(bf, __fadd_rn(cost[i], fc));
+  }
+  const float best_final = block_min(bf, sred), best_plain = block_min(bp, sred);
+  const bool any_final = best_final != INFINITY;
+  const float final_best = any_final ? best_final : best_plain;
+
+  for (int f = F - 1; f >= 0; --f) {
+    const int tb = ftok[f], te = ftok[f + 1];
+    for (int i = tb + threadIdx.x; i < te; i += DEC_THREADS) {
+      float e0 = INFINITY;
+      if (f == F - 1) {
+        const float fc = any_final ? p.fin[tok_state[i]] : 0.0f;
+        e0 = __fsub_rn(__fadd_rn(cost[i], fc), final_best);
+        if (!(e0 <= lb)) e0 = INFINITY;                    // te > lattice_beam -> inf (also catches NaN from inf - inf)
+      }
+      extra[i] = __float_as_uint(e0);
+    }
+    __syncthreads();
+    // emitting links out of level f (their destinations, level f + 1, are final already): one pass
+    if (f < F - 1) {
+      for (int l = flink[f + 1] + threadIdx.x; l < flink[f + 2]; l += DEC_THREADS) {
+        const DLink k = links[l];
+        if (k.il == 0) continue;
+        float lec = link_extra(cost, extra, k);
+        if (!(lec <= lb)) continue;
+        if (lec < 0.0f) lec = 0.0f;
+        atomicMin(&extra[k.src], __float_as_uint(lec));
+      }
+    }
+    // epsilon links inside level f: relax until nothing changes
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_flag = 0;
+      __syncthreads();
+      for (int l = flink[f] + threadIdx.x; l < flink[f + 1]; l += DEC_THREADS) {
+        const DLink k = links[l];
+        if (k.il != 0) continue;
+        float lec = link_extra(cost, extra, k);
+        if (!(lec <= lb)) continue;
+        if (lec < 0.0f) lec = 0.0f;
+        const unsigned int nb = __float_as_uint(lec);
+        if (atomicMin(&extra[k.src], nb) > nb) s_flag = 1;
+      }
+      __syncthreads();
+      if (!s_flag) break;
+    }
+  }
+  __syncthreads();
+
+  // ---- stable compaction of the surviving tokens, level by level
+  int run = 0;
+  for (int f = 0; f < F; ++f) {
+    if (threadIdx.x == 0) c_ftok[f] = run;
+    for (int base = ftok[f]; base < ftok[f + 1]; base += DEC_THREADS) {
+      const int i = base + threadIdx.x;
+      const bool in = i < ftok[f + 1];
+      const bool alive = in && extra[i] != INF_BITS;
+      int st = 0; float c = 0.f;
+      if (alive) { st = tok_state[i]; c = cost[i]; }
+      int rank;
+      const int total = block_rank(alive, &rank, s_warp);
+      if (in) newidx[i] = alive ? run + rank : -1;
+      if (alive) { tok_state[run + rank] = st; cost[run + rank] = c; }       // run + rank <= i: in place is safe (reads of the chunk are done)
+      run += total;
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) { c_ftok[F] = run; p.c_counts[slot * 2] = run; }
+  __syncthreads();
+  // ---- links: alive iff both ends survive and the link itself stays inside the beam.  The costs were compacted above, so the
+  //      link test uses the new indices; extra is still indexed by the old ones.
+  int lrun = 0;
+  const int nl = flink[F];
+  for (int base = 0; base < nl; base += DEC_THREADS) {
+    const int l = base + threadIdx.x;
+    bool alive = false;
+    DLink k;
+    if (l < nl) {
+      k = links[l];
+      const int ns = newidx[k.src], nd = newidx[k.dst];
+      if (ns >= 0 && nd >= 0) {
+        const float lec = __fadd_rn(__uint_as_float(extra[k.dst]), __fsub_rn(__fadd_rn(__fadd_rn(cost[ns], k.ac), k.graph), cost[nd]));
+        alive = lec <= lb;
+        k.src = ns; k.dst = nd;
+      }
+    }
+    int rank;
+    const int total = block_rank(alive, &rank, s_warp);
+    if (alive) links[lrun + rank] = k;
+    lrun += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p.c_counts[slot * 2 + 1] = lrun;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct HostGraph {
   int start = -1;
@@ -471,6 +637,7 @@ struct b2t_decoder {
   DLink* d_links = nullptr;
   int *d_ftok = nullptr, *d_flink = nullptr, *d_counters = nullptr, *d_nfed = nullptr, *d_slot_ids = nullptr;
   float *d_coff = nullptr, *d_logp = nullptr;
+  float* d_fin = nullptr; unsigned int* d_extra = nullptr; int *d_newidx = nullptr, *d_cftok = nullptr, *d_ccounts = nullptr;   // GPU lattice pruning
   std::vector<Slot> slots;
   cudaStream_t stream = nullptr;
   double last_kernel_ms = 0.0;
@@ -540,11 +707,16 @@ int fetch_lattice(b2t_decoder* d, int slot, Lattice* L) {
   if (nl) DCK(cudaMemcpyAsync(L->links.data(), d->d_links + (size_t)slot * d->link_cap, nl * sizeof(DLink), cudaMemcpyDeviceToHost, d->stream));
   if (nf) DCK(cudaMemcpyAsync(L->coff.data(), d->d_coff + (size_t)slot * d->max_frames, nf * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
   DCK(cudaStreamSynchronize(d->stream));
-  // order links by source token (stable) and index them
-  std::stable_sort(L->links.begin(), L->links.end(), [](const DLink& a, const DLink& b) { return a.src < b.src; });
+  // order links by source token (stable counting sort) and index them
   L->lbeg.assign(nt + 1, 0);
   for (const DLink& k : L->links) L->lbeg[k.src + 1]++;
   for (int i = 0; i < nt; ++i) L->lbeg[i + 1] += L->lbeg[i];
+  {
+    std::vector<int> pos(L->lbeg.begin(), L->lbeg.end() - 1);
+    std::vector<DLink> sorted(L->links.size());
+    for (const DLink& k : L->links) sorted[pos[k.src]++] = k;
+    L->links.swap(sorted);
+  }
   L->frame_of.resize(nt);
   for (int f = 0; f < L->F; ++f)
     for (int i = L->ftok[f]; i < L->ftok[f + 1]; ++i) L->frame_of[i] = f;
@@ -707,46 +879,80 @@ void nbest_from_lattice(b2t_decoder* d, Slot& s, const Lattice& L, const std::ve
   bool any_final = false;
   for (int i = L.ftok[L.F - 1]; i < L.ftok[L.F]; ++i)
     if (d->g.fin[L.state[i]] != INFINITY) any_final = true;
-  WordTrie trie;
-  std::vector<std::vector<Hyp>> hyps(nt);
-  hyps[0].push_back({0, 0.0f, 0.0f});
-  std::vector<Hyp> finals;
-  auto merge = [&](std::vector<Hyp>& v, const Hyp& h) {
-    for (Hyp& e : v)
-      if (e.seq == h.seq) { if (hyp_better(h, e)) e = h; return; }
-    v.push_back(h);
-  };
-  auto trim = [&](std::vector<Hyp>& v) {
-    if ((int)v.size() > K) {
-      std::partial_sort(v.begin(), v.begin() + K, v.end(), hyp_better);
-      v.resize(K);
-    }
-  };
-  for (int i : order) {
-    std::vector<Hyp>& hv = hyps[i];
-    if (hv.empty()) continue;
-    trim(hv);
-    if (L.frame_of[i] == L.F - 1) {
-      const float fc = any_final ? d->g.fin[L.state[i]] : 0.0f;
-      if (fc != INFINITY)
-        for (const Hyp& h : hv) merge(finals, Hyp{h.seq, h.g + fc, h.a});
-    }
+  auto alive = [&](int l) { return keep[l] && extra[L.links[l].dst] != INFINITY; };
+  // exact cost-to-final of every surviving token (un-offset costs), reverse topological order
+  std::vector<float> beta(nt, INFINITY);
+  for (int i = L.ftok[L.F - 1]; i < L.ftok[L.F]; ++i)
+    if (extra[i] != INFINITY) beta[i] = any_final ? d->g.fin[L.state[i]] : 0.0f;
+  for (int q = (int)order.size() - 1; q >= 0; --q) {
+    const int i = order[q];
+    float bi = beta[i];
     for (int l = L.lbeg[i]; l < L.lbeg[i + 1]; ++l) {
-      if (!keep[l]) continue;
+      if (!alive(l)) continue;
       const DLink& k = L.links[l];
-      if (extra[k.dst] == INFINITY) continue;
-      const float ac = link_ac(L, k);
-      for (const Hyp& h : hv) merge(hyps[k.dst], Hyp{k.ol != 0 ? trie.extend(h.seq, k.ol) : h.seq, h.g + k.graph, h.a + ac});
+      const float c = k.graph + link_ac(L, k) + beta[k.dst];
+      if (c < bi) bi = c;
     }
-    std::vector<Hyp>().swap(hv);
+    beta[i] = bi;
   }
-  std::stable_sort(finals.begin(), finals.end(), hyp_better);
-  if (!finals.empty()) {
-    const float limit = finals[0].g + finals[0].a + d->opt.lattice_beam + 1e-4f;
-    for (size_t i = 0; i < finals.size() && (int)i < K; ++i) {
-      if (finals[i].g + finals[i].a > limit) break;
-      push_result(d, s, trie.words(finals[i].seq), finals[i].g, finals[i].a);
+  if (order.empty() || beta[0] == INFINITY) return;
+  // A hypothesis is dropped as soon as even its best completion exceeds `limit` (admissible: beta is exact).  The n best
+  // sequences usually lie within a fraction of the lattice beam, so the search runs with a small margin first and widens it
+  // until the K-th result is inside the margin (then nothing that was dropped could have ranked among the first K) or the
+  // margin is the whole lattice beam.
+  const float full = d->opt.lattice_beam;
+  auto dedupe_trim = [&](std::vector<Hyp>& v, int cap) {
+    // candidates are appended unmerged; one sort keeps the best hypothesis of every word sequence (the earliest inserted
+    // among equals) and then the `cap` cheapest
+    if (v.size() > 1) {
+      std::stable_sort(v.begin(), v.end(), [](const Hyp& x, const Hyp& y) { return x.seq != y.seq ? x.seq < y.seq : hyp_better(x, y); });
+      size_t w = 0;
+      for (size_t r = 0; r < v.size(); ++r)
+        if (r == 0 || v[r].seq != v[r - 1].seq) v[w++] = v[r];
+      v.resize(w);
     }
+    if (cap > 0 && (int)v.size() > cap) {
+      std::partial_sort(v.begin(), v.begin() + cap, v.end(), hyp_better);
+      v.resize(cap);
+    }
+  };
+  for (float margin = std::min(1.0f, full);; margin = std::min(margin * 2.0f, full)) {
+    const float limit = beta[0] + margin + 1e-4f;
+    WordTrie trie;
+    std::vector<std::vector<Hyp>> hyps(nt);
+    hyps[0].push_back({0, 0.0f, 0.0f});
+    std::vector<Hyp> finals;
+    for (int i : order) {
+      std::vector<Hyp>& hv = hyps[i];
+      if (hv.empty()) continue;
+      dedupe_trim(hv, K);
+      if (L.frame_of[i] == L.F - 1) {
+        const float fc = any_final ? d->g.fin[L.state[i]] : 0.0f;
+        if (fc != INFINITY)
+          for (const Hyp& h : hv)
+            if (h.g + fc + h.a <= limit) finals.push_back(Hyp{h.seq, h.g + fc, h.a});
+      }
+      for (int l = L.lbeg[i]; l < L.lbeg[i + 1]; ++l) {
+        if (!alive(l)) continue;
+        const DLink& k = L.links[l];
+        const float ac = link_ac(L, k), bn = beta[k.dst];
+        if (bn == INFINITY) continue;
+        std::vector<Hyp>& dv = hyps[k.dst];
+        for (const Hyp& h : hv) {
+          const float g = h.g + k.graph, a = h.a + ac;
+          if (g + a + bn > limit) continue;
+          dv.push_back(Hyp{k.ol != 0 ? trie.extend(h.seq, k.ol) : h.seq, g, a});
+        }
+        if (dv.size() > (size_t)8 * K + 64) dedupe_trim(dv, 0);      // bound the memory of high in-degree tokens
+      }
+      std::vector<Hyp>().swap(hv);
+    }
+    dedupe_trim(finals, 0);
+    std::stable_sort(finals.begin(), finals.end(), hyp_better);
+    const bool complete = margin >= full || ((int)finals.size() >= K && finals[K - 1].g + finals[K - 1].a <= beta[0] + margin);
+    if (!complete) continue;
+    for (size_t i = 0; i < finals.size() && (int)i < K; ++i) push_result(d, s, trie.words(finals[i].seq), finals[i].g, finals[i].a);
+    break;
   }
 }
 
@@ -843,23 +1049,156 @@ int partial_result(b2t_decoder* d, int slot) {   // ctc_wfst_beam_search.cc:112-
   return 0;
 }
 
-int finish_slot(b2t_decoder* d, int slot) {      // ctc_wfst_beam_search.cc:123-160
+// Run lattice_prune_kernel for the given (finished) slots; afterwards the slots' token / link pools hold only the survivors.
+int prune_slots_on_gpu(b2t_decoder* d, const std::vector<int>& ids) {
+  if (ids.empty()) return 0;
+  DCK(cudaMemcpyAsync(d->d_slot_ids, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  PruneParams p;
+  p.fin = d->d_fin; p.lattice_beam = d->opt.lattice_beam;
+  p.tok_state = d->d_tok_state; p.tok_cost = d->d_tok_cost; p.links = d->d_links; p.extra = d->d_extra; p.newidx = d->d_newidx;
+  p.frame_tok_off = d->d_ftok; p.frame_link_off = d->d_flink; p.counters = d->d_counters; p.c_ftok = d->d_cftok; p.c_counts = d->d_ccounts;
+  p.slot_ids = d->d_slot_ids; p.tok_cap = d->tok_cap; p.link_cap = d->link_cap; p.max_frames = d->max_frames;
+  lattice_prune_kernel<<<(int)ids.size(), DEC_THREADS, 0, d->stream>>>(p);
+  DCK(cudaGetLastError());
+  return 0;
+}
+
+// Host view of a slot after prune_slots_on_gpu: every token and link is a survivor.
+int fetch_pruned_lattice(b2t_decoder* d, int slot, Lattice* L) {
+  int counters[4], cc[2];
+  DCK(cudaMemcpyAsync(counters, d->d_counters + slot * 4, sizeof(counters), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaMemcpyAsync(cc, d->d_ccounts + slot * 2, sizeof(cc), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaStreamSynchronize(d->stream));
+  if (counters[3] == 1) return dfail(B2T_ERR_WORKSPACE, "decoder token pool overflow (capacity %d): raise max_active-derived capacity or lower beam", d->tok_cap);
+  if (counters[3] == 2) return dfail(B2T_ERR_WORKSPACE, "decoder link pool overflow (capacity %d)", d->link_cap);
+  const int nf = counters[2], nt = cc[0], nl = cc[1];
+  L->F = nf + 1;
+  L->ftok.resize(L->F + 1); L->flink.assign(L->F + 1, 0);
+  L->state.resize(nt); L->bp.assign(nt, -1); L->cost.resize(nt); L->links.resize(nl); L->coff.resize(nf);
+  DCK(cudaMemcpyAsync(L->ftok.data(), d->d_cftok + (size_t)slot * (d->max_frames + 3), (L->F + 1) * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  if (nt) {
+    DCK(cudaMemcpyAsync(L->state.data(), d->d_tok_state + (size_t)slot * d->tok_cap, nt * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+    DCK(cudaMemcpyAsync(L->cost.data(), d->d_tok_cost + (size_t)slot * d->tok_cap, nt * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+  }
+  if (nl) DCK(cudaMemcpyAsync(L->links.data(), d->d_links + (size_t)slot * d->link_cap, nl * sizeof(DLink), cudaMemcpyDeviceToHost, d->stream));
+  if (nf) DCK(cudaMemcpyAsync(L->coff.data(), d->d_coff + (size_t)slot * d->max_frames, nf * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaStreamSynchronize(d->stream));
+  L->lbeg.assign(nt + 1, 0);
+  for (const DLink& k : L->links) L->lbeg[k.src + 1]++;
+  for (int i = 0; i < nt; ++i) L->lbeg[i + 1] += L->lbeg[i];
+  {
+    std::vector<int> pos(L->lbeg.begin(), L->lbeg.end() - 1);
+    std::vector<DLink> sorted(L->links.size());
+    for (const DLink& k : L->links) sorted[pos[k.src]++] = k;
+    L->links.swap(sorted);
+  }
+  L->frame_of.resize(nt);
+  for (int f = 0; f < L->F; ++f)
+    for (int i = L->ftok[f]; i < L->ftok[f + 1]; ++i) L->frame_of[i] = f;
+  return 0;
+}
+
+// FinalizeSearch (ctc_wfst_beam_search.cc:123-160), host part: n-best (or 1-best) of a fetched lattice.  Touches only the slot.
+void finish_from_lattice(b2t_decoder* d, int slot, const Lattice& L, double fetch_ms, bool pruned) {
+  static const bool timing = getenv("B2T_DECODER_TIMING") != nullptr;      // host-phase timing to stderr (profiling aid)
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   Slot& s = d->slots[slot];
-  s.results.clear();
-  s.finished = true;
-  if (s.n_fed == 0) return 0;
-  Lattice L;
-  int rc = fetch_lattice(d, slot, &L);
-  if (rc) return rc;
+  const double t1 = now();
+  double t2 = t1;
   if (d->opt.nbest == 1) {
     std::vector<int> w; float g, a;
     if (best_path(d, L, true, &w, &g, &a)) push_result(d, s, w, g, a);
   } else {
     std::vector<float> extra; std::vector<char> keep;
-    prune_final(d, L, &extra, &keep);
+    if (pruned) { extra.assign(L.state.size(), 0.0f); keep.assign(L.links.size(), 1); }   // lattice_prune_kernel left only survivors
+    else prune_final(d, L, &extra, &keep);
+    t2 = now();
     nbest_from_lattice(d, s, L, extra, keep);
   }
+  if (timing)
+    fprintf(stderr, "b2t decoder slot %d: %zu tokens, %zu links; fetch+sort %.2f ms, prune %.2f ms, n-best %.2f ms, %zu results\n", slot, L.state.size(),
+            L.links.size(), fetch_ms, t2 - t1, now() - t2, s.results.size());
+}
+
+bool use_gpu_prune() {
+  static const bool on = !(getenv("B2T_DECODER_HOST_PRUNE") && atoi(getenv("B2T_DECODER_HOST_PRUNE")) != 0);   // A/B switch: host restatement of the pruning
+  return on;
+}
+
+int finish_slot(b2t_decoder* d, int slot) {
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  Slot& s = d->slots[slot];
+  if (s.finished) return 0;                       // the lattice was compacted by the first call; its results stand
+  s.results.clear();
+  s.finished = true;
+  if (s.n_fed == 0) return 0;
+  const double t0 = now();
+  Lattice L;
+  const bool gpu_prune = d->opt.nbest != 1 && use_gpu_prune();
+  int rc = gpu_prune ? prune_slots_on_gpu(d, std::vector<int>{slot}) : 0;
+  if (rc) return rc;
+  rc = gpu_prune ? fetch_pruned_lattice(d, slot, &L) : fetch_lattice(d, slot, &L);
+  if (rc) return rc;
+  finish_from_lattice(d, slot, L, now() - t0, gpu_prune);
   return 0;
+}
+
+// Finish several slots: the lattices are fetched one after the other (one copy stream), the host-side pruning and n-best
+// extraction of different utterances run on worker threads.
+int finish_slots(b2t_decoder* d, int N) {
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int n_workers = (int)std::min<unsigned>(hw, 16u);
+  std::vector<std::thread> workers;
+  std::vector<Lattice> lats(N);
+  std::vector<double> fetch_ms(N, 0.0);
+  std::mutex mu;
+  std::condition_variable cv;
+  int fetched = 0, next = 0;
+  bool failed = false;
+  const bool gpu_prune = d->opt.nbest != 1 && use_gpu_prune();
+  auto work = [&] {
+    for (;;) {
+      int n;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return next < fetched || failed || (fetched == N && next >= N); });
+        if (next >= fetched) return;
+        n = next++;
+      }
+      if (d->slots[n].n_fed > 0) finish_from_lattice(d, n, lats[n], fetch_ms[n], gpu_prune);
+      Lattice().state.swap(lats[n].state);
+      std::vector<DLink>().swap(lats[n].links);
+    }
+  };
+  int rc = 0;
+  if (gpu_prune) {
+    std::vector<int> ids;
+    for (int n = 0; n < N; ++n)
+      if (d->slots[n].n_fed > 0) ids.push_back(n);
+    if ((rc = prune_slots_on_gpu(d, ids))) return rc;
+  }
+  for (int i = 0; i < std::min(n_workers, N); ++i) workers.emplace_back(work);
+  for (int n = 0; n < N && !rc; ++n) {
+    Slot& s = d->slots[n];
+    s.results.clear();
+    s.finished = true;
+    const double t0 = now();
+    if (s.n_fed > 0) rc = gpu_prune ? fetch_pruned_lattice(d, n, &lats[n]) : fetch_lattice(d, n, &lats[n]);
+    fetch_ms[n] = now() - t0;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (rc) failed = true; else fetched = n + 1;
+    }
+    cv.notify_all();
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (rc) failed = true;
+  }
+  cv.notify_all();
+  for (auto& w : workers) w.join();
+  return rc;
 }
 
 int ensure_C(b2t_decoder* d, int C) {
@@ -902,11 +1241,15 @@ b2t_decoder* b2t_decoder_create(const char* fst_path, const char* words_path, co
        cudaMalloc(&d->d_dirty, (size_t)max_slots * d->tok_cap) == cudaSuccess && cudaMalloc(&d->d_links, (size_t)max_slots * d->link_cap * sizeof(DLink)) == cudaSuccess &&
        cudaMalloc(&d->d_ftok, (size_t)max_slots * (max_frames + 3) * 4) == cudaSuccess && cudaMalloc(&d->d_flink, (size_t)max_slots * (max_frames + 3) * 4) == cudaSuccess &&
        cudaMalloc(&d->d_coff, (size_t)max_slots * max_frames * 4) == cudaSuccess && cudaMalloc(&d->d_counters, (size_t)max_slots * 16) == cudaSuccess &&
-       cudaMalloc(&d->d_nfed, (size_t)max_slots * 4) == cudaSuccess && cudaMalloc(&d->d_slot_ids, (size_t)max_slots * 4) == cudaSuccess;
+       cudaMalloc(&d->d_nfed, (size_t)max_slots * 4) == cudaSuccess && cudaMalloc(&d->d_slot_ids, (size_t)max_slots * 4) == cudaSuccess &&
+       cudaMalloc(&d->d_fin, std::max<size_t>(ns, 1) * 4) == cudaSuccess && cudaMalloc(&d->d_extra, (size_t)max_slots * d->tok_cap * 4) == cudaSuccess &&
+       cudaMalloc(&d->d_newidx, (size_t)max_slots * d->tok_cap * 4) == cudaSuccess && cudaMalloc(&d->d_cftok, (size_t)max_slots * (max_frames + 3) * 4) == cudaSuccess &&
+       cudaMalloc(&d->d_ccounts, (size_t)max_slots * 8) == cudaSuccess;
   if (!ok) { dfail(B2T_ERR_CUDA, "decoder allocation failed: %s (states %zu, slots %d, token pool %d)", cudaGetErrorString(cudaGetLastError()), ns, max_slots, d->tok_cap); b2t_decoder_destroy(d); return nullptr; }
   cudaMemcpy(d->d_arcs, d->g.arcs.data(), na * sizeof(DArc), cudaMemcpyHostToDevice);
   cudaMemcpy(d->d_off, d->g.off.data(), (ns + 1) * sizeof(long long), cudaMemcpyHostToDevice);
   cudaMemcpy(d->d_has_eps, d->g.has_eps.data(), ns, cudaMemcpyHostToDevice);
+  cudaMemcpy(d->d_fin, d->g.fin.data(), ns * sizeof(float), cudaMemcpyHostToDevice);
   cudaMemset(d->d_best, 0xff, (size_t)max_slots * ns * 8);
   cudaMemset(d->d_tokidx, 0xff, (size_t)max_slots * ns * 4);
   d->slots.resize(max_slots);
@@ -918,7 +1261,7 @@ b2t_decoder* b2t_decoder_create(const char* fst_path, const char* words_path, co
 void b2t_decoder_destroy(b2t_decoder* d) {
   if (!d) return;
   void* ptrs[] = {d->d_arcs, d->d_off, d->d_has_eps, d->d_best, d->d_tokidx, d->d_tok_state, d->d_tok_cost, d->d_tok_bp, d->d_dirty, d->d_links,
-                  d->d_ftok, d->d_flink, d->d_coff, d->d_counters, d->d_nfed, d->d_slot_ids, d->d_logp};
+                  d->d_ftok, d->d_flink, d->d_coff, d->d_counters, d->d_nfed, d->d_slot_ids, d->d_logp, d->d_fin, d->d_extra, d->d_newidx, d->d_cftok, d->d_ccounts};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
@@ -1010,9 +1353,7 @@ int b2t_decoder_decode_batch(b2t_decoder* d, const float* logits, const int* len
     ids.push_back(n);
   }
   if ((rc = launch_slots(d, ids))) return rc;
-  if (finish)
-    for (int n = 0; n < N; ++n)
-      if ((rc = finish_slot(d, n))) return rc;
+  if (finish && (rc = finish_slots(d, N))) return rc;
   return 0;
 }
 

@@ -3,12 +3,16 @@
 // Reference: language_model/runtime/core/decoder/ctc_prefix_beam_search.cc:44-136, PrefixScore .h:27-42,
 // LogAdd utils/utils.cc:24-30.  Golden vector: ctc_prefix_beam_search_test.cc:18-59.
 //
-// The per-frame update is a chain of order-dependent float LogAdd merges over at most
-// first_beam x second_beam (default 10 x 10) candidates, so there is no useful parallelism inside one utterance;
-// the kernel therefore runs one utterance per thread and gets its throughput from decoding many utterances
-// at once (the pipeline is embarrassingly parallel over trials).  Prefixes are interned as (parent, token) trie
-// nodes so that prefix identity is an integer comparison.
+// One WARP per utterance.  The per-frame update is a chain of order-dependent merges (which candidate is created first
+// decides ties in the second beam), so lane 0 walks the (token, hypothesis) pairs in the reference's order, but every step of
+// that walk is O(1): prefixes are interned as (parent, token) trie nodes found through a hash table, the candidates of the
+// frame are found through a second hash table keyed by trie node, and the per-hypothesis Viterbi time vectors are copied by
+// all 32 lanes.  The first beam (top-k classes) and the second beam (top-n candidates, earlier candidate first among equal
+// scores) are warp-wide arg-max selections.  Throughput comes from decoding many utterances at once.
 #include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <chrono>
 #include <stdio.h>
 
 #include <vector>
@@ -31,8 +35,8 @@ struct PbParams {
   int N, T, C, blank, first_beam, second_beam, max_len;
   // per-utterance scratch
   int* trie_parent; int* trie_token; int trie_cap;     // [N][trie_cap]
+  int* trie_hash; int trie_hash_cap;                   // [N][trie_hash_cap] (power of two) -> trie node or -1
   int* times;          // [N][2 buffers][PB_MAX_CAND][2 (s, ns)][max_len]
-  struct Hyp* hyps;    // [N][PB_MAX_BEAM + PB_MAX_CAND]
   // outputs
   int* out_ids; int* out_len; float* out_score; float* out_viterbi; int* out_times; int* out_n;
   int* status;
@@ -43,6 +47,9 @@ struct Hyp {
   float s, ns, v_s, v_ns, cur_token_prob;
 };
 
+constexpr int PB_HASH_CAND = 2048;  // >= 2 * PB_MAX_CAND, power of two
+constexpr unsigned FULL = 0xffffffffu;
+
 __device__ inline float log_add(float x, float y) {
   if (x <= PB_NEG) return y;
   if (y <= PB_NEG) return x;
@@ -51,137 +58,199 @@ __device__ inline float log_add(float x, float y) {
 }
 __device__ inline float hyp_score(const Hyp& h) { return log_add(h.s, h.ns); }
 __device__ inline float hyp_viterbi(const Hyp& h) { return h.v_s > h.v_ns ? h.v_s : h.v_ns; }
+__device__ inline unsigned mix(unsigned a, unsigned b) {
+  unsigned h = a * 0x9E3779B1u ^ (b + 0x85EBCA6Bu + (a << 6) + (a >> 2));
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+  return h;
+}
 
-__global__ void prefix_beam_kernel(const PbParams p) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+// warp-wide arg-max of (value, index): larger value first, smaller index among equal values; idx < 0 = no candidate
+__device__ inline void warp_argmax(float& v, int& idx) {
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(FULL, v, o);
+    const int oi = __shfl_xor_sync(FULL, idx, o);
+    if (oi >= 0 && (idx < 0 || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+  }
+}
+
+__global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
+  // the state lane 0 walks with dependent accesses lives in shared memory (33 KB); the trie, its hash and the time vectors stay
+  // in global memory (one or two accesses per pair / copied by all lanes)
+  __shared__ int s_top[PB_MAX_TOPK];
+  __shared__ int s_order[PB_MAX_BEAM];
+  __shared__ Hyp s_cur[PB_MAX_BEAM];
+  __shared__ Hyp s_nxt[PB_MAX_CAND];
+  __shared__ int s_chash[PB_HASH_CAND];
+  const int u = blockIdx.x, lane = threadIdx.x;
   if (u >= p.N) return;
   const float* logp = p.logp + (size_t)u * p.T * p.C;
   const int Tn = min(max(p.lens[u], 0), p.T);
   int* tpar = p.trie_parent + (size_t)u * p.trie_cap;
   int* ttok = p.trie_token + (size_t)u * p.trie_cap;
-  int ntrie = 1;                                        // node 0 = empty prefix
-  tpar[0] = -1; ttok[0] = -1;
+  int* thash = p.trie_hash + (size_t)u * p.trie_hash_cap;
+  int* chash = s_chash;
+  int ntrie = 1;                                        // node 0 = empty prefix (lane 0's copy is the authoritative one)
+  if (lane == 0) { tpar[0] = -1; ttok[0] = -1; }
+  for (int i = lane; i < p.trie_hash_cap; i += 32) thash[i] = -1;
+  for (int i = lane; i < PB_HASH_CAND; i += 32) chash[i] = -1;
   const size_t tstride = (size_t)2 * p.max_len;          // per hypothesis: times_s | times_ns
   int* tbuf[2] = {p.times + (size_t)u * 2 * PB_MAX_CAND * tstride, p.times + ((size_t)u * 2 + 1) * PB_MAX_CAND * tstride};
 
-  Hyp* cur = p.hyps + (size_t)u * (PB_MAX_BEAM + PB_MAX_CAND);
-  Hyp* nxt = cur + PB_MAX_BEAM;
-  int ncur = 1, cb = 0;
-  cur[0] = Hyp{0, 0, -1, 0.0f, PB_NEG, 0.0f, 0.0f, PB_NEG};
+  Hyp* cur = s_cur;
+  Hyp* nxt = s_nxt;
+  int ncur = 1;
+  if (lane == 0) cur[0] = Hyp{0, 0, -1, 0.0f, PB_NEG, 0.0f, 0.0f, PB_NEG};
   const int k = min(min(p.first_beam, p.C), PB_MAX_TOPK);
   bool overflow = false;
+  __syncwarp();
 
   for (int t = 0; t < Tn; ++t) {
     const float* row = logp + (size_t)t * p.C;
-    // 1. first beam: top-k classes, descending value, lower index first among ties
-    int top[PB_MAX_TOPK];
-    for (int i = 0; i < k; ++i) {
-      int best = -1;
-      for (int c = 0; c < p.C; ++c) {
-        bool used = false;
-        for (int j = 0; j < i; ++j) used |= (top[j] == c);
-        if (!used && (best < 0 || row[c] > row[best])) best = c;
+    // 1. first beam: top-k classes, descending value, lower index first among ties (lane l owns classes l and l + 32)
+    {
+      float v0 = lane < p.C ? row[lane] : 0.f, v1 = lane + 32 < p.C ? row[lane + 32] : 0.f;
+      bool u0 = lane < p.C, u1 = lane + 32 < p.C;       // still available
+      for (int i = 0; i < k; ++i) {
+        float v; int idx;
+        if (u0 && (!u1 || v0 >= v1)) { v = v0; idx = lane; } else if (u1) { v = v1; idx = lane + 32; } else { v = 0.f; idx = -1; }
+        warp_argmax(v, idx);
+        if (idx == lane) u0 = false;
+        if (idx == lane + 32) u1 = false;
+        if (lane == 0) s_top[i] = idx;
       }
-      top[i] = best;
     }
-    // 2. token passing into nxt[] (linear-probe on (node) identity)
+    __syncwarp();
+    // 2. token passing into nxt[]: lane 0 walks the pairs in the reference's order, all lanes copy the time vectors
     int nn = 0;
-    int* tc = tbuf[cb];
-    int* tn = tbuf[cb ^ 1];
-    auto find_or_add = [&](int node, int len, int last) -> int {
-      for (int i = 0; i < nn; ++i)
-        if (nxt[i].node == node) return i;
-      if (nn >= PB_MAX_CAND) { overflow = true; return nn - 1; }
-      nxt[nn] = Hyp{node, len, last, PB_NEG, PB_NEG, PB_NEG, PB_NEG, PB_NEG};
-      return nn++;
-    };
-    auto child = [&](int node, int tok) -> int {
-      for (int i = ntrie - 1; i > 0; --i)
-        if (tpar[i] == node && ttok[i] == tok) return i;
-      if (ntrie >= p.trie_cap) { overflow = true; return ntrie - 1; }
-      tpar[ntrie] = node; ttok[ntrie] = tok;
-      return ntrie++;
-    };
-    auto copy_times = [&](int* dst, const int* src, int n) { for (int i = 0; i < n && i < p.max_len; ++i) dst[i] = src[i]; };
+    int* tc = tbuf[0];
+    int* tn = tbuf[1];
     for (int i = 0; i < k; ++i) {
-      const int id = top[i];
+      const int id = s_top[i];
       const float prob = row[id];
       for (int h = 0; h < ncur; ++h) {
-        const Hyp ps = cur[h];
-        const int* ps_ts = tc + (size_t)h * tstride;
-        const int* ps_tns = ps_ts + p.max_len;
-        const int* ps_times = ps.v_s > ps.v_ns ? ps_ts : ps_tns;
-        if (id == p.blank) {
-          const int j = find_or_add(ps.node, ps.len, ps.last);
-          nxt[j].s = log_add(nxt[j].s, hyp_score(ps) + prob);
-          nxt[j].v_s = hyp_viterbi(ps) + prob;
-          copy_times(tn + (size_t)j * tstride, ps_times, ps.len);
-        } else if (ps.len > 0 && id == ps.last) {
-          const int j1 = find_or_add(ps.node, ps.len, ps.last);
-          nxt[j1].ns = log_add(nxt[j1].ns, ps.ns + prob);
-          if (nxt[j1].v_ns < ps.v_ns + prob) {
-            nxt[j1].v_ns = ps.v_ns + prob;
-            if (nxt[j1].cur_token_prob < prob) {
-              nxt[j1].cur_token_prob = prob;
-              int* d = tn + (size_t)j1 * tstride + p.max_len;
-              copy_times(d, ps_tns, ps.len);
-              if (ps.len > 0 && ps.len <= p.max_len) d[ps.len - 1] = t;
+        // up to two time-vector copies per pair: (dst, src, n, position that receives t or -1)
+        long long c_dst[2] = {-1, -1}, c_src[2] = {0, 0};
+        int c_n[2] = {0, 0}, c_set[2] = {-1, -1}, ncp = 0;
+        if (lane == 0) {
+          auto find_or_add = [&](int node, int len, int last) -> int {
+            unsigned slot = mix((unsigned)node, 0x51u) & (PB_HASH_CAND - 1);
+            for (;;) {
+              const int j = chash[slot];
+              if (j < 0) break;
+              if (nxt[j].node == node) return j;
+              slot = (slot + 1) & (PB_HASH_CAND - 1);
+            }
+            if (nn >= PB_MAX_CAND) { overflow = true; return nn - 1; }
+            nxt[nn] = Hyp{node, len, last, PB_NEG, PB_NEG, PB_NEG, PB_NEG, PB_NEG};
+            chash[slot] = nn;
+            return nn++;
+          };
+          auto child = [&](int node, int tok) -> int {
+            unsigned slot = mix((unsigned)node, (unsigned)tok) & (unsigned)(p.trie_hash_cap - 1);
+            for (;;) {
+              const int j = thash[slot];
+              if (j < 0) break;
+              if (tpar[j] == node && ttok[j] == tok) return j;
+              slot = (slot + 1) & (unsigned)(p.trie_hash_cap - 1);
+            }
+            if (ntrie >= p.trie_cap) { overflow = true; return ntrie - 1; }
+            tpar[ntrie] = node; ttok[ntrie] = tok;
+            thash[slot] = ntrie;
+            return ntrie++;
+          };
+          auto want_copy = [&](int* dst, const int* src, int n, int set_pos) {
+            c_dst[ncp] = dst - p.times; c_src[ncp] = src - p.times; c_n[ncp] = n; c_set[ncp] = set_pos; ++ncp;
+          };
+          const Hyp ps = cur[h];
+          const int* ps_ts = tc + (size_t)h * tstride;
+          const int* ps_tns = ps_ts + p.max_len;
+          const int* ps_times = ps.v_s > ps.v_ns ? ps_ts : ps_tns;
+          if (id == p.blank) {
+            const int j = find_or_add(ps.node, ps.len, ps.last);
+            nxt[j].s = log_add(nxt[j].s, hyp_score(ps) + prob);
+            nxt[j].v_s = hyp_viterbi(ps) + prob;
+            want_copy(tn + (size_t)j * tstride, ps_times, ps.len, -1);
+          } else if (ps.len > 0 && id == ps.last) {
+            const int j1 = find_or_add(ps.node, ps.len, ps.last);
+            nxt[j1].ns = log_add(nxt[j1].ns, ps.ns + prob);
+            if (nxt[j1].v_ns < ps.v_ns + prob) {
+              nxt[j1].v_ns = ps.v_ns + prob;
+              if (nxt[j1].cur_token_prob < prob) {
+                nxt[j1].cur_token_prob = prob;
+                want_copy(tn + (size_t)j1 * tstride + p.max_len, ps_tns, ps.len, (ps.len > 0 && ps.len <= p.max_len) ? ps.len - 1 : -1);
+              }
+            }
+            if (ps.len + 1 > p.max_len) overflow = true;
+            else {
+              const int j2 = find_or_add(child(ps.node, id), ps.len + 1, id);
+              nxt[j2].ns = log_add(nxt[j2].ns, ps.s + prob);
+              if (nxt[j2].v_ns < ps.v_s + prob) {
+                nxt[j2].v_ns = ps.v_s + prob;
+                nxt[j2].cur_token_prob = prob;
+                want_copy(tn + (size_t)j2 * tstride + p.max_len, ps_ts, ps.len, ps.len);
+              }
+            }
+          } else {
+            if (ps.len + 1 > p.max_len) overflow = true;
+            else {
+              const int j = find_or_add(child(ps.node, id), ps.len + 1, id);
+              nxt[j].ns = log_add(nxt[j].ns, hyp_score(ps) + prob);
+              if (nxt[j].v_ns < hyp_viterbi(ps) + prob) {
+                nxt[j].v_ns = hyp_viterbi(ps) + prob;
+                nxt[j].cur_token_prob = prob;
+                want_copy(tn + (size_t)j * tstride + p.max_len, ps_times, ps.len, ps.len);
+              }
             }
           }
-          if (ps.len + 1 > p.max_len) { overflow = true; continue; }
-          const int j2 = find_or_add(child(ps.node, id), ps.len + 1, id);
-          nxt[j2].ns = log_add(nxt[j2].ns, ps.s + prob);
-          if (nxt[j2].v_ns < ps.v_s + prob) {
-            nxt[j2].v_ns = ps.v_s + prob;
-            nxt[j2].cur_token_prob = prob;
-            int* d = tn + (size_t)j2 * tstride + p.max_len;
-            copy_times(d, ps_ts, ps.len);
-            d[ps.len] = t;
-          }
-        } else {
-          if (ps.len + 1 > p.max_len) { overflow = true; continue; }
-          const int j = find_or_add(child(ps.node, id), ps.len + 1, id);
-          nxt[j].ns = log_add(nxt[j].ns, hyp_score(ps) + prob);
-          if (nxt[j].v_ns < hyp_viterbi(ps) + prob) {
-            nxt[j].v_ns = hyp_viterbi(ps) + prob;
-            nxt[j].cur_token_prob = prob;
-            int* d = tn + (size_t)j * tstride + p.max_len;
-            copy_times(d, ps_times, ps.len);
-            d[ps.len] = t;
-          }
+        }
+        ncp = __shfl_sync(FULL, ncp, 0);
+        for (int c = 0; c < ncp; ++c) {                  // in order: a later copy may overwrite an earlier one's destination
+          const long long dsto = __shfl_sync(FULL, c_dst[c], 0), srco = __shfl_sync(FULL, c_src[c], 0);
+          const int n = __shfl_sync(FULL, c_n[c], 0), sp = __shfl_sync(FULL, c_set[c], 0);
+          int* dst = p.times + dsto;
+          const int* src = p.times + srco;
+          const int lim = min(max(n, sp + 1), p.max_len);
+          for (int q = lane; q < lim; q += 32) dst[q] = (q == sp) ? t : src[q];
+          __syncwarp();
         }
       }
     }
-    // 3. second beam: keep the best second_beam by score (descending); selection sort keeps earlier candidates on ties
+    nn = __shfl_sync(FULL, nn, 0);
+    __syncwarp();
+    // 3. second beam: the best second_beam candidates by score, descending; the earlier candidate wins among equal scores
     const int keep = min(min(nn, p.second_beam), PB_MAX_BEAM);
-    int order[PB_MAX_BEAM];
-    for (int r = 0; r < keep; ++r) {
-      int best = -1;
-      float bs = 0.f;
-      for (int i = 0; i < nn; ++i) {
-        bool used = false;
-        for (int j = 0; j < r; ++j) used |= (order[j] == i);
-        if (used) continue;
-        const float sc = hyp_score(nxt[i]);
-        if (best < 0 || sc > bs) { best = i; bs = sc; }
+    {
+      // candidate scores are recomputed per round from nxt (cheap); taken candidates are marked in a per-lane bitmask
+      // (lane l owns candidates l, l + 32, ...: at most PB_MAX_CAND / 32 = 22 of them)
+      unsigned taken = 0;
+      for (int r = 0; r < keep; ++r) {
+        float bv = 0.f; int bi = -1;
+        for (int i = lane, q = 0; i < nn; i += 32, ++q) {
+          if ((taken >> q) & 1u) continue;
+          const float sc = hyp_score(nxt[i]);
+          if (bi < 0 || sc > bv) { bv = sc; bi = i; }
+        }
+        warp_argmax(bv, bi);
+        if (bi >= 0 && (bi & 31) == lane) taken |= 1u << (bi >> 5);
+        if (lane == 0) s_order[r] = bi;
       }
-      order[r] = best;
     }
-    // 4. new beam; compact the time vectors into the other buffer in beam order
-    for (int r = 0; r < keep; ++r) cur[r] = nxt[order[r]];
-    // tn currently holds times indexed by candidate; re-index into tc (free now) by beam position
+    __syncwarp();
+    // 4. new beam; compact the time vectors into the other buffer in beam order; clear the candidate hash
+    for (int r = lane; r < keep; r += 32) cur[r] = nxt[s_order[r]];
     for (int r = 0; r < keep; ++r) {
-      const int* src = tn + (size_t)order[r] * tstride;
+      const int* src = tn + (size_t)s_order[r] * tstride;
       int* dst = tc + (size_t)r * tstride;
-      for (int i = 0; i < (int)tstride; ++i) dst[i] = src[i];
+      for (int i = lane; i < (int)tstride; i += 32) dst[i] = src[i];
     }
+    for (int i = lane; i < PB_HASH_CAND; i += 32) chash[i] = -1;
     ncur = keep;
-    // tc now holds the current beam's times; keep cb unchanged
+    __syncwarp();
   }
   // outputs
-  p.out_n[u] = ncur;
-  const int* tc = tbuf[cb];
-  for (int r = 0; r < ncur; ++r) {
+  if (lane == 0) p.out_n[u] = ncur;
+  const int* tc = tbuf[0];
+  for (int r = lane; r < ncur; r += 32) {
     const Hyp& h = cur[r];
     const size_t o = (size_t)u * p.second_beam + r;
     p.out_len[o] = h.len;
@@ -193,7 +262,8 @@ __global__ void prefix_beam_kernel(const PbParams p) {
     const int* src = h.v_s > h.v_ns ? ts : ts + p.max_len;
     for (int i = 0; i < h.len; ++i) p.out_times[o * p.max_len + i] = src[i];
   }
-  if (overflow) p.status[u] = 1;
+  overflow = __any_sync(FULL, overflow);
+  if (overflow && lane == 0) p.status[u] = 1;
 }
 
 thread_local char g_perr[256] = "";
@@ -216,34 +286,58 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
     snprintf(g_perr, sizeof(g_perr), "beam sizes must be in [1, %d]", PB_MAX_BEAM);
     return B2T_ERR_UNSUPPORTED;
   }
+  const double t_begin = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   PbParams p;
   p.N = N; p.T = T; p.C = C; p.blank = blank; p.first_beam = first_beam; p.second_beam = second_beam; p.max_len = max_len;
   p.trie_cap = 1 + T * second_beam * first_beam;
   float *d_logp, *d_score, *d_vit;
-  int *d_lens, *d_tp, *d_tt, *d_times, *d_ids, *d_len, *d_otimes, *d_n, *d_status;
-  Hyp* d_hyps;
+  int *d_lens, *d_tp, *d_tt, *d_th, *d_times, *d_ids, *d_len, *d_otimes, *d_n, *d_status;
+  p.trie_hash_cap = 1024;
+  while (p.trie_hash_cap < 2 * p.trie_cap) p.trie_hash_cap *= 2;
   if (second_beam * (first_beam + 1) > PB_MAX_CAND) {
     snprintf(g_perr, sizeof(g_perr), "second_beam * (first_beam + 1) must be <= %d", PB_MAX_CAND);
     return B2T_ERR_UNSUPPORTED;
   }
   const size_t nb = (size_t)N * second_beam;
   const size_t times_elems = (size_t)N * 2 * PB_MAX_CAND * 2 * max_len;
-  bool ok = cudaMalloc(&d_logp, (size_t)N * T * C * 4 + 4) == cudaSuccess && cudaMalloc(&d_lens, N * 4) == cudaSuccess &&
-            cudaMalloc(&d_tp, (size_t)N * p.trie_cap * 4) == cudaSuccess && cudaMalloc(&d_tt, (size_t)N * p.trie_cap * 4) == cudaSuccess &&
-            cudaMalloc(&d_times, times_elems * 4) == cudaSuccess && cudaMalloc(&d_ids, nb * max_len * 4) == cudaSuccess &&
-            cudaMalloc(&d_len, nb * 4) == cudaSuccess && cudaMalloc(&d_score, nb * 4) == cudaSuccess && cudaMalloc(&d_vit, nb * 4) == cudaSuccess &&
-            cudaMalloc(&d_otimes, nb * max_len * 4) == cudaSuccess && cudaMalloc(&d_n, N * 4) == cudaSuccess && cudaMalloc(&d_status, N * 4) == cudaSuccess &&
-            cudaMalloc(&d_hyps, (size_t)N * (PB_MAX_BEAM + PB_MAX_CAND) * sizeof(Hyp)) == cudaSuccess;
+  // one cached device workspace per host thread, grown on demand (cudaMalloc / cudaFree per call cost more than the search)
+  struct Ws { void* base = nullptr; size_t cap = 0; ~Ws() { /* released with the context */ } };
+  static thread_local Ws ws;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+  const size_t o_logp = carve((size_t)N * T * C * 4 + 4), o_lens = carve((size_t)N * 4), o_tp = carve((size_t)N * p.trie_cap * 4),
+               o_tt = carve((size_t)N * p.trie_cap * 4), o_th = carve((size_t)N * p.trie_hash_cap * 4), o_times = carve(times_elems * 4),
+               o_ids = carve(nb * max_len * 4), o_len = carve(nb * 4), o_score = carve(nb * 4), o_vit = carve(nb * 4),
+               o_otimes = carve(nb * max_len * 4), o_n = carve((size_t)N * 4), o_status = carve((size_t)N * 4);
+  bool ok = true;
+  if (off > ws.cap) {
+    if (ws.base) cudaFree(ws.base);
+    ws.base = nullptr; ws.cap = 0;
+    ok = cudaMalloc(&ws.base, off) == cudaSuccess;
+    if (ok) ws.cap = off;
+  }
+  if (ok) {
+    uint8_t* b8 = reinterpret_cast<uint8_t*>(ws.base);
+    d_logp = reinterpret_cast<float*>(b8 + o_logp); d_lens = reinterpret_cast<int*>(b8 + o_lens);
+    d_tp = reinterpret_cast<int*>(b8 + o_tp); d_tt = reinterpret_cast<int*>(b8 + o_tt); d_th = reinterpret_cast<int*>(b8 + o_th);
+    d_times = reinterpret_cast<int*>(b8 + o_times); d_ids = reinterpret_cast<int*>(b8 + o_ids); d_len = reinterpret_cast<int*>(b8 + o_len);
+    d_score = reinterpret_cast<float*>(b8 + o_score); d_vit = reinterpret_cast<float*>(b8 + o_vit);
+    d_otimes = reinterpret_cast<int*>(b8 + o_otimes); d_n = reinterpret_cast<int*>(b8 + o_n); d_status = reinterpret_cast<int*>(b8 + o_status);
+  }
   if (!ok) { snprintf(g_perr, sizeof(g_perr), "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())); return B2T_ERR_CUDA; }
   cudaMemcpy(d_logp, logp, (size_t)N * T * C * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(d_lens, lens, N * 4, cudaMemcpyHostToDevice);
   cudaMemset(d_status, 0, N * 4); cudaMemset(d_ids, 0, nb * max_len * 4); cudaMemset(d_otimes, 0, nb * max_len * 4);
   cudaMemset(d_len, 0, nb * 4); cudaMemset(d_score, 0, nb * 4); cudaMemset(d_vit, 0, nb * 4);
-  p.hyps = d_hyps;
-  p.logp = d_logp; p.lens = d_lens; p.trie_parent = d_tp; p.trie_token = d_tt; p.times = d_times;
+  p.logp = d_logp; p.lens = d_lens; p.trie_parent = d_tp; p.trie_token = d_tt; p.trie_hash = d_th; p.times = d_times;
   p.out_ids = d_ids; p.out_len = d_len; p.out_score = d_score; p.out_viterbi = d_vit; p.out_times = d_otimes; p.out_n = d_n; p.status = d_status;
-  prefix_beam_kernel<<<(N + 31) / 32, 32>>>(p);
+  static const bool timing = getenv("B2T_DECODER_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  cudaDeviceSynchronize();
+  const double t_k0 = now();
+  prefix_beam_kernel<<<N, 32>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
+  if (timing) fprintf(stderr, "b2t prefix beam: N=%d T=%d beams %dx%d trie_cap %d: setup %.2f ms, kernel %.2f ms\n", N, T, first_beam, second_beam, p.trie_cap, t_k0 - t_begin, now() - t_k0);
   int rc = 0;
   if (e != cudaSuccess) { snprintf(g_perr, sizeof(g_perr), "prefix_beam_kernel: %s", cudaGetErrorString(e)); rc = B2T_ERR_CUDA; }
   std::vector<int> status(N);
@@ -255,8 +349,6 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
     for (int i = 0; i < N; ++i)
       if (status[i]) { snprintf(g_perr, sizeof(g_perr), "utterance %d: prefix longer than max_len=%d or candidate overflow", i, max_len); rc = B2T_ERR_WORKSPACE; }
   }
-  void* ptrs[] = {d_logp, d_lens, d_tp, d_tt, d_times, d_ids, d_len, d_score, d_vit, d_otimes, d_n, d_status, d_hyps};
-  for (void* q : ptrs) cudaFree(q);
   return rc;
 }
 
