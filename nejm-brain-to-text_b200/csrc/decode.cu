@@ -1063,8 +1063,26 @@ int prune_slots_on_gpu(b2t_decoder* d, const std::vector<int>& ids) {
   return 0;
 }
 
-// Host view of a slot after prune_slots_on_gpu: every token and link is a survivor.
-int fetch_pruned_lattice(b2t_decoder* d, int slot, Lattice* L) {
+// links ordered by source token (stable counting sort) + per-token link ranges and frame levels
+void index_lattice(Lattice* L) {
+  const int nt = (int)L->state.size();
+  L->lbeg.assign(nt + 1, 0);
+  for (const DLink& k : L->links) L->lbeg[k.src + 1]++;
+  for (int i = 0; i < nt; ++i) L->lbeg[i + 1] += L->lbeg[i];
+  {
+    std::vector<int> pos(L->lbeg.begin(), L->lbeg.end() - 1);
+    std::vector<DLink> sorted(L->links.size());
+    for (const DLink& k : L->links) sorted[pos[k.src]++] = k;
+    L->links.swap(sorted);
+  }
+  L->frame_of.resize(nt);
+  for (int f = 0; f < L->F; ++f)
+    for (int i = L->ftok[f]; i < L->ftok[f + 1]; ++i) L->frame_of[i] = f;
+}
+
+// Host view of a slot after prune_slots_on_gpu: every token and link is a survivor.  With index_now == false only the copies
+// are done here (the caller indexes the lattice on a worker thread).
+int fetch_pruned_lattice(b2t_decoder* d, int slot, Lattice* L, bool index_now = true) {
   int counters[4], cc[2];
   DCK(cudaMemcpyAsync(counters, d->d_counters + slot * 4, sizeof(counters), cudaMemcpyDeviceToHost, d->stream));
   DCK(cudaMemcpyAsync(cc, d->d_ccounts + slot * 2, sizeof(cc), cudaMemcpyDeviceToHost, d->stream));
@@ -1083,18 +1101,7 @@ int fetch_pruned_lattice(b2t_decoder* d, int slot, Lattice* L) {
   if (nl) DCK(cudaMemcpyAsync(L->links.data(), d->d_links + (size_t)slot * d->link_cap, nl * sizeof(DLink), cudaMemcpyDeviceToHost, d->stream));
   if (nf) DCK(cudaMemcpyAsync(L->coff.data(), d->d_coff + (size_t)slot * d->max_frames, nf * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
   DCK(cudaStreamSynchronize(d->stream));
-  L->lbeg.assign(nt + 1, 0);
-  for (const DLink& k : L->links) L->lbeg[k.src + 1]++;
-  for (int i = 0; i < nt; ++i) L->lbeg[i + 1] += L->lbeg[i];
-  {
-    std::vector<int> pos(L->lbeg.begin(), L->lbeg.end() - 1);
-    std::vector<DLink> sorted(L->links.size());
-    for (const DLink& k : L->links) sorted[pos[k.src]++] = k;
-    L->links.swap(sorted);
-  }
-  L->frame_of.resize(nt);
-  for (int f = 0; f < L->F; ++f)
-    for (int i = L->ftok[f]; i < L->ftok[f + 1]; ++i) L->frame_of[i] = f;
+  if (index_now) index_lattice(L);
   return 0;
 }
 
@@ -1120,9 +1127,9 @@ void finish_from_lattice(b2t_decoder* d, int slot, const Lattice& L, double fetc
             L.links.size(), fetch_ms, t2 - t1, now() - t2, s.results.size());
 }
 
-bool use_gpu_prune() {
-  static const bool on = !(getenv("B2T_DECODER_HOST_PRUNE") && atoi(getenv("B2T_DECODER_HOST_PRUNE")) != 0);   // A/B switch: host restatement of the pruning
-  return on;
+bool use_gpu_prune() {   // A/B switch (read at every call so that tests can flip it): host restatement of the pruning
+  const char* v = getenv("B2T_DECODER_HOST_PRUNE");
+  return !(v && atoi(v) != 0);
 }
 
 int finish_slot(b2t_decoder* d, int slot) {
@@ -1166,7 +1173,10 @@ int finish_slots(b2t_decoder* d, int N) {
         if (next >= fetched) return;
         n = next++;
       }
-      if (d->slots[n].n_fed > 0) finish_from_lattice(d, n, lats[n], fetch_ms[n], gpu_prune);
+      if (d->slots[n].n_fed > 0) {
+        if (gpu_prune) index_lattice(&lats[n]);
+        finish_from_lattice(d, n, lats[n], fetch_ms[n], gpu_prune);
+      }
       Lattice().state.swap(lats[n].state);
       std::vector<DLink>().swap(lats[n].links);
     }
@@ -1184,7 +1194,7 @@ int finish_slots(b2t_decoder* d, int N) {
     s.results.clear();
     s.finished = true;
     const double t0 = now();
-    if (s.n_fed > 0) rc = gpu_prune ? fetch_pruned_lattice(d, n, &lats[n]) : fetch_lattice(d, n, &lats[n]);
+    if (s.n_fed > 0) rc = gpu_prune ? fetch_pruned_lattice(d, n, &lats[n], false) : fetch_lattice(d, n, &lats[n]);
     fetch_ms[n] = now() - t0;
     {
       std::lock_guard<std::mutex> lk(mu);

@@ -161,3 +161,41 @@ def test_prefix_beam_golden_and_oracle(LM):
         assert [r[0] for r in ours[n]] == [r[0] for r in ref]                        # identical hypotheses, same order
         assert all(abs(a[1] - b[1]) < 1e-4 and abs(a[2] - b[2]) < 1e-4 for a, b in zip(ours[n], ref))
         assert [r[3] for r in ours[n]] == [r[3] for r in ref]
+
+
+def test_gpu_lattice_pruning_equals_host_pruning(LM, graph, monkeypatch):
+    """lattice_prune_kernel (extra costs + compaction on the device) against the host restatement of FinalizeDecoding:
+    identical n-best lists, scores included, on a wide beam where most of the lattice is pruned away."""
+    fst, words, info = graph
+    opts = (7000, 200, 17.0, 8.0, 0.325, 1.0, 0.0, 100)
+    N, T = 6, 100
+    rng = np.random.RandomState(21)
+    batch = np.stack([TLG.render_logits([info["prons"][w] for w in rng.randint(0, 300, size=rng.randint(2, 5))], T=T, seed=300 + n, noise=1.3)
+                      for n in range(N)])
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B2T_DECODER_HOST_PRUNE", mode)
+        dec = _ours(LM, fst, words, opts, max_frames=128, max_slots=N)
+        dec.DecodeBatch(batch, blank_penalty=math.log(90.0))
+        res[mode] = [[(r.sentence, r.ac_score, r.lm_score) for r in dec.result(slot=n)] for n in range(N)]
+        single = _ours(LM, fst, words, opts, max_frames=128)       # the single-utterance entry points take the same path
+        LM.DecodeNumpy(single, batch[0], np.zeros_like(batch[0]), math.log(90.0))
+        single.FinishDecoding()
+        single.FinishDecoding()                                    # idempotent
+        assert [(r.sentence, r.ac_score, r.lm_score) for r in single.result()] == res[mode][0]
+    assert all(len(r) > 1 for r in res["0"])
+    assert res["0"] == res["1"]
+
+
+def test_prefix_beam_wide(LM):
+    """Beam sizes at the kernel's limits (second beam 64, first beam = all classes) against the oracle."""
+    rng = np.random.RandomState(4)
+    x = rng.randn(3, 40, 41).astype(np.float32) * 1.5
+    x[..., 0] += 2.0
+    lp = x - np.log(np.exp(x).sum(-1, keepdims=True))
+    for fb, sb in ((41, 16), (10, 64)):
+        ours = LM.ctc_prefix_beam_search(lp, first_beam_size=fb, second_beam_size=sb)
+        for n in range(3):
+            ref = D.prefix_search(lp[n], fb, sb)
+            assert [r[0] for r in ours[n]] == [r[0] for r in ref]
+            assert all(abs(a[1] - b[1]) < 1e-4 and abs(a[2] - b[2]) < 1e-4 for a, b in zip(ours[n], ref))

@@ -94,13 +94,29 @@ def main():
         out.append(f"| {ma} | {dt * 1e3:.1f} | {kms:.1f} | {dt * 1e3 / Nutt:.3f} | {dto * 1e3:.2f} | {dto / (dt / Nutt):.1f}x | {agree}/{Nutt} | {w_o:.3f} | {w_r:.3f} | "
                    f"{np.mean([len(a) for a in ours]):.1f} / {np.mean([len(b) for b in refs]):.1f} |")
         del dec
+    # ---- throughput with many utterances in flight (no oracle: it would take minutes)
+    if not only or "wfst" in only:
+        out.append("\n## WFST decoder throughput, 64 utterances per call (same graph and settings, n-best 100)\n")
+        out.append("| max_active | ms per batch | trials/s | GPU search kernel ms | GPU share |\n|---:|---:|---:|---:|---:|")
+        rng2 = np.random.RandomState(8)
+        big = np.stack([TLG.render_logits([info["prons"][w] for w in rng2.randint(0, 1000, size=rng2.randint(2, 4))], T=T, seed=900 + n, noise=1.0) for n in range(64)])
+        for ma in (200, 7000):
+            opts = (ma, min(200, ma), 17.0, 8.0, 0.325, 1.0, 0.0, 100)
+            dec = LM.BrainSpeechDecoder(LM.DecodeResource(fst, "", "", words, ""), LM.DecodeOptions(*opts), max_frames=128, max_slots=64)
+            dec.DecodeBatch(big, blank_penalty=bp)
+            t0 = time.perf_counter()
+            dec.DecodeBatch(big, blank_penalty=bp)
+            dt = time.perf_counter() - t0
+            kms = dec.stats(slot=0)["kernel_ms"]
+            out.append(f"| {ma} | {dt * 1e3:.1f} | {64 / dt:.0f} | {kms:.1f} | {kms / (dt * 1e3):.2f} |")
+            del dec
     # ---- prefix beam
     out.append(f"\n## LM-free CTC prefix beam search, {Nutt} utterances x {T} frames per call (log-softmax of the same logits)\n")
     out.append("| first_beam x second_beam | ours: ms per batch | ours: ms per trial | oracle (1 CPU thread): ms per trial | identical hypothesis lists |")
     out.append("|---|---:|---:|---:|---:|")
     lp = batch - np.log(np.exp(batch).sum(-1, keepdims=True))
     for fb, sb in (((10, 10), (10, 20), (10, 50), (10, 64), (41, 16)) if not only or "prefix" in only else ()):
-        LM.ctc_prefix_beam_search(lp[:2], first_beam_size=fb, second_beam_size=sb)
+        LM.ctc_prefix_beam_search(lp, first_beam_size=fb, second_beam_size=sb)     # warm-up (device workspace)
         t0 = time.perf_counter()
         ours = LM.ctc_prefix_beam_search(lp, first_beam_size=fb, second_beam_size=sb)
         dt = time.perf_counter() - t0
