@@ -561,6 +561,118 @@ lattice_prune_kernel(const PruneParams p) {
   if (threadIdx.x == 0) p.c_counts[slot * 2 + 1] = lrun;
 }
 
+// ------------------------------------------------------------------------------------------------ best path on the GPU
+// Online GetBestPath (lattice-faster-online-decoder.cc:59-177): best token of the last level (with or without final costs),
+// back-pointers to the start, the cheapest matching link at every hop, weights multiplied from the start state forward.
+// One CTA per slot; only the word ids and two floats cross PCIe (the partial result after every Decode() chunk).
+constexpr int BP_MAX_PATH = 4096;
+struct BestPathParams {
+  const float* fin;
+  const int* tok_state; const float* tok_cost; const int* tok_bp; const DLink* links;
+  const int* frame_tok_off; const int* frame_link_off; const float* cost_offsets; const int* counters;
+  const int* slot_ids;
+  int* out_words;          // [slots][BP_MAX_PATH]
+  float* out_cost;         // [slots][4]: graph, acoustic, ok (1 / 0), number of words
+  float* scratch;          // [slots][BP_MAX_PATH][2] (graph, acoustic) of the hops, last hop first
+  int* scratch_ol;         // [slots][BP_MAX_PATH]
+  int tok_cap, link_cap, max_frames, use_final;
+};
+
+__global__ void __launch_bounds__(256, 1)
+best_path_kernel(const BestPathParams p) {
+  __shared__ unsigned long long s_key[8];
+  __shared__ unsigned long long s_best;
+  __shared__ int s_any;
+  const int slot = p.slot_ids[blockIdx.x];
+  const int* tok_state = p.tok_state + (size_t)slot * p.tok_cap;
+  const float* cost = p.tok_cost + (size_t)slot * p.tok_cap;
+  const int* bp = p.tok_bp + (size_t)slot * p.tok_cap;
+  const DLink* links = p.links + (size_t)slot * p.link_cap;
+  const int* ftok = p.frame_tok_off + (size_t)slot * (p.max_frames + 3);
+  const int* flink = p.frame_link_off + (size_t)slot * (p.max_frames + 3);
+  const float* coff = p.cost_offsets + (size_t)slot * p.max_frames;
+  float* hop = p.scratch + (size_t)slot * BP_MAX_PATH * 2;
+  int* hop_ol = p.scratch_ol + (size_t)slot * BP_MAX_PATH;
+  int* words = p.out_words + (size_t)slot * BP_MAX_PATH;
+  float* out = p.out_cost + slot * 4;
+  const int F = p.counters[slot * 4 + 2] + 1;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // block-wide minimum of 64-bit keys
+  auto block_min_key = [&](unsigned long long k) {
+    for (int o = 16; o; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, k, o); if (x < k) k = x; }
+    __syncthreads();
+    if (lane == 0) s_key[w] = k;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long b = s_key[0]; for (int i = 1; i < 8; ++i) if (s_key[i] < b) b = s_key[i]; s_best = b; }
+    __syncthreads();
+    return s_best;
+  };
+  const int fb = ftok[F - 1], fe = ftok[F];
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  if (p.use_final)
+    for (int i = fb + threadIdx.x; i < fe; i += 256)
+      if (p.fin[tok_state[i]] != INFINITY) s_any = 1;
+  __syncthreads();
+  const bool any_final = p.use_final && s_any;
+  // best token: smallest cost, the LAST created among equal costs (the reference walks the list in reverse creation order)
+  unsigned long long key = ~0ull;
+  for (int i = fb + threadIdx.x; i < fe; i += 256) {
+    float c = cost[i];
+    if (any_final) { const float fc = p.fin[tok_state[i]]; c = fc != INFINITY ? __fadd_rn(c, fc) : INFINITY; }
+    if (c == INFINITY) continue;
+    const unsigned long long k = ((unsigned long long)fkey(c) << 32) | (unsigned int)(0x7fffffff - i);
+    if (k < key) key = k;
+  }
+  key = block_min_key(key);
+  if (key == ~0ull) { if (threadIdx.x == 0) { out[0] = 0.f; out[1] = 0.f; out[2] = 0.f; out[3] = 0.f; } return; }
+  int tok = 0x7fffffff - (int)(unsigned int)key;
+  const float best_final = any_final ? p.fin[tok_state[tok]] : 0.0f;
+  int level = F - 1, nh = 0;
+  bool ok = true;
+  while (tok >= 0 && ok) {
+    const int b = bp[tok];
+    float gc = 0.0f, ac = 0.0f;
+    int ol = 0;
+    if (b >= 0) {
+      // every link INTO a level-f token is in [flink[f], flink[f+1]); cheapest (graph + ac), first created among equals
+      unsigned long long lk = ~0ull;
+      for (int l = flink[level] + threadIdx.x; l < flink[level + 1]; l += 256) {
+        const DLink k = links[l];
+        if (k.src != b || k.dst != tok) continue;
+        const unsigned long long kk = ((unsigned long long)fkey(__fadd_rn(k.graph, k.ac)) << 32) | (unsigned int)l;
+        if (kk < lk) lk = kk;
+      }
+      lk = block_min_key(lk);
+      if (lk == ~0ull) ok = false;
+      else {
+        const DLink k = links[(unsigned int)lk];
+        const int src_level = b >= ftok[level] ? level : level - 1;
+        gc = k.graph; ol = k.ol;
+        ac = k.il != 0 ? __fsub_rn(k.ac, coff[src_level]) : k.ac;
+        if (b < ftok[level]) level -= 1;
+      }
+    }
+    if (nh >= BP_MAX_PATH) ok = false;
+    if (ok && threadIdx.x == 0) { hop[2 * nh] = gc; hop[2 * nh + 1] = ac; hop_ol[nh] = ol; }
+    ++nh;
+    tok = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tg = 0.0f, ta = 0.0f;
+    int nw = 0;
+    if (ok) {
+      for (int i = nh - 1; i >= 0; --i) {
+        tg = __fadd_rn(tg, hop[2 * i]); ta = __fadd_rn(ta, hop[2 * i + 1]);
+        if (hop_ol[i] != 0) words[nw++] = hop_ol[i];
+      }
+      tg = __fadd_rn(tg, best_final);
+    }
+    out[0] = tg; out[1] = ta; out[2] = ok ? 1.0f : 0.0f; out[3] = (float)nw;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct HostGraph {
   int start = -1;
@@ -638,6 +750,7 @@ struct b2t_decoder {
   int *d_ftok = nullptr, *d_flink = nullptr, *d_counters = nullptr, *d_nfed = nullptr, *d_slot_ids = nullptr;
   float *d_coff = nullptr, *d_logp = nullptr;
   float* d_fin = nullptr; unsigned int* d_extra = nullptr; int *d_newidx = nullptr, *d_cftok = nullptr, *d_ccounts = nullptr;   // GPU lattice pruning
+  int* d_bp_words = nullptr; float *d_bp_cost = nullptr, *d_bp_hop = nullptr; int* d_bp_ol = nullptr;                                                    // GPU best path
   std::vector<Slot> slots;
   cudaStream_t stream = nullptr;
   double last_kernel_ms = 0.0;
@@ -1037,14 +1150,52 @@ int reset_slot(b2t_decoder* d, int slot) {
   return 0;
 }
 
+bool use_gpu_prune() {   // A/B switch (read at every call so that tests can flip it): host restatement of pruning / best path
+  const char* v = getenv("B2T_DECODER_HOST_PRUNE");
+  return !(v && atoi(v) != 0);
+}
+
+// 1-best of a slot through best_path_kernel; returns 1 when a path was found
+int best_path_on_gpu(b2t_decoder* d, int slot, bool use_final, std::vector<int>* words, float* graph, float* acoustic) {
+  int counters[4];
+  DCK(cudaMemcpyAsync(counters, d->d_counters + slot * 4, sizeof(counters), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaMemcpyAsync(d->d_slot_ids, &slot, sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  DCK(cudaStreamSynchronize(d->stream));
+  if (counters[3] == 1) return dfail(B2T_ERR_WORKSPACE, "decoder token pool overflow (capacity %d): raise max_active-derived capacity or lower beam", d->tok_cap);
+  if (counters[3] == 2) return dfail(B2T_ERR_WORKSPACE, "decoder link pool overflow (capacity %d)", d->link_cap);
+  BestPathParams p;
+  p.fin = d->d_fin; p.tok_state = d->d_tok_state; p.tok_cost = d->d_tok_cost; p.tok_bp = d->d_tok_bp; p.links = d->d_links;
+  p.frame_tok_off = d->d_ftok; p.frame_link_off = d->d_flink; p.cost_offsets = d->d_coff; p.counters = d->d_counters; p.slot_ids = d->d_slot_ids;
+  p.out_words = d->d_bp_words; p.out_cost = d->d_bp_cost; p.scratch = d->d_bp_hop; p.scratch_ol = d->d_bp_ol;
+  p.tok_cap = d->tok_cap; p.link_cap = d->link_cap; p.max_frames = d->max_frames; p.use_final = use_final ? 1 : 0;
+  best_path_kernel<<<1, 256, 0, d->stream>>>(p);
+  DCK(cudaGetLastError());
+  float oc[4];
+  DCK(cudaMemcpyAsync(oc, d->d_bp_cost + slot * 4, sizeof(oc), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaStreamSynchronize(d->stream));
+  if (oc[2] == 0.0f) return 0;
+  const int nw = (int)oc[3];
+  words->resize(nw);
+  if (nw) DCK(cudaMemcpyAsync(words->data(), d->d_bp_words + (size_t)slot * BP_MAX_PATH, nw * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  DCK(cudaStreamSynchronize(d->stream));
+  *graph = oc[0]; *acoustic = oc[1];
+  return 1;
+}
+
 int partial_result(b2t_decoder* d, int slot) {   // ctc_wfst_beam_search.cc:112-120: 1-best without final costs after every chunk
   Slot& s = d->slots[slot];
   s.results.clear();
   if (s.n_fed == 0) return 0;
+  std::vector<int> w; float g, a;
+  if (use_gpu_prune()) {                       // (the same A/B switch selects the host restatement of the best path)
+    const int rc = best_path_on_gpu(d, slot, false, &w, &g, &a);
+    if (rc < 0) return rc;
+    if (rc > 0) push_result(d, s, w, g, a);
+    return 0;
+  }
   Lattice L;
   int rc = fetch_lattice(d, slot, &L);
   if (rc) return rc;
-  std::vector<int> w; float g, a;
   if (best_path(d, L, false, &w, &g, &a)) push_result(d, s, w, g, a);
   return 0;
 }
@@ -1127,11 +1278,6 @@ void finish_from_lattice(b2t_decoder* d, int slot, const Lattice& L, double fetc
             L.links.size(), fetch_ms, t2 - t1, now() - t2, s.results.size());
 }
 
-bool use_gpu_prune() {   // A/B switch (read at every call so that tests can flip it): host restatement of the pruning
-  const char* v = getenv("B2T_DECODER_HOST_PRUNE");
-  return !(v && atoi(v) != 0);
-}
-
 int finish_slot(b2t_decoder* d, int slot) {
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   Slot& s = d->slots[slot];
@@ -1140,6 +1286,13 @@ int finish_slot(b2t_decoder* d, int slot) {
   s.finished = true;
   if (s.n_fed == 0) return 0;
   const double t0 = now();
+  if (d->opt.nbest == 1 && use_gpu_prune()) {     // 1-best with final costs: back-pointer walk on the device
+    std::vector<int> w; float g, a;
+    const int r = best_path_on_gpu(d, slot, true, &w, &g, &a);
+    if (r < 0) return r;
+    if (r > 0) push_result(d, s, w, g, a);
+    return 0;
+  }
   Lattice L;
   const bool gpu_prune = d->opt.nbest != 1 && use_gpu_prune();
   int rc = gpu_prune ? prune_slots_on_gpu(d, std::vector<int>{slot}) : 0;
@@ -1154,6 +1307,10 @@ int finish_slot(b2t_decoder* d, int slot) {
 // extraction of different utterances run on worker threads.
 int finish_slots(b2t_decoder* d, int N) {
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  if (d->opt.nbest == 1 && use_gpu_prune()) {
+    for (int n = 0; n < N; ++n) { const int rc = finish_slot(d, n); if (rc) return rc; }
+    return 0;
+  }
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
   const int n_workers = (int)std::min<unsigned>(hw, 16u);
   std::vector<std::thread> workers;
@@ -1254,7 +1411,9 @@ b2t_decoder* b2t_decoder_create(const char* fst_path, const char* words_path, co
        cudaMalloc(&d->d_nfed, (size_t)max_slots * 4) == cudaSuccess && cudaMalloc(&d->d_slot_ids, (size_t)max_slots * 4) == cudaSuccess &&
        cudaMalloc(&d->d_fin, std::max<size_t>(ns, 1) * 4) == cudaSuccess && cudaMalloc(&d->d_extra, (size_t)max_slots * d->tok_cap * 4) == cudaSuccess &&
        cudaMalloc(&d->d_newidx, (size_t)max_slots * d->tok_cap * 4) == cudaSuccess && cudaMalloc(&d->d_cftok, (size_t)max_slots * (max_frames + 3) * 4) == cudaSuccess &&
-       cudaMalloc(&d->d_ccounts, (size_t)max_slots * 8) == cudaSuccess;
+       cudaMalloc(&d->d_ccounts, (size_t)max_slots * 8) == cudaSuccess &&
+       cudaMalloc(&d->d_bp_words, (size_t)max_slots * BP_MAX_PATH * 4) == cudaSuccess && cudaMalloc(&d->d_bp_cost, (size_t)max_slots * 16) == cudaSuccess &&
+       cudaMalloc(&d->d_bp_hop, (size_t)max_slots * BP_MAX_PATH * 8) == cudaSuccess && cudaMalloc(&d->d_bp_ol, (size_t)max_slots * BP_MAX_PATH * 4) == cudaSuccess;
   if (!ok) { dfail(B2T_ERR_CUDA, "decoder allocation failed: %s (states %zu, slots %d, token pool %d)", cudaGetErrorString(cudaGetLastError()), ns, max_slots, d->tok_cap); b2t_decoder_destroy(d); return nullptr; }
   cudaMemcpy(d->d_arcs, d->g.arcs.data(), na * sizeof(DArc), cudaMemcpyHostToDevice);
   cudaMemcpy(d->d_off, d->g.off.data(), (ns + 1) * sizeof(long long), cudaMemcpyHostToDevice);
@@ -1271,7 +1430,7 @@ b2t_decoder* b2t_decoder_create(const char* fst_path, const char* words_path, co
 void b2t_decoder_destroy(b2t_decoder* d) {
   if (!d) return;
   void* ptrs[] = {d->d_arcs, d->d_off, d->d_has_eps, d->d_best, d->d_tokidx, d->d_tok_state, d->d_tok_cost, d->d_tok_bp, d->d_dirty, d->d_links,
-                  d->d_ftok, d->d_flink, d->d_coff, d->d_counters, d->d_nfed, d->d_slot_ids, d->d_logp, d->d_fin, d->d_extra, d->d_newidx, d->d_cftok, d->d_ccounts};
+                  d->d_ftok, d->d_flink, d->d_coff, d->d_counters, d->d_nfed, d->d_slot_ids, d->d_logp, d->d_fin, d->d_extra, d->d_newidx, d->d_cftok, d->d_ccounts, d->d_bp_words, d->d_bp_cost, d->d_bp_hop, d->d_bp_ol};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;

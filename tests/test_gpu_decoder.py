@@ -185,6 +185,22 @@ def test_gpu_lattice_pruning_equals_host_pruning(LM, graph, monkeypatch):
         assert [(r.sentence, r.ac_score, r.lm_score) for r in single.result()] == res[mode][0]
     assert all(len(r) > 1 for r in res["0"])
     assert res["0"] == res["1"]
+    # 1-best: back-pointer walk on the device (partial result after every chunk, final result with final costs) vs host walk
+    one = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B2T_DECODER_HOST_PRUNE", mode)
+        dec = _ours(LM, fst, words, (7000, 200, 17.0, 8.0, 0.325, 1.0, 0.0, 1), max_frames=128)
+        got = []
+        for n in range(3):
+            dec.Reset()
+            lp = batch[n] - np.log(np.exp(batch[n]).sum(1, keepdims=True))
+            for i in range(0, T, 25):
+                LM.DecodeNumpyLogProbs(dec, lp[i:i + 25].astype(np.float32))
+                got.append([(r.sentence, r.ac_score, r.lm_score) for r in dec.result()])
+            dec.FinishDecoding()
+            got.append([(r.sentence, r.ac_score, r.lm_score) for r in dec.result()])
+        one[mode] = got
+    assert one["0"] == one["1"] and all(len(g) == 1 for g in one["0"])
 
 
 def test_prefix_beam_wide(LM):
