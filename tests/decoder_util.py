@@ -93,3 +93,98 @@ def prefix_search(logp, first_beam=10, second_beam=10, blank=0):
         out.append((ids[:n].tolist(), sc.value, vt.value, times[:n].tolist()))
     lib.orc_prefix_destroy(h)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's shipped 1-gram graph (language_model/pretrained_language_models/openwebtext_1gram_lm_sil).  It is reference
+# DATA, not source: __graft_entry__.build() stages it under oracle/_ref/ (git-ignored, travels to the GPU box) when
+# /root/reference is present; nothing here reads /root/reference at test time.
+REAL_GRAPH_DIR = os.path.join(ROOT, "oracle", "_ref", "openwebtext_1gram_lm_sil")
+
+
+def real_graph():
+    fst, words = os.path.join(REAL_GRAPH_DIR, "TLG.fst"), os.path.join(REAL_GRAPH_DIR, "words.txt")
+    return (fst, words) if os.path.exists(fst) and os.path.exists(words) else None
+
+
+def read_fst(path):
+    """OpenFST binary 'vector' FST with 'standard' arcs -> (start, finals[ns], offsets[ns + 1], arcs[na] structured array)."""
+    import struct
+    buf = open(path, "rb").read()
+    pos = 0
+
+    def take(fmt):
+        nonlocal pos
+        v = struct.unpack_from(fmt, buf, pos)
+        pos += struct.calcsize(fmt)
+        return v if len(v) > 1 else v[0]
+
+    def take_str():
+        nonlocal pos
+        n = take("<i")
+        s = buf[pos:pos + n].decode()
+        pos += n
+        return s
+
+    assert take("<i") == 2125659606, "not an OpenFST binary file"
+    ft, at = take_str(), take_str()
+    assert ft == "vector" and at == "standard", (ft, at)
+    _version, flags = take("<i"), take("<i")
+    _props, start, ns, na = take("<Q"), take("<q"), take("<q"), take("<q")
+    for bit in (1, 2):                      # embedded symbol tables
+        if flags & bit:
+            take("<i"); take_str(); take("<q")
+            size = take("<q")
+            for _ in range(size):
+                take_str(); take("<q")
+    arc_dt = np.dtype([("il", "<i4"), ("ol", "<i4"), ("w", "<f4"), ("next", "<i4")])
+    finals = np.empty(ns, np.float32); off = np.zeros(ns + 1, np.int64)
+    chunks = []
+    for s in range(ns):
+        fw, cnt = struct.unpack_from("<fq", buf, pos)
+        pos += 12
+        finals[s] = fw; off[s + 1] = off[s] + cnt
+        chunks.append(np.frombuffer(buf, arc_dt, cnt, pos))
+        pos += 16 * cnt
+    arcs = np.concatenate(chunks) if chunks else np.empty(0, arc_dt)
+    assert len(arcs) == na or na <= 0
+    return int(start), finals, off, arcs
+
+
+def random_walk_utterance(graph, rng, n_words=3, T=95, C=41, peak=7.0, noise=0.8, max_arcs=400):
+    """a seeded random walk from the start state until `n_words` words were emitted and a final state
+    is reached; the visited input labels (1 = blank, 2 = SIL, 3.. = phones; 0 = epsilon) are rendered as peaky posteriors.
+    Returns (logits [T, C], word ids) or None when the walk does not fit into T frames."""
+    start, finals, off, arcs = graph
+    s, labels, words = start, [], []
+    for _ in range(max_arcs):
+        if len(words) >= n_words and np.isfinite(finals[s]):
+            break
+        a = arcs[off[s]:off[s + 1]]
+        if len(a) == 0:
+            return None
+        cand = a[a["il"] != 1] if np.any(a["il"] != 1) else a          # do not idle on blank self loops
+        if len(words) >= n_words:                                       # head for a final state: prefer non-word arcs
+            c2 = cand[cand["ol"] == 0]
+            cand = c2 if len(c2) else cand
+        k = cand[rng.randint(len(cand))]
+        if k["il"] > 1:
+            labels.append(int(k["il"]) - 1)                             # graph ilabel -> logit column
+        if k["ol"] != 0:
+            words.append(int(k["ol"]))
+        s = int(k["next"])
+    else:
+        return None
+    x = noise * rng.randn(T, C).astype(np.float32)
+    x[:, 0] += 2.0
+    t, prev = int(rng.randint(1, 3)), None
+    for cls in labels:
+        if prev == cls:
+            t += 1                                                      # CTC needs a blank between repeated labels
+        d = int(rng.randint(2, 4))
+        if t + d >= T - 1:
+            return None
+        x[t:t + d, cls] += peak
+        t += d + int(rng.randint(0, 2))
+        prev = cls
+    return x, words

@@ -215,3 +215,42 @@ def test_prefix_beam_wide(LM):
             ref = D.prefix_search(lp[n], fb, sb)
             assert [r[0] for r in ours[n]] == [r[0] for r in ref]
             assert all(abs(a[1] - b[1]) < 1e-4 and abs(a[2] - b[2]) < 1e-4 for a, b in zip(ours[n], ref))
+
+
+@pytest.mark.skipif(D.real_graph() is None, reason="the shipped 1-gram graph is staged under oracle/_ref/ by __graft_entry__.build()")
+@pytest.mark.parametrize("max_active,n_utt", [(7000, 2), (500, 5)])
+def test_shipped_1gram_graph_vs_oracle(LM, max_active, n_utt):
+    """The reference's own decoding graph (openwebtext 1-gram TLG, 179 946 states) at its shipped decoder settings
+    (LM/README.md: beam 17, lattice_beam 8, acoustic_scale 0.325, blank penalty log 90, n-best 100): utterances rendered from
+    random walks through the graph, GPU decoder against the oracle."""
+    fst, words = D.real_graph()
+    g = D.read_fst(fst)
+    rng = np.random.RandomState(7)
+    utts = []
+    while len(utts) < n_utt:
+        u = D.random_walk_utterance(g, rng, n_words=int(rng.randint(1, 4)), peak=9.0, noise=0.6)
+        if u is not None:
+            utts.append(u[0])
+    batch = np.stack(utts)
+    opts = (max_active, 200, 17.0, 8.0, 0.325, 1.0, 0.0, 100)
+    dec = _ours(LM, fst, words, opts, max_frames=128, max_slots=n_utt)
+    dec.DecodeBatch(batch, blank_penalty=math.log(90.0))
+    ref = D.OracleDecoder(fst, words, *opts)
+    for n in range(n_utt):
+        ref.reset(); ref.decode_logits(batch[n], np.zeros_like(batch[n]), math.log(90.0)); ref.finish()
+        ours, r = dec.result(slot=n), ref.results()
+        # max_active is binding on this graph (thousands of tokens per frame), where Kaldi's own pruning depends on hash order
+        # (DESIGN.md, decode parity note), and the vocabulary is full of homophones with near-equal scores at the n-best cut:
+        # the 1-best and the scores of the shared hypotheses must agree, the two n-best sets must overlap almost entirely
+        byref = {x[2]: x for x in r}
+        byours = {x.sentence: x for x in ours}
+        shared = [x for x in ours if x.sentence in byref]
+        info = (ours[0], r[0], len(shared), len(ours), len(r))
+        if max_active >= 7000:
+            assert ours[0].sentence == r[0][2], info
+        else:       # heavily binding: either decoder's best hypothesis must at least be a hypothesis of the other, at the same score
+            assert ours[0].sentence in byref and r[0][2] in byours, info
+        assert len(shared) >= 0.8 * max(len(ours), len(r)), info
+        for x in shared:
+            assert abs(x.ac_score - byref[x.sentence][0]) < 1e-3 * max(1.0, abs(x.ac_score))
+            assert abs(x.lm_score - byref[x.sentence][1]) < 1e-3 * max(1.0, abs(x.lm_score))
