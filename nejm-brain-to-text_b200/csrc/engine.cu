@@ -365,13 +365,6 @@ extern "C" int b2t_refresh_weights(b2t_engine* e, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------ plans
-static int make_2d(CUtensorMap* tm, const void* p, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows) {
-  const uint64_t dims[4] = {inner, rows, 1, 1};
-  const uint64_t str[3] = {ld, 8, 8};
-  const uint32_t box[4] = {64, box_rows, 1, 1};
-  return make_tmap_bf16_4d(tm, p, dims, str, box);
-}
-
 static int build_plans(b2t_engine* e) {
   e->poll_delay = env_int("B2T_POLL_DELAY", 700);
   e->poll_delay_b = env_int("B2T_POLL_DELAY_BWD", 300);

@@ -1,0 +1,118 @@
+"""ARPA + lexicon -> TLG compiler (nejm-brain-to-text_b200/graph_compiler.py) checked with the decoder oracle: the best path
+through the compiled graph for a cleanly rendered word sequence is that sequence, and its graph cost equals the back-off
+n-gram cost of the sentence computed by an independent scorer plus the optional-silence costs."""
+import importlib.util
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import decoder_util as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import make_toy_tlg as TLG  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("graph_compiler", os.path.join(ROOT, "nejm-brain-to-text_b200", "graph_compiler.py"))
+GC = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(GC)
+
+ARPA = """\\data\\
+ngram 1=7
+ngram 2=8
+ngram 3=4
+
+\\1-grams:
+-1.2 </s>
+-99 <s> -0.4
+-0.9 alpha -0.3
+-0.8 beta -0.25
+-1.1 gamma -0.2
+-1.3 delta
+-1.0 beater -0.1
+
+\\2-grams:
+-0.5 <s> alpha -0.2
+-0.7 <s> beta
+-0.4 alpha beta -0.15
+-0.9 alpha gamma
+-0.6 beta gamma -0.1
+-0.3 gamma </s>
+-0.8 beta </s>
+-0.5 beater alpha
+
+\\3-grams:
+-0.2 <s> alpha beta
+-0.35 alpha beta gamma
+-0.15 beta gamma </s>
+-0.6 alpha beta </s>
+
+\\end\\
+"""
+PHONES = [f"P{i}" for i in range(39)]
+LEXICON = {"alpha": ["P0 P1 P2"], "beta": ["P3 P4"], "gamma": ["P5 P6 P7 P8"], "delta": ["P9 P9 P10"], "beater": ["P3 P4 P11"]}
+
+
+@pytest.fixture(scope="module")
+def compiled(tmp_path_factory):
+    d = tmp_path_factory.mktemp("gc")
+    arpa, lex = str(d / "lm.arpa"), str(d / "lexicon.txt")
+    open(arpa, "w").write(ARPA)
+    with open(lex, "w") as f:
+        for w, prons in LEXICON.items():
+            for pr in prons:
+                f.write(f"{w} {pr}\n")
+    fst, words = str(d / "TLG.fst"), str(d / "words.txt")
+    info = GC.compile_to_files(arpa, lex, PHONES, fst, words)
+    order, grams = GC.parse_arpa(arpa)
+    return fst, words, info, GC.NgramLM(order, grams)
+
+
+def test_scorer_backoff():
+    order, grams = 3, {("a",): (-1.0, -0.5), ("b",): (-2.0, 0.0), ("a", "b"): (-0.3, 0.0)}
+    lm = GC.NgramLM(order, grams)
+    assert abs(lm.cost(("a",), "b") - 0.3 * GC.LN10) < 1e-9
+    assert abs(lm.cost(("b",), "a") - (1.0 + 0.0) * GC.LN10) < 1e-9          # back-off weight of "b" is 0
+    assert abs(lm.cost(("x", "a"), "a") - (0.5 + 1.0) * GC.LN10) < 1e-9      # bow(a) + P(a)
+
+
+@pytest.mark.parametrize("sentence", [["alpha", "beta", "gamma"], ["beta", "gamma"], ["alpha", "gamma"], ["delta", "alpha", "beta"],
+                                      ["beater", "alpha", "beta"], ["gamma", "delta", "delta"]])
+def test_best_path_cost_equals_ngram_cost(compiled, sentence):
+    fst, words, info, lm = compiled
+    assert info["order"] == 3 and info["n_words"] == 5
+    ids = {p: 3 + i for i, p in enumerate(PHONES)}
+    prons = [[ids[p] for p in LEXICON[w][0].split()] for w in sentence]
+    logits = TLG.render_logits(prons, T=90, seed=1, peak=12.0, noise=0.1)
+    dec = D.OracleDecoder(fst, words, 7000, 200, 30.0, 10.0, 1.0, 1.0, 0.0, 5)
+    dec.decode_logits(logits, np.zeros_like(logits), 0.0)
+    dec.finish()
+    res = dec.results()
+    assert res and res[0][2].split() == sentence, res[:2]
+    want = lm.sentence_cost(sentence) + (len(sentence) + 1) * math.log(2.0)      # optional silence: ln 2 at the start and after each word
+    assert abs(-res[0][1] - want) < 1e-3 * max(1.0, want), (-res[0][1], want)
+
+
+@pytest.mark.gpu
+def test_compiled_graph_gpu_vs_oracle(compiled, pkg):
+    import b2t_pkg
+    LM = b2t_pkg.submodule("lm_decoder")
+    fst, words, info, lm = compiled
+    ids = {p: 3 + i for i, p in enumerate(PHONES)}
+    opts = (7000, 200, 17.0, 8.0, 0.6, 1.0, 0.0, 20)
+    dec = LM.BrainSpeechDecoder(LM.DecodeResource(fst, "", "", words, ""), LM.DecodeOptions(*opts), max_frames=128)
+    for k, sentence in enumerate((["alpha", "beta", "gamma"], ["beater", "alpha"], ["delta", "gamma"])):
+        prons = [[ids[p] for p in LEXICON[w][0].split()] for w in sentence]
+        logits = TLG.render_logits(prons, T=90, seed=3 + k, peak=7.0, noise=1.0)
+        ref = D.OracleDecoder(fst, words, *opts)
+        ref.decode_logits(logits, np.zeros_like(logits), math.log(3.0)); ref.finish()
+        dec.Reset()
+        LM.DecodeNumpy(dec, logits, np.zeros_like(logits), math.log(3.0))
+        dec.FinishDecoding()
+        ours, r = dec.result(), ref.results()
+        assert [x.sentence for x in ours][:1] == [x[2] for x in r][:1]
+        assert {x.sentence for x in ours} == {x[2] for x in r}
+        byref = {x[2]: x for x in r}
+        assert all(abs(x.lm_score - byref[x.sentence][1]) < 1e-3 * max(1.0, abs(x.lm_score)) for x in ours)

@@ -110,6 +110,50 @@ def main():
             kms = dec.stats(slot=0)["kernel_ms"]
             out.append(f"| {ma} | {dt * 1e3:.1f} | {64 / dt:.0f} | {kms:.1f} | {kms / (dt * 1e3):.2f} |")
             del dec
+    # ---- synthetic 3-gram / 5-gram graphs compiled by nejm-brain-to-text_b200/graph_compiler.py (configs[4]: width sweep with n-gram LMs)
+    if not only or "lm" in only:
+        import importlib.util
+        import make_synth_lm as SL
+        spec = importlib.util.spec_from_file_location("graph_compiler", os.path.join(ROOT, "nejm-brain-to-text_b200", "graph_compiler.py"))
+        GC = importlib.util.module_from_spec(spec); spec.loader.exec_module(GC)
+        out.append("\n## Width sweep on synthetic n-gram graphs (1000-word vocabulary, 20 000-sentence corpus; ARPA -> TLG by graph_compiler.py), "
+                   "8 utterances sampled from the corpus, shipped decoder settings, n-best 100\n")
+        out.append("| LM | graph states / arcs | max_active | ours: ms per trial | oracle: ms per trial | speed-up | 1-best agreement | WER ours | WER oracle |")
+        out.append("|---|---|---:|---:|---:|---:|---:|---:|---:|")
+        for order in (3, 5):
+            dd = os.path.join(d, f"lm{order}")
+            li = SL.build(dd, order=order, n_words=1000, n_sent=20000, seed=order)
+            gfst, gwords = os.path.join(dd, "TLG.fst"), os.path.join(dd, "words.txt")
+            gi = GC.compile_to_files(li["arpa"], li["lexicon"], li["phones"], gfst, gwords)
+            widx = {w: i for i, w in enumerate(li["words"])}
+            rs = np.random.RandomState(11)
+            sents = [s[1:-1] for s in li["corpus"] if 2 <= len(s) - 2 <= 4]
+            sents = [sents[i] for i in rs.choice(len(sents), size=8, replace=False)]
+            ub = np.stack([TLG.render_logits([li["prons"][widx[w]] for w in s], T=T, seed=700 + n, noise=1.0) for n, s in enumerate(sents)])
+            for ma in (10, 100, 500, 7000):
+                opts = (ma, min(200, ma), 17.0, 8.0, 0.325, 1.0, 0.0, 100)
+                dec = LM.BrainSpeechDecoder(LM.DecodeResource(gfst, "", "", gwords, ""), LM.DecodeOptions(*opts), max_frames=128, max_slots=8)
+                dec.DecodeBatch(ub[:2], blank_penalty=bp)
+                t0 = time.perf_counter()
+                dec.DecodeBatch(ub, blank_penalty=bp)
+                dt = (time.perf_counter() - t0) / 8
+                ours = [dec.result(slot=n) for n in range(8)]
+                ref = D.OracleDecoder(gfst, gwords, *opts)
+                t1 = time.perf_counter()
+                refs = []
+                for n in range(8):
+                    ref.reset(); ref.decode_logits(ub[n], np.zeros_like(ub[n]), bp); ref.finish()
+                    refs.append(ref.results())
+                dto = (time.perf_counter() - t1) / 8
+                agree = sum(1 for a, b in zip(ours, refs) if (a[0].sentence if a else "") == (b[0][2] if b else ""))
+                def werl(hyps):
+                    e = l = 0
+                    for n, h in enumerate(hyps):
+                        de, dl = wer(sents[n], h.split()); e += de; l += dl
+                    return e / max(l, 1)
+                out.append(f"| {order}-gram | {gi['n_states']} / {gi['n_arcs']} | {ma} | {dt * 1e3:.2f} | {dto * 1e3:.2f} | {dto / dt:.1f}x | {agree}/8 | "
+                           f"{werl([a[0].sentence if a else '' for a in ours]):.3f} | {werl([b[0][2] if b else '' for b in refs]):.3f} |")
+                del dec
     # ---- prefix beam
     out.append(f"\n## LM-free CTC prefix beam search, {Nutt} utterances x {T} frames per call (log-softmax of the same logits)\n")
     out.append("| first_beam x second_beam | ours: ms per batch | ours: ms per trial | oracle (1 CPU thread): ms per trial | identical hypothesis lists |")
