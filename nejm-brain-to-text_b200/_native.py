@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2t_b200.so")
+LIB_PATH = os.environ.get("B2T_LIB_PATH") or os.path.join(_HERE, "libb2t_b200.so")     # B2T_LIB_PATH: A/B builds of the same ABI
 
 
 class B2TError(RuntimeError):

@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
     "-DB2T_EXPORTS",
-]
+] + os.environ.get("B2T_NVCC_EXTRA", "").split()       # e.g. B2T_NVCC_EXTRA="-DB2T_FWD_POLL_GROUP=6" for A/B builds
 
 
 def _digest():

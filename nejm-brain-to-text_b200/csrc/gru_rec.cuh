@@ -85,6 +85,9 @@ template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile(
 constexpr uint32_t REC_SENTINEL = 0xFFFFFFFFu;       // "not written yet" marker of an hseq word (two bf16)
 constexpr uint32_t REC_MAX_SPINS = 1u << 24;           // bounded polling: a lost peer traps instead of hanging the GPU
 
+#ifndef B2T_FWD_POLL_GROUP
+#define B2T_FWD_POLL_GROUP 6      // chunks of h_{t-1} polled together by the forward loaders (16 = all of them in one round); measured on B200: 6 -> 4.24 ms per step, 16 -> 4.32, 4 -> 4.29, 3 -> 4.35
+#endif
 #ifndef B2T_POLL_RELAXED
 #define B2T_POLL_RELAXED 0
 #endif
@@ -265,12 +268,32 @@ gru_rec_fwd_kernel(const RecFwdParams p) {
       }
       const uint8_t* g = reinterpret_cast<const uint8_t*>(p.hseq + ((size_t)t * p.Bpad + b0 + row) * p.H) + seg * 16;   // slot t = h_{t-1}
       uint8_t* sdst = sH + (size_t)buf * KC * CHUNK_BYTES + soff;
-      if constexpr (PC >= 16) {                              // all chunks (KC <= 16) in one group: no group loop (it costs registers)
+      if constexpr (PC >= 16) {
+#if B2T_FWD_POLL_GROUP >= 16
+        // all chunks (KC <= 16) in one group: no group loop (a run-time loop around the register array costs spills)
         uint64_t* bars = &bar_h[buf * 16];
         poll_and_stage<PC, UPT>(KC, active, [&](int c) { return g + c * 128; }, g_unit, sdst, CHUNK_BYTES, ROWS_PER_PASS * 128, [&](int c) {
           if (lane == 0) mbar_arrive(&bars[c]);
           if (lt == 0 && c == 0) REC_TRACE(t, 0);          // first chunk of h_{t-1} staged
         });
+#else
+        // groups of B2T_FWD_POLL_GROUP chunks, unrolled at compile time: a polling round moves fewer bytes, so the first
+        // chunks reach the MMA (the step's critical resource) earlier
+        constexpr int PG = B2T_FWD_POLL_GROUP;
+#pragma unroll
+        for (int gi = 0; gi < (16 + PG - 1) / PG; ++gi) {
+          const int c0 = gi * PG;
+          if (c0 < KC) {
+            uint64_t* bars = &bar_h[buf * 16 + c0];
+            const uint8_t* gg = g + c0 * 128;
+            poll_and_stage<PG, UPT>(KC - c0 < PG ? KC - c0 : PG, active, [&](int c) { return gg + c * 128; }, g_unit,
+                                    sdst + (size_t)c0 * CHUNK_BYTES, CHUNK_BYTES, ROWS_PER_PASS * 128, [&](int c) {
+                                      if (lane == 0) mbar_arrive(&bars[c]);
+                                      if (lt == 0 && c0 + c == 0) REC_TRACE(t, 0);
+                                    });
+          }
+        }
+#endif
       } else {
         for (int c0 = 0; c0 < KC; c0 += PC) {                // chunk groups in the order the MMA consumes them
           const uint8_t* gg = g + c0 * 128;
