@@ -116,3 +116,28 @@ def test_compiled_graph_gpu_vs_oracle(compiled, pkg):
         assert {x.sentence for x in ours} == {x[2] for x in r}
         byref = {x[2]: x for x in r}
         assert all(abs(x.lm_score - byref[x.sentence][1]) < 1e-3 * max(1.0, abs(x.lm_score)) for x in ours)
+
+
+def test_unigram_lm_pron_probs_and_missing_words(tmp_path):
+    """A 1-gram LM (the shipped openwebtext graph is one), lexiconp-style pronunciation probabilities, a second pronunciation,
+    and an LM word without a lexicon entry (dropped from the graph)."""
+    arpa = tmp_path / "uni.arpa"
+    arpa.write_text("\\data\\\nngram 1=5\n\n\\1-grams:\n-0.7 </s>\n-99 <s>\n-0.5 red\n-0.9 green\n-1.5 nolex\n\n\\end\\\n")
+    lex = tmp_path / "lexiconp.txt"
+    lex.write_text("red 0.8 P0 P1\nred 0.2 P2 P1 P3\ngreen 1.0 P4 P5 P6\n")
+    fst, words = str(tmp_path / "TLG.fst"), str(tmp_path / "words.txt")
+    info = GC.compile_to_files(str(arpa), str(lex), PHONES, fst, words)
+    assert info["order"] == 1 and info["n_words"] == 2
+    assert "nolex" not in open(words).read()
+    lm = GC.NgramLM(*GC.parse_arpa(str(arpa)))
+    ids = {p: 3 + i for i, p in enumerate(PHONES)}
+    for sentence, prons, pron_cost in ((["red", "green"], [["P0", "P1"], ["P4", "P5", "P6"]], -math.log(0.8)),
+                                       (["green", "red"], [["P4", "P5", "P6"], ["P2", "P1", "P3"]], -math.log(0.2))):
+        logits = TLG.render_logits([[ids[p] for p in pr] for pr in prons], T=70, seed=2, peak=12.0, noise=0.1)
+        dec = D.OracleDecoder(fst, words, 7000, 200, 30.0, 10.0, 1.0, 1.0, 0.0, 3)
+        dec.decode_logits(logits, np.zeros_like(logits), 0.0)
+        dec.finish()
+        res = dec.results()
+        assert res[0][2].split() == sentence
+        want = lm.sentence_cost(sentence) + 3 * math.log(2.0) + pron_cost
+        assert abs(-res[0][1] - want) < 1e-3 * want, (-res[0][1], want)
