@@ -148,6 +148,43 @@ class FusedClipAdamW(torch.optim.Optimizer):
         self._pending_state = None
 
 
+class _DevicePrefetcher:
+    """Iterates a (pinned-memory) batch loader one batch ahead: the host -> device copy of batch i+1 runs on a side stream
+    while step i computes (the reference copies inside the step, rnn_trainer.py:513-519, and its loss.item() every step keeps
+    that copy from overlapping with anything).  Yields the reference's batch dict with the tensors already on the device."""
+
+    def __init__(self, loader, device):
+        self.it, self.device = iter(loader), device
+        self.stream = torch.cuda.Stream(device=device)
+        self.batch = self.event = None
+        self._load()
+
+    def _load(self):
+        try:
+            b = next(self.it)
+        except StopIteration:
+            self.batch = None
+            return
+        with torch.cuda.stream(self.stream):
+            self.batch = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) and k != 'transcriptions' else v) for k, v in b.items()}
+            self.event = torch.cuda.Event()
+            self.event.record(self.stream)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.batch is None:
+            raise StopIteration
+        cur = self.batch
+        torch.cuda.current_stream().wait_event(self.event)
+        for v in cur.values():
+            if torch.is_tensor(v) and v.is_cuda:
+                v.record_stream(torch.cuda.current_stream())          # allocated on the copy stream, consumed on this one
+        self._load()
+        return cur
+
+
 class BrainToTextDecoder_Trainer:
     """
     This class will initialize and train a brain-to-text phoneme decoder
@@ -461,7 +498,7 @@ class BrainToTextDecoder_Trainer:
         early_stopping_val_steps = self.args['early_stopping_val_steps']
         train_start_time = time.time()
         i = -1
-        for i, batch in enumerate(self.train_loader):
+        for i, batch in enumerate(_DevicePrefetcher(self.train_loader, self.device)):
             self.model.train()
             start_time = time.time()
             loss, stats = self._train_step(batch)
