@@ -254,3 +254,32 @@ def test_shipped_1gram_graph_vs_oracle(LM, max_active, n_utt):
         for x in shared:
             assert abs(x.ac_score - byref[x.sentence][0]) < 1e-3 * max(1.0, abs(x.ac_score))
             assert abs(x.lm_score - byref[x.sentence][1]) < 1e-3 * max(1.0, abs(x.lm_score))
+
+
+REF_LOGITS = os.path.join(ROOT, "oracle", "_ref", "test_logits.npy")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LOGITS), reason="test_logits.npy (input fixture of the reference's x86/python/test.py) is staged under oracle/_ref/ by build()")
+def test_prefix_beam_on_reference_logits(LM):
+    """The reference's own handwriting logits [32, 3469, 32] (x86/python/test.py:30-36, columns rearranged as there): long
+    sequences (3 469 frames, prefixes of several hundred tokens) through the prefix beam search, GPU vs oracle."""
+    logits = np.load(REF_LOGITS)
+    logits = logits[:, :, [31] + [26, 27, 30, 29, 28] + list(range(26))]
+    x = logits[:3, :1200].astype(np.float32)
+    lp = x - x.max(-1, keepdims=True)
+    lp = lp - np.log(np.exp(lp).sum(-1, keepdims=True))
+    lens = np.array([1200, 777, 1200], dtype=np.int32)
+    ours = LM.ctc_prefix_beam_search(lp, lens=lens)
+    for n in range(3):
+        ref = D.prefix_search(lp[n, :lens[n]])
+        assert [r[0] for r in ours[n]] == [r[0] for r in ref]
+        assert all(abs(a[1] - b[1]) < 1e-3 * max(1.0, abs(b[1])) and abs(a[2] - b[2]) < 1e-3 * max(1.0, abs(b[2])) for a, b in zip(ours[n], ref))
+        # Viterbi times: the reference keeps the FIRST writer's time vector of a frame when a later writer brings a better Viterbi
+        # score at the same token probability (the cur_token_prob guard, ctc_prefix_beam_search.cc:79-86), and "first" is the
+        # iteration order of its unordered_map.  The oracle iterates like libstdc++ does, the kernel in beam order: hypotheses and
+        # both scores are identical, a token's time can differ by at most its duration (DESIGN.md section 5).
+        for a, b in zip(ours[n], ref):
+            assert len(a[3]) == len(b[3]) == len(a[0])
+            assert all(x <= y for x, y in zip(a[3], a[3][1:]))
+            assert max((abs(x - y) for x, y in zip(a[3], b[3])), default=0) <= 8
+        assert len(ours[n][0][0]) > 20
