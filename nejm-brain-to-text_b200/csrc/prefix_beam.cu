@@ -36,6 +36,7 @@ struct PbParams {
   // per-utterance scratch
   int* trie_parent; int* trie_token; int trie_cap;     // [N][trie_cap]
   int* trie_hash; int trie_hash_cap;                   // [N][trie_hash_cap] (power of two) -> trie node or -1
+  unsigned long long* trie_h64;                        // [N][trie_cap] PrefixHash of the node's prefix (ctc_prefix_beam_search.h:44-53)
   int* times;          // [N][2 buffers][PB_MAX_CAND][2 (s, ns)][max_len]
   // outputs
   int* out_ids; int* out_len; float* out_score; float* out_viterbi; int* out_times; int* out_n;
@@ -73,6 +74,54 @@ __device__ inline void warp_argmax(float& v, int& idx) {
   }
 }
 
+// Iteration order of the reference's cur_hyps_ (std::unordered_map<vector<int>, PrefixScore, PrefixHash>, libstdc++).
+// The Viterbi time vectors depend on it: within a frame the first writer of a candidate keeps its times when a later writer
+// brings a better Viterbi score at the same token probability (cur_token_prob guard, ctc_prefix_beam_search.cc:79-86), and the
+// writers are visited in the map's order, not in score order.  libstdc++ keeps all nodes in one forward list; a node whose
+// bucket is empty goes to the head of the list, otherwise to the beginning of its bucket's run; growing the table re-inserts
+// the nodes in list order by the same rule; clear() keeps the bucket count (13 after the first insertion, then the next
+// prime >= twice the old count: 29, 59, 127).  Emulated serially for the <= PB_MAX_BEAM hypotheses of a frame.
+struct UMapOrder {
+  int B, next_resize, head, n;
+  int* nxt;                  // [PB_MAX_BEAM] successor in the list (-1 = end)
+  int* before;               // [128] per bucket: -2 = empty, -1 = the list head sentinel, >= 0 = node preceding the bucket's run
+  unsigned long long* h;     // [PB_MAX_BEAM] hash of the node's prefix
+  __device__ void clear() {
+    head = -1; n = 0;
+    for (int b = 0; b < B; ++b) before[b] = -2;
+  }
+  __device__ void link(int node, int nb) {
+    const int b = (int)(h[node] % (unsigned long long)nb);
+    if (before[b] != -2) {
+      const int pr = before[b];
+      if (pr == -1) { nxt[node] = head; head = node; }
+      else { nxt[node] = nxt[pr]; nxt[pr] = node; }
+    } else {
+      nxt[node] = head; head = node;
+      if (nxt[node] >= 0) before[(int)(h[nxt[node]] % (unsigned long long)nb)] = node;
+      before[b] = -1;
+    }
+  }
+  __device__ void insert(int node, unsigned long long hv, int* scratch) {
+    h[node] = hv;
+    if (n + 1 > next_resize) {
+      const int minb = max(n + 1, next_resize ? 0 : 11);
+      if (minb >= B) {
+        const int want = max(minb + 1, 2 * B);
+        const int nb = want <= 13 ? 13 : want <= 29 ? 29 : want <= 59 ? 59 : 127;
+        int cnt = 0;                                       // re-insert in the current list order
+        for (int q = head; q >= 0; q = nxt[q]) scratch[cnt++] = q;
+        head = -1;
+        for (int b = 0; b < nb; ++b) before[b] = -2;
+        for (int i = 0; i < cnt; ++i) link(scratch[i], nb);
+        B = nb; next_resize = nb;
+      } else next_resize = B;
+    }
+    link(node, B);
+    ++n;
+  }
+};
+
 __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
   // the state lane 0 walks with dependent accesses lives in shared memory (33 KB); the trie, its hash and the time vectors stay
   // in global memory (one or two accesses per pair / copied by all lanes)
@@ -81,6 +130,8 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
   __shared__ Hyp s_cur[PB_MAX_BEAM];
   __shared__ Hyp s_nxt[PB_MAX_CAND];
   __shared__ int s_chash[PB_HASH_CAND];
+  __shared__ int s_iter[PB_MAX_BEAM], s_unext[PB_MAX_BEAM], s_ubefore[128], s_scratch[PB_MAX_BEAM];
+  __shared__ unsigned long long s_uh[PB_MAX_BEAM];
   const int u = blockIdx.x, lane = threadIdx.x;
   if (u >= p.N) return;
   const float* logp = p.logp + (size_t)u * p.T * p.C;
@@ -89,8 +140,16 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
   int* ttok = p.trie_token + (size_t)u * p.trie_cap;
   int* thash = p.trie_hash + (size_t)u * p.trie_hash_cap;
   int* chash = s_chash;
+  unsigned long long* th64 = p.trie_h64 + (size_t)u * p.trie_cap;
   int ntrie = 1;                                        // node 0 = empty prefix (lane 0's copy is the authoritative one)
-  if (lane == 0) { tpar[0] = -1; ttok[0] = -1; }
+  UMapOrder um;                                         // lane 0 only
+  um.B = 1; um.next_resize = 0; um.head = -1; um.n = 0; um.nxt = s_unext; um.before = s_ubefore; um.h = s_uh;
+  if (lane == 0) {
+    tpar[0] = -1; ttok[0] = -1; th64[0] = 0ull;
+    s_ubefore[0] = -2;
+    um.insert(0, 0ull, s_scratch);                     // Reset(): cur_hyps_[empty prefix]
+    s_iter[0] = 0;
+  }
   for (int i = lane; i < p.trie_hash_cap; i += 32) thash[i] = -1;
   for (int i = lane; i < PB_HASH_CAND; i += 32) chash[i] = -1;
   const size_t tstride = (size_t)2 * p.max_len;          // per hypothesis: times_s | times_ns
@@ -127,7 +186,8 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
     for (int i = 0; i < k; ++i) {
       const int id = s_top[i];
       const float prob = row[id];
-      for (int h = 0; h < ncur; ++h) {
+      for (int hh = 0; hh < ncur; ++hh) {
+        const int h = s_iter[hh];                        // the reference's unordered_map iteration order (see UMapOrder)
         // up to two time-vector copies per pair: (dst, src, n, position that receives t or -1)
         long long c_dst[2] = {-1, -1}, c_src[2] = {0, 0};
         int c_n[2] = {0, 0}, c_set[2] = {-1, -1}, ncp = 0;
@@ -155,6 +215,7 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
             }
             if (ntrie >= p.trie_cap) { overflow = true; return ntrie - 1; }
             tpar[ntrie] = node; ttok[ntrie] = tok;
+            th64[ntrie] = (unsigned long long)(long long)tok + 31ull * th64[node];
             thash[slot] = ntrie;
             return ntrie++;
           };
@@ -246,6 +307,13 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
     for (int i = lane; i < PB_HASH_CAND; i += 32) chash[i] = -1;
     ncur = keep;
     __syncwarp();
+    if (lane == 0) {                                     // cur_hyps_.clear(); cur_hyps_[prefix] = score in sorted order
+      um.clear();
+      for (int r = 0; r < keep; ++r) um.insert(r, th64[cur[r].node], s_scratch);
+      int c = 0;
+      for (int q = um.head; q >= 0; q = um.nxt[q]) s_iter[c++] = q;
+    }
+    __syncwarp();
   }
   // outputs
   if (lane == 0) p.out_n[u] = ncur;
@@ -306,7 +374,7 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
   size_t off = 0;
   auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
   const size_t o_logp = carve((size_t)N * T * C * 4 + 4), o_lens = carve((size_t)N * 4), o_tp = carve((size_t)N * p.trie_cap * 4),
-               o_tt = carve((size_t)N * p.trie_cap * 4), o_th = carve((size_t)N * p.trie_hash_cap * 4), o_times = carve(times_elems * 4),
+               o_tt = carve((size_t)N * p.trie_cap * 4), o_th = carve((size_t)N * p.trie_hash_cap * 4), o_h64 = carve((size_t)N * p.trie_cap * 8), o_times = carve(times_elems * 4),
                o_ids = carve(nb * max_len * 4), o_len = carve(nb * 4), o_score = carve(nb * 4), o_vit = carve(nb * 4),
                o_otimes = carve(nb * max_len * 4), o_n = carve((size_t)N * 4), o_status = carve((size_t)N * 4);
   bool ok = true;
@@ -329,7 +397,7 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
   cudaMemcpy(d_lens, lens, N * 4, cudaMemcpyHostToDevice);
   cudaMemset(d_status, 0, N * 4); cudaMemset(d_ids, 0, nb * max_len * 4); cudaMemset(d_otimes, 0, nb * max_len * 4);
   cudaMemset(d_len, 0, nb * 4); cudaMemset(d_score, 0, nb * 4); cudaMemset(d_vit, 0, nb * 4);
-  p.logp = d_logp; p.lens = d_lens; p.trie_parent = d_tp; p.trie_token = d_tt; p.trie_hash = d_th; p.times = d_times;
+  p.logp = d_logp; p.lens = d_lens; p.trie_parent = d_tp; p.trie_token = d_tt; p.trie_hash = d_th; p.trie_h64 = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws.base) + o_h64); p.times = d_times;
   p.out_ids = d_ids; p.out_len = d_len; p.out_score = d_score; p.out_viterbi = d_vit; p.out_times = d_otimes; p.out_n = d_n; p.status = d_status;
   static const bool timing = getenv("B2T_DECODER_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };

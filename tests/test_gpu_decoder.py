@@ -272,14 +272,16 @@ def test_prefix_beam_on_reference_logits(LM):
     ours = LM.ctc_prefix_beam_search(lp, lens=lens)
     for n in range(3):
         ref = D.prefix_search(lp[n, :lens[n]])
-        assert [r[0] for r in ours[n]] == [r[0] for r in ref]
-        assert all(abs(a[1] - b[1]) < 1e-3 * max(1.0, abs(b[1])) and abs(a[2] - b[2]) < 1e-3 * max(1.0, abs(b[2])) for a, b in zip(ours[n], ref))
-        # Viterbi times: the reference keeps the FIRST writer's time vector of a frame when a later writer brings a better Viterbi
-        # score at the same token probability (the cur_token_prob guard, ctc_prefix_beam_search.cc:79-86), and "first" is the
-        # iteration order of its unordered_map.  The oracle iterates like libstdc++ does, the kernel in beam order: hypotheses and
-        # both scores are identical, a token's time can differ by at most its duration.
-        for a, b in zip(ours[n], ref):
-            assert len(a[3]) == len(b[3]) == len(a[0])
-            assert all(x <= y for x, y in zip(a[3], a[3][1:]))
-            assert max((abs(x - y) for x, y in zip(a[3], b[3])), default=0) <= 8
+        assert len(ours[n]) == len(ref)
+        # The tail of these beams holds several hypotheses with EXACTLY the same score (tokens at the probability floor); which of
+        # them survive the second-beam cut is decided by std::nth_element / std::sort in the reference and by creation order in the
+        # kernel.  Everything strictly above the cut score must agree exactly: hypotheses, scores, Viterbi scores and Viterbi times
+        # (the times depend on the iteration order of the reference's unordered_map, which the kernel reproduces: UMapOrder).
+        cut = ref[-1][1]
+        k = sum(1 for r in ref if r[1] > cut + 1e-6)
+        assert k >= 5
+        assert [r[0] for r in ours[n][:k]] == [r[0] for r in ref[:k]]
+        assert all(abs(a[1] - b[1]) < 1e-3 * max(1.0, abs(b[1])) and abs(a[2] - b[2]) < 1e-3 * max(1.0, abs(b[2])) for a, b in zip(ours[n][:k], ref[:k]))
+        assert [r[3] for r in ours[n][:k]] == [r[3] for r in ref[:k]]
+        assert all(abs(a[1] - cut) < 1e-3 * abs(cut) for a in ours[n][k:])          # the rest are other members of the tie
         assert len(ours[n][0][0]) > 20
