@@ -186,17 +186,21 @@ int b2t_decoder_reset(b2t_decoder* d, int slot);                                
 int b2t_decoder_decode_logits(b2t_decoder* d, int slot, const float* logits, const float* log_priors, int T, int C,
                               float blank_penalty);
 int b2t_decoder_decode_logprobs(b2t_decoder* d, int slot, const float* logp, int T, int C);   /* DecodeNumpyLogProbs */
-int b2t_decoder_finish(b2t_decoder* d, int slot);                                     /* FinishDecoding */
+/* FinishDecoding: final costs, lattice pruning within lattice_beam (on the device), n-best (nbest > 1: top-n distinct word
+ * sequences; nbest == 1: back-pointer best path on the device).  Idempotent: a second call keeps the first call's results. */
+int b2t_decoder_finish(b2t_decoder* d, int slot);
 int b2t_decoder_rescore(b2t_decoder* d, int slot);                                    /* Rescore: not implemented (next row N1) */
 int b2t_decoder_num_results(b2t_decoder* d, int slot);                                /* len(result()) */
 int b2t_decoder_get_result(b2t_decoder* d, int slot, int i, float* ac_score, float* lm_score, char* sentence, int cap);
-/* Batched extension: reset + decode (+ finish) N <= max_slots utterances concurrently; logits host [N][T][C]. */
+/* Batched extension: reset + decode (+ finish) N <= max_slots utterances concurrently (one CTA per utterance for the search and
+ * for the lattice pruning; the host part of finish runs on internal worker threads); logits host [N][T][C]. */
 int b2t_decoder_decode_batch(b2t_decoder* d, const float* logits, const int* lens, int N, int T, int C, float blank_penalty,
                              int finish);
 int b2t_decoder_stats(b2t_decoder* d, int slot, int* frames, long long* tokens, long long* links, double* kernel_ms);
 int b2t_decoder_tokens_per_frame(b2t_decoder* d, int slot, int* out, int cap);
 
-/* LM-free CTC prefix beam search (ctc_prefix_beam_search.cc:44-136), batched over utterances.
+/* LM-free CTC prefix beam search (ctc_prefix_beam_search.cc:44-136), one warp per utterance; first_beam, second_beam <= 64.
+ * Hypotheses are walked in the iteration order of the reference's unordered_map (libstdc++), on which its Viterbi times depend.
  * logp: host [N][T][C] log-probabilities; lens: host [N].  Outputs (host, best first): ids [N][second_beam][max_len],
  * len / score / viterbi [N][second_beam], times [N][second_beam][max_len], n_hyp [N]. */
 const char* b2t_prefix_last_error(void);
