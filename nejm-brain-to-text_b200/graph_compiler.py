@@ -243,6 +243,39 @@ def write_fst(path, start, finals, arcs_by_state):
                 f.write(struct.pack("<iifi", il, ol, w, nx))
 
 
+def write_g_fst(order, grams, word_ids, path):
+    """The n-gram model as the word acceptor `Rescore()` composes lattices with (G.fst / G_no_prune.fst after
+    ReadAndPrepareLmFst: back-off arcs are eps:eps, words on both sides, </s> as final costs).  Words without an id are dropped."""
+    start_h, arcs, backoff, final = build_g(order, grams)
+    ids = {start_h: 0}
+
+    def sid(h):
+        if h not in ids:
+            ids[h] = len(ids)
+        return ids[h]
+
+    todo, out, fin = [start_h], {}, {}
+    while todo:
+        h = todo.pop()
+        i = sid(h)
+        if i in out:
+            continue
+        lst = []
+        for w, c, hn in arcs.get(h, ()):
+            if w in word_ids:
+                lst.append((word_ids[w], word_ids[w], c, sid(hn)))
+                todo.append(hn)
+        if h in backoff:
+            bc, hb = backoff[h]
+            lst.append((0, 0, bc, sid(hb)))
+            todo.append(hb)
+        out[i] = sorted(lst)
+        fin[i] = final.get(h, math.inf)
+    n = len(ids)
+    write_fst(path, 0, [fin.get(i, math.inf) for i in range(n)], [out.get(i, []) for i in range(n)])
+    return {"n_states": n, "n_arcs": sum(len(v) for v in out.values())}
+
+
 def compile_to_files(arpa_path, lexicon_path, phones, out_fst, out_words, sil_prob=0.5):
     """phones: list of phone names in unit order (phones[0] gets label 3).  Writes TLG.fst and words.txt; returns sizes."""
     order, grams = parse_arpa(arpa_path)

@@ -792,6 +792,64 @@ std::string ProcessBlank(const std::string& s) {
   return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// BrainSpeechDecoder::Rescore (brain_speech_decoder.cc:47-101).  The lattice it starts from is CtcWfstBeamSearch::Lattice(),
+// i.e. the DETERMINISED word lattice of FinalizeSearch (ctc_wfst_beam_search.cc:139-142): one path per distinct word sequence W
+// within lattice_beam, weight (g_W, a_W).  LatticeRescore(lat, lm, scale) = scale the graph costs, compose with the LM acceptor,
+// determinise, scale back; with scale = -1 for the LM the graph was built from and +1 for the rescoring LM this gives, per W,
+//     graph' = g_W - c_old(W) + c_new(W),   acoustic' = a_W,
+// where c(W) is the cheapest path of W through the LM FST INCLUDING its final cost.  ReadAndPrepareLmFst
+// (kaldi/fstext/kaldi-fst-io.cc) projects the LM on its output labels, so the back-off arcs (#0 : eps on disk) are epsilon
+// arcs that composition may take at any time; determinisation keeps the cheapest route.  A W the LM does not accept disappears.
+// ShortestPath(lat, result_.size()) then keeps as many entries as the first pass had, ordered by graph' + acoustic'.
+// The reference has no test for this path and OpenFST is not available offline: PARITY UNPINNED.
+struct LmFst {
+  Graph g;                                       // ilabels == olabels after projection on the output side
+  bool Read(const char* path, std::string* err) {
+    if (!ReadFst(path, &g, err)) return false;
+    for (auto& a : g.arcs) a.il = a.ol;          // PROJECT_OUTPUT
+    return true;
+  }
+  void Closure(std::map<int, float>* st) const {  // epsilon (back-off) arcs; back-off chains are acyclic
+    std::vector<int> work;
+    for (auto& kv : *st) work.push_back(kv.first);
+    while (!work.empty()) {
+      const int s = work.back(); work.pop_back();
+      const float c = (*st)[s];
+      for (long long a = g.off[s]; a < g.off[s + 1]; ++a) {
+        const Arc& arc = g.arcs[a];
+        if (arc.il != 0) continue;
+        auto it = st->find(arc.next);
+        const float nc = c + arc.w;
+        if (it == st->end() || nc < it->second) { (*st)[arc.next] = nc; work.push_back(arc.next); }
+      }
+    }
+  }
+  float Cost(const std::vector<int>& words) const {
+    std::map<int, float> cur;
+    cur[g.start] = 0.0f;
+    Closure(&cur);
+    for (int w : words) {
+      std::map<int, float> nxt;
+      for (auto& kv : cur)
+        for (long long a = g.off[kv.first]; a < g.off[kv.first + 1]; ++a) {
+          const Arc& arc = g.arcs[a];
+          if (arc.il != w) continue;
+          auto it = nxt.find(arc.next);
+          const float nc = kv.second + arc.w;
+          if (it == nxt.end() || nc < it->second) nxt[arc.next] = nc;
+        }
+      if (nxt.empty()) return kInf;
+      Closure(&nxt);
+      cur.swap(nxt);
+    }
+    float best = kInf;
+    for (auto& kv : cur)
+      if (g.fin[kv.first] != kInf) best = std::min(best, kv.second + g.fin[kv.first]);
+    return best;
+  }
+};
+
 struct Result { float ac_score, lm_score; std::string sentence; };
 
 // CtcWfstBeamSearch + BrainSpeechDecoder facade
@@ -867,6 +925,23 @@ struct Facade {
       for (const NBestEntry& e : NBest(dec, nbest)) Push(e.words, -e.graph, -e.acoustic);
     }
   }
+  // Rescore(): see the comment above LmFst.  Returns false when an LM is missing.
+  bool Rescore(const LmFst* old_lm, const LmFst* new_lm) {
+    if (!old_lm || !new_lm) return false;
+    const size_t keep = results.size();
+    struct R { std::vector<int> words; float g, a; };
+    std::vector<R> all;
+    for (const NBestEntry& e : NBest(dec, 0x7fffffff)) {           // every distinct word sequence within lattice_beam
+      const float c_old = old_lm->Cost(e.words), c_new = new_lm->Cost(e.words);
+      if (c_old == kInf || c_new == kInf) continue;
+      // graph cost through the two scalings: -( -g + c_old ) then + c_new
+      all.push_back({e.words, -(-e.graph + c_old) + c_new, e.acoustic});
+    }
+    std::stable_sort(all.begin(), all.end(), [](const R& x, const R& y) { return Better(Hyp{x.g, x.a}, Hyp{y.g, y.a}); });
+    results.clear();
+    for (size_t i = 0; i < all.size() && i < keep; ++i) Push(all[i].words, -all[i].g, -all[i].a);
+    return true;
+  }
 };
 
 bool ReadWords(const char* path, std::vector<std::string>* words) {
@@ -928,6 +1003,16 @@ void orc_decode_logits(void* h, const float* logits, const float* log_priors, in
   ((Facade*)h)->Search(lp.data(), T, C);
 }
 void orc_finish(void* h) { ((Facade*)h)->Finish(); }
+// Rescore with the LM the graph was built from (lm_fst_path) and the rescoring LM; returns 0, or -1 on error
+int orc_rescore(void* h, const char* lm_fst_path, const char* rescore_lm_fst_path, char* err, int err_cap) {
+  LmFst a, b;
+  std::string e;
+  if (!a.Read(lm_fst_path, &e) || !b.Read(rescore_lm_fst_path, &e)) {
+    if (err) snprintf(err, err_cap, "%s", e.c_str());
+    return -1;
+  }
+  return ((Facade*)h)->Rescore(&a, &b) ? 0 : -1;
+}
 int orc_num_results(void* h) { return (int)((Facade*)h)->results.size(); }
 int orc_get_result(void* h, int i, float* ac, float* lm, char* buf, int cap) {
   Facade* f = (Facade*)h;

@@ -29,6 +29,7 @@ def oracle_lib():
         lib.orc_tokens_per_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         lib.orc_graph_info.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         lib.orc_prefix_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        lib.orc_rescore.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         lib.orc_prefix_num.argtypes = [C.c_void_p]
         lib.orc_prefix_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_int]
         _lib = lib
@@ -64,6 +65,11 @@ class OracleDecoder:
 
     def finish(self):
         self.lib.orc_finish(self.h)
+
+    def rescore(self, lm_fst, rescore_lm_fst):
+        err = C.create_string_buffer(256)
+        if self.lib.orc_rescore(self.h, lm_fst.encode(), rescore_lm_fst.encode(), err, 256) != 0:
+            raise RuntimeError("rescore: " + err.value.decode())
 
     def results(self):
         out = []

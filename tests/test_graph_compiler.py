@@ -141,3 +141,91 @@ def test_unigram_lm_pron_probs_and_missing_words(tmp_path):
         assert res[0][2].split() == sentence
         want = lm.sentence_cost(sentence) + 3 * math.log(2.0) + pron_cost
         assert abs(-res[0][1] - want) < 1e-3 * want, (-res[0][1], want)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Rescore() restatement of the oracle (brain_speech_decoder.cc:47-101): groundwork for the next row N1.
+ARPA_NEW = ARPA.replace("-0.4 alpha beta -0.15", "-1.4 alpha beta -0.15").replace("-0.9 alpha gamma", "-0.1 alpha gamma") \
+               .replace("-0.35 alpha beta gamma", "-1.9 alpha beta gamma").replace("-1.3 delta", "-0.6 delta")
+
+
+def _fst_min_cost(order, grams, words):
+    """Independent checker: cheapest path of `words` through the back-off acceptor, epsilon (back-off) arcs free to take at any
+    time, final cost included -- what composition + determinisation of a one-path lattice with G yields."""
+    start, arcs, backoff, final = GC.build_g(order, grams)
+
+    def closure(st):
+        work = list(st)
+        while work:
+            h = work.pop()
+            if h in backoff:
+                c, hb = backoff[h]
+                if st[h] + c < st.get(hb, math.inf):
+                    st[hb] = st[h] + c
+                    work.append(hb)
+        return st
+
+    cur = closure({start: 0.0})
+    for w in words:
+        nxt = {}
+        for h, c in cur.items():
+            for ww, cost, hn in arcs.get(h, ()):
+                if ww == w and c + cost < nxt.get(hn, math.inf):
+                    nxt[hn] = c + cost
+        if not nxt:
+            return math.inf
+        cur = closure(nxt)
+    return min((c + final[h] for h, c in cur.items() if h in final), default=math.inf)
+
+
+def test_rescore_restatement(compiled, tmp_path):
+    fst, words, info, lm = compiled
+    order, grams_old = GC.parse_arpa(os.path.join(os.path.dirname(fst), "lm.arpa"))
+    arpa_new = tmp_path / "new.arpa"
+    arpa_new.write_text(ARPA_NEW)
+    _, grams_new = GC.parse_arpa(str(arpa_new))
+    word_ids = {}
+    for line in open(words):
+        w, i = line.split()
+        if int(i) > 0:
+            word_ids[w] = int(i)
+    g_old, g_new = str(tmp_path / "G.fst"), str(tmp_path / "G_new.fst")
+    GC.write_g_fst(order, grams_old, word_ids, g_old)
+    GC.write_g_fst(order, grams_new, word_ids, g_new)
+    ids = {p: 3 + i for i, p in enumerate(PHONES)}
+    sentence = ["alpha", "beta", "gamma"]
+    logits = TLG.render_logits([[ids[p] for p in LEXICON[w][0].split()] for w in sentence], T=90, seed=5, peak=5.0, noise=1.2)
+    dec = D.OracleDecoder(fst, words, 7000, 200, 20.0, 8.0, 0.5, 1.0, 0.0, 50)
+    dec.decode_logits(logits, np.zeros_like(logits), 0.0)
+    dec.finish()
+    first = dec.results()
+    assert len(first) >= 5 and first[0][2].split() == sentence
+    # (1) rescoring with the LM the graph was built from changes nothing but float noise
+    dec.rescore(g_old, g_old)
+    same = dec.results()
+    assert [r[2] for r in same] == [r[2] for r in first]
+    assert all(abs(a[1] - b[1]) < 1e-4 * max(1.0, abs(b[1])) and a[0] == b[0] for a, b in zip(same, first))
+    # (2) new LM: graph' = g - c_old(W) + c_new(W) for every first-pass W, re-ranked by graph' + acoustic
+    dec2 = D.OracleDecoder(fst, words, 7000, 200, 20.0, 8.0, 0.5, 1.0, 0.0, 10 ** 6)      # all distinct sequences within the lattice beam
+    dec2.decode_logits(logits, np.zeros_like(logits), 0.0)
+    dec2.finish()
+    every = dec2.results()
+    expect = []
+    for ac, lmv, sent in every:
+        ws = sent.split()
+        c_old, c_new = _fst_min_cost(order, grams_old, ws), _fst_min_cost(order, grams_new, ws)
+        if math.isfinite(c_old) and math.isfinite(c_new):
+            g = -lmv - c_old + c_new
+            expect.append((g + (-ac * 0.5), g, ac, sent))                     # total cost with the acoustic cost unscaled (ac = -a / acoustic_scale)
+    expect.sort(key=lambda e: (e[0], e[1]))
+    dec = D.OracleDecoder(fst, words, 7000, 200, 20.0, 8.0, 0.5, 1.0, 0.0, 50)    # a fresh first pass (Rescore follows FinishDecoding once)
+    dec.decode_logits(logits, np.zeros_like(logits), 0.0)
+    dec.finish()
+    n_first = len(dec.results())
+    dec.rescore(g_old, g_new)
+    got = dec.results()
+    assert len(got) == min(n_first, len(expect))
+    assert [r[2] for r in got] == [e[3] for e in expect[:len(got)]]
+    for r, e in zip(got, expect):
+        assert abs(-r[1] - e[1]) < 1e-3 * max(1.0, abs(e[1])) and abs(r[0] - e[2]) < 1e-4 * max(1.0, abs(e[2]))
+    assert [r[2] for r in got] != [r[2] for r in first[:len(got)]]            # the new LM really re-ranks this example
