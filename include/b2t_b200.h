@@ -189,7 +189,13 @@ int b2t_decoder_decode_logprobs(b2t_decoder* d, int slot, const float* logp, int
 /* FinishDecoding: final costs, lattice pruning within lattice_beam (on the device), n-best (nbest > 1: top-n distinct word
  * sequences; nbest == 1: back-pointer best path on the device).  Idempotent: a second call keeps the first call's results. */
 int b2t_decoder_finish(b2t_decoder* d, int slot);
-int b2t_decoder_rescore(b2t_decoder* d, int slot);                                    /* Rescore: not implemented (next row N1) */
+int b2t_decoder_rescore(b2t_decoder* d, int slot);                                    /* Rescore: not wired yet (next row N1), see below */
+/* Host core of Rescore() (brain_speech_decoder.cc:47-101), no GPU involved: n word sequences (ids concatenated in `words`,
+ * lengths in `lens`) with first-pass (graph, acoustic) costs are re-scored as graph' = graph - c_old + c_new, where c is the
+ * cheapest path through the LM acceptor (OpenFST file; back-off arcs taken as epsilons, final cost included), and ordered by
+ * graph' + acoustic; at most `keep` entries are written: order_out[i] = index of the i-th best input, graph_out[i] = graph'. */
+int b2t_lm_rescore_sequences(const char* lm_fst_path, const char* rescore_lm_fst_path, int n, const int* words, const int* lens,
+                             const float* graph, const float* acoustic, int keep, int* order_out, float* graph_out);
 int b2t_decoder_num_results(b2t_decoder* d, int slot);                                /* len(result()) */
 int b2t_decoder_get_result(b2t_decoder* d, int slot, int i, float* ac_score, float* lm_score, char* sentence, int cap);
 /* Batched extension: reset + decode (+ finish) N <= max_slots utterances concurrently (one CTA per utterance for the search and

@@ -1382,6 +1382,60 @@ int ensure_C(b2t_decoder* d, int C) {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ C ABI
+namespace {
+// ---- lattice LM rescoring, host core (brain_speech_decoder.cc:47-101).  FinalizeSearch leaves the
+// determinised word lattice: one path per distinct word sequence W within lattice_beam.  The two LatticeRescore passes
+// (LM the graph was built from with scale -1, rescoring LM with scale +1) then reduce to graph'(W) = g_W - c_old(W) + c_new(W),
+// acoustic' = a_W, where c(W) is the cheapest path of W through the LM acceptor: back-off arcs are epsilons after
+// ReadAndPrepareLmFst (projection on the output labels), the final cost counts, a W the LM rejects disappears.
+struct LmAcceptor {
+  HostGraph g;
+  int load(const char* path) {
+    if (load_fst(path, &g)) return B2T_ERR_ARG;
+    for (DArc& a : g.arcs) a.il = a.ol;              // PROJECT_OUTPUT
+    return 0;
+  }
+  void closure(std::map<int, float>* st) const {
+    std::vector<int> work;
+    for (auto& kv : *st) work.push_back(kv.first);
+    while (!work.empty()) {
+      const int s = work.back(); work.pop_back();
+      const float c = (*st)[s];
+      for (long long a = g.off[s]; a < g.off[s + 1]; ++a) {
+        const DArc& arc = g.arcs[a];
+        if (arc.il != 0) continue;
+        const float nc = c + arc.w;
+        auto it = st->find(arc.next);
+        if (it == st->end() || nc < it->second) { (*st)[arc.next] = nc; work.push_back(arc.next); }
+      }
+    }
+  }
+  float cost(const int* w, int n) const {
+    std::map<int, float> cur;
+    cur[g.start] = 0.0f;
+    closure(&cur);
+    for (int i = 0; i < n; ++i) {
+      std::map<int, float> nxt;
+      for (auto& kv : cur)
+        for (long long a = g.off[kv.first]; a < g.off[kv.first + 1]; ++a) {
+          const DArc& arc = g.arcs[a];
+          if (arc.il != w[i]) continue;
+          const float nc = kv.second + arc.w;
+          auto it = nxt.find(arc.next);
+          if (it == nxt.end() || nc < it->second) nxt[arc.next] = nc;
+        }
+      if (nxt.empty()) return INFINITY;
+      closure(&nxt);
+      cur.swap(nxt);
+    }
+    float best = INFINITY;
+    for (auto& kv : cur)
+      if (g.fin[kv.first] != INFINITY) best = std::min(best, kv.second + g.fin[kv.first]);
+    return best;
+  }
+};
+}  // namespace
+
 extern "C" {
 
 const char* b2t_decoder_last_error(void) { return g_derr; }
@@ -1483,7 +1537,36 @@ int b2t_decoder_finish(b2t_decoder* d, int slot) {
 
 int b2t_decoder_rescore(b2t_decoder* d, int slot) {
   (void)d; (void)slot;
-  return dfail(B2T_ERR_UNSUPPORTED, "Rescore() (lattice LM rescoring with G.fst / G_no_prune.fst) is the 'next' row N1 and is not implemented yet");
+  return dfail(B2T_ERR_UNSUPPORTED, "Rescore() is not wired into the decoder yet (next row N1); its host core is b2t_lm_rescore_sequences");
+}
+
+// Host core of Rescore(), usable on its own (no GPU involved): n word sequences (ids concatenated in `words`, lengths in `lens`)
+// with their first-pass (graph, acoustic) costs are re-scored as graph' = graph - c_old + c_new and ordered by graph' + acoustic
+// (then by smaller graph', LatticeWeight Compare); at most `keep` survive.  order_out[i] = index of the i-th best input sequence,
+// graph_out[i] its new graph cost.  Returns the number of entries written, or a negative error code.
+int b2t_lm_rescore_sequences(const char* lm_fst_path, const char* rescore_lm_fst_path, int n, const int* words, const int* lens,
+                             const float* graph, const float* acoustic, int keep, int* order_out, float* graph_out) {
+  if (!lm_fst_path || !rescore_lm_fst_path || n < 0 || (n > 0 && (!words || !lens || !graph || !acoustic)) || !order_out || !graph_out)
+    return dfail(B2T_ERR_ARG, "bad arguments");
+  LmAcceptor lm_old, lm_new;
+  if (lm_old.load(lm_fst_path) || lm_new.load(rescore_lm_fst_path)) return B2T_ERR_ARG;
+  struct R { int idx; float g, a; };
+  std::vector<R> all;
+  size_t pos = 0;
+  for (int i = 0; i < n; ++i) {
+    const float c_old = lm_old.cost(words + pos, lens[i]), c_new = lm_new.cost(words + pos, lens[i]);
+    pos += (size_t)lens[i];
+    if (c_old == INFINITY || c_new == INFINITY) continue;
+    all.push_back({i, -(-graph[i] + c_old) + c_new, acoustic[i]});
+  }
+  std::stable_sort(all.begin(), all.end(), [](const R& x, const R& y) {
+    const float fx = x.g + x.a, fy = y.g + y.a;
+    if (fx != fy) return fx < fy;
+    return x.g < y.g;
+  });
+  int m = 0;
+  for (; m < (int)all.size() && m < keep; ++m) { order_out[m] = all[m].idx; graph_out[m] = all[m].g; }
+  return m;
 }
 
 int b2t_decoder_num_results(b2t_decoder* d, int slot) {

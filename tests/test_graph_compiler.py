@@ -229,3 +229,52 @@ def test_rescore_restatement(compiled, tmp_path):
     for r, e in zip(got, expect):
         assert abs(-r[1] - e[1]) < 1e-3 * max(1.0, abs(e[1])) and abs(r[0] - e[2]) < 1e-4 * max(1.0, abs(e[2]))
     assert [r[2] for r in got] != [r[2] for r in first[:len(got)]]            # the new LM really re-ranks this example
+
+
+def test_product_rescore_core_matches_oracle(compiled, tmp_path, pkg):
+    """b2t_lm_rescore_sequences (host core of Rescore() in the product library, no GPU involved) against the oracle's Rescore()
+    on the same first-pass sequences and the same LM acceptors."""
+    import ctypes as C
+    fst, words, info, lm = compiled
+    order, grams_old = GC.parse_arpa(os.path.join(os.path.dirname(fst), "lm.arpa"))
+    arpa_new = tmp_path / "new.arpa"
+    arpa_new.write_text(ARPA_NEW)
+    _, grams_new = GC.parse_arpa(str(arpa_new))
+    word_ids = {}
+    for line in open(words):
+        w, i = line.split()
+        if int(i) > 0:
+            word_ids[w.lower()] = int(i)
+    g_old, g_new = str(tmp_path / "G.fst"), str(tmp_path / "G_new.fst")
+    GC.write_g_fst(order, grams_old, {w: i for w, i in word_ids.items()}, g_old)
+    GC.write_g_fst(order, grams_new, {w: i for w, i in word_ids.items()}, g_new)
+    ids = {p: 3 + i for i, p in enumerate(PHONES)}
+    sentence = ["beater", "alpha", "beta"]
+    logits = TLG.render_logits([[ids[p] for p in LEXICON[w][0].split()] for w in sentence], T=90, seed=8, peak=5.0, noise=1.2)
+    scale = 0.5
+
+    def first_pass(nbest):
+        d = D.OracleDecoder(fst, words, 7000, 200, 20.0, 8.0, scale, 1.0, 0.0, nbest)
+        d.decode_logits(logits, np.zeros_like(logits), 0.0)
+        d.finish()
+        return d
+
+    every = first_pass(10 ** 6).results()                              # all distinct sequences within the lattice beam
+    ref = first_pass(30)
+    keep = len(ref.results())
+    ref.rescore(g_old, g_new)
+    want = ref.results()
+    seqs = [[word_ids[w] for w in s.split()] for _, _, s in every]
+    flat = np.array([i for s in seqs for i in s], dtype=np.int32)
+    lens = np.array([len(s) for s in seqs], dtype=np.int32)
+    graph = np.array([-lmv for _, lmv, _ in every], dtype=np.float32)
+    acoustic = np.array([-ac * scale for ac, _, _ in every], dtype=np.float32)
+    order_out = np.zeros(keep, dtype=np.int32); graph_out = np.zeros(keep, dtype=np.float32)
+    lib = C.CDLL(os.path.join(ROOT, "nejm-brain-to-text_b200", "libb2t_b200.so"))
+    lib.b2t_lm_rescore_sequences.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    m = lib.b2t_lm_rescore_sequences(g_old.encode(), g_new.encode(), len(seqs), flat.ctypes.data, lens.ctypes.data, graph.ctypes.data,
+                                     acoustic.ctypes.data, keep, order_out.ctypes.data, graph_out.ctypes.data)
+    assert m == len(want) > 5
+    assert [every[order_out[i]][2] for i in range(m)] == [r[2] for r in want]
+    assert all(abs(-graph_out[i] - want[i][1]) < 1e-4 * max(1.0, abs(want[i][1])) for i in range(m))
+    assert lib.b2t_lm_rescore_sequences(b"/nonexistent.fst", g_new.encode(), 0, None, None, None, None, 1, order_out.ctypes.data, graph_out.ctypes.data) < 0
