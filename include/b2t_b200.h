@@ -152,6 +152,12 @@ int b2t_debug_set_trace(b2t_engine* e, long long* device_buf);
 int b2t_debug_timeline(int enable);
 int b2t_debug_dump_timeline(char* buf, int cap);
 
+/* Test hook: device pointer (and element count) of an internal activation buffer of the last forward/backward: "xs", "xd",
+ * "dpre" (bf16 [Bpad][T][neural_dim], Bpad = batch rounded up to 16), per layer "hseq" (bf16 [(T'+1)][Bpad][H], slot 0 = initial
+ * state), "hdrop" (bf16 [T'][Bpad][H], the dropped copy read by the next layer), "gx" (fp32 [T'][Bpad][3H]), "dGx", "dGh"
+ * (bf16 [T'][Bpad][3H]), "dY" (fp32 [T'][Bpad][H]), "logits" (fp32 [T'][Bpad][64]).  Used by the dropout-mask parity tests. */
+int b2t_debug_buffer(b2t_engine* e, const char* name, int layer, void** ptr, long long* elems);
+
 /* Number of kernels this library has launched on behalf of the calling process (bench accounting). */
 long long b2t_launch_count(void);
 

@@ -66,6 +66,7 @@ def _load():
         "b2t_optimizer_step": (ci, [vp, C.POINTER(AdamWArgs), vp, vp]),
         "b2t_step_counters": (vp, [vp]),
         "b2t_debug_set_trace": (ci, [vp, vp]),
+        "b2t_debug_buffer": (ci, [vp, C.c_char_p, ci, C.POINTER(vp), C.POINTER(ll)]),
         "b2t_debug_timeline": (ci, [ci]),
         "b2t_debug_dump_timeline": (ci, [C.c_char_p, ci]),
         "b2t_greedy_edit": (ci, [vp, vp, ci, vp, vp, vp, vp, vp, vp]),

@@ -356,6 +356,32 @@ extern "C" int b2t_debug_set_trace(b2t_engine* e, long long* buf) {
   return 0;
 }
 
+// Test hook: device pointer of an internal activation buffer of the last forward/backward (layouts in DESIGN.md section 2).
+extern "C" int b2t_debug_buffer(b2t_engine* e, const char* name, int layer, void** ptr, long long* elems) {
+  if (!e || !name || !ptr) return fail(B2T_ERR_ARG, "null argument");
+  if (layer < 0 || layer >= e->L) return fail(B2T_ERR_ARG, "layer out of range");
+  const std::string n(name);
+  const LayerBuf& b = e->lay[layer];
+  const long long Bp = e->Bpad, M = e->M, H = e->H;
+  void* p = nullptr;
+  long long cnt = 0;
+  if (n == "xs") { p = e->xs; cnt = Bp * e->T_in * e->D; }
+  else if (n == "xd") { p = e->xd; cnt = Bp * e->T_in * e->D; }
+  else if (n == "dpre") { p = e->dpre; cnt = Bp * e->T_in * e->D; }
+  else if (n == "hseq") { p = b.hseq; cnt = (M + Bp) * H; }
+  else if (n == "hdrop") { p = b.hdrop; cnt = M * H; }
+  else if (n == "gx") { p = b.gx; cnt = M * 3 * H; }
+  else if (n == "dGx") { p = b.dGx; cnt = M * 3 * H; }
+  else if (n == "dGh") { p = b.dGh; cnt = M * 3 * H; }
+  else if (n == "dY") { p = b.dY; cnt = M * H; }
+  else if (n == "logits") { p = e->logits; cnt = M * LDL; }
+  else return fail(B2T_ERR_ARG, "unknown buffer '%s'", name);
+  if (!p) return fail(B2T_ERR_STATE, "buffer '%s' does not exist in this engine (inference-only, or last layer)", name);
+  *ptr = p;
+  if (elems) *elems = cnt;
+  return 0;
+}
+
 extern "C" int b2t_refresh_weights(b2t_engine* e, void* stream) {
   if (!e) return fail(B2T_ERR_ARG, "null engine");
   cudaStream_t st = (cudaStream_t)stream;

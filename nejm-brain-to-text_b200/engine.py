@@ -105,6 +105,26 @@ class Engine:
             N.lib.b2t_engine_destroy(h)
             self.handle = None
 
+    # ------------------------------------------------------------------ optimizer step counters
+    def steps_tensor(self) -> torch.Tensor:
+        """Per-segment AdamW step counters (device int32, aliasing the engine's own memory; b2t_step_counters)."""
+        n = len(param_layout(self.cfg))
+        ptr = N.lib.b2t_step_counters(self.handle)
+
+        class _Wrap:
+            pass
+        w = _Wrap()
+        w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+        return torch.as_tensor(w, device=self.device)
+
+    def adopt_optimizer_state(self, old: "Engine"):
+        """Carry the AdamW state of ``old`` (moments AND per-segment step counters) into this engine.  Used when the model
+        regrows its engine for a larger batch or a longer trial: resetting the step counters while the moments stay warm
+        would change the bias correction (bc1 = 1 - beta1**step) and with it the update size."""
+        self.exp_avg.copy_(old.exp_avg)
+        self.exp_avg_sq.copy_(old.exp_avg_sq)
+        self.steps_tensor().copy_(old.steps_tensor())
+
     # ------------------------------------------------------------------ weights
     def refresh_weights(self):
         N.check(N.lib.b2t_refresh_weights(self.handle, _stream()), "b2t_refresh_weights")
@@ -164,8 +184,22 @@ class Engine:
         return cls._taps_cache[key]
 
     # ------------------------------------------------------------------ loss / backward / optimizer
+    @staticmethod
+    def _trim_labels(labels: torch.Tensor, tgt_len: torch.Tensor, max_target_len: Optional[int]) -> torch.Tensor:
+        """Labels arrive zero-padded to a fixed width (the reference dataset pads seq_class_ids to 500); the CTC kernels
+        pick their variant from the padded width, so cut the padding down to the longest target of the batch.  The width
+        is taken from ``max_target_len`` (known on the host, no device sync) or from a CPU ``tgt_len``."""
+        if max_target_len is None and not tgt_len.is_cuda and tgt_len.numel() > 0:
+            max_target_len = int(tgt_len.max())
+        if max_target_len is not None:
+            w = max(1, min(int(max_target_len), labels.shape[1]))
+            if w < labels.shape[1]:
+                labels = labels[:, :w]
+        return labels
+
     def ctc_loss(self, labels: torch.Tensor, in_len: torch.Tensor, tgt_len: torch.Tensor, *, grad_scale: float,
-                 want_grad: bool = True) -> torch.Tensor:
+                 want_grad: bool = True, max_target_len: Optional[int] = None) -> torch.Tensor:
+        labels = self._trim_labels(labels, tgt_len, max_target_len)
         labels = labels.to(device=self.device, dtype=torch.int32).contiguous()
         in_len = in_len.to(device=self.device, dtype=torch.int32).contiguous()
         tgt_len = tgt_len.to(device=self.device, dtype=torch.int32).contiguous()
@@ -192,7 +226,8 @@ class Engine:
         N.check(N.lib.b2t_optimizer_step(self.handle, C.byref(a), self.stats.data_ptr(), _stream()), "b2t_optimizer_step")
         return self.stats
 
-    def greedy_edit(self, labels, in_len, tgt_len):
+    def greedy_edit(self, labels, in_len, tgt_len, max_target_len: Optional[int] = None):
+        labels = self._trim_labels(labels, tgt_len, max_target_len)
         labels = labels.to(device=self.device, dtype=torch.int32).contiguous()
         in_len = in_len.to(device=self.device, dtype=torch.int32).contiguous()
         tgt_len = tgt_len.to(device=self.device, dtype=torch.int32).contiguous()
@@ -203,6 +238,20 @@ class Engine:
         N.check(N.lib.b2t_greedy_edit(self.handle, labels.data_ptr(), labels.shape[1], in_len.data_ptr(), tgt_len.data_ptr(),
                                       dec.data_ptr(), dlen.data_ptr(), ed.data_ptr(), _stream()), "b2t_greedy_edit")
         return dec, dlen, ed
+
+    def debug_buffer(self, name: str, layer: int = 0) -> torch.Tensor:
+        """Test hook (b2t_debug_buffer): an internal activation buffer of the last forward/backward as a flat device tensor
+        aliasing the engine's workspace (bf16 or fp32 depending on the buffer, see include/b2t_b200.h)."""
+        ptr, n = C.c_void_p(), C.c_longlong()
+        N.check(N.lib.b2t_debug_buffer(self.handle, name.encode(), int(layer), C.byref(ptr), C.byref(n)), "b2t_debug_buffer")
+        f32 = name in ("gx", "dY", "logits")
+
+        class _Wrap:
+            pass
+        w = _Wrap()
+        w.__cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4" if f32 else "<i2", "data": (int(ptr.value), False), "version": 2}
+        t = torch.as_tensor(w, device=self.device)
+        return t if f32 else t.view(torch.bfloat16)
 
     def touched_days(self) -> torch.Tensor:
         return self.grads[self.n_params:self.n_params + self.cfg.n_days]

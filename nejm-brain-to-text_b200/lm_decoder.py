@@ -144,9 +144,14 @@ class BrainSpeechDecoder:
 def DecodeNumpy(decoder: BrainSpeechDecoder, logits, log_priors, blank_penalty, slot: int = 0):
     """lm_decoder.cc:14-37."""
     x = np.ascontiguousarray(logits, dtype=np.float32)            # py::array::forcecast
-    pr = np.ascontiguousarray(log_priors, dtype=np.float32)
+    pr = np.asarray(log_priors, dtype=np.float32)
     if x.ndim != 2 or pr.ndim != 2:
         raise ValueError("DecodeNumpy expects 2-D logits and log_priors")
+    # the reference subtracts with torch broadcasting (lm_decoder.cc:30), so a [1, C] prior is legal; the C ABI wants [T, C]
+    try:
+        pr = np.ascontiguousarray(np.broadcast_to(pr, x.shape), dtype=np.float32)
+    except ValueError:
+        raise ValueError(f"DecodeNumpy: log_priors of shape {pr.shape} do not broadcast to the logits {x.shape}") from None
     _check(_lib.b2t_decoder_decode_logits(decoder._h, slot, x.ctypes.data, pr.ctypes.data, x.shape[0], x.shape[1], float(blank_penalty)),
            "DecodeNumpy")
 

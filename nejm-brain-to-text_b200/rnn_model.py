@@ -55,7 +55,8 @@ class _GRUDecoderFn(torch.autograd.Function):
                 grads.append(None)              # day layer not in this batch: grad stays None, AdamW skips it
                 continue
             off, n = model._slots[name]
-            grads.append(eng.grads[off:off + n].view(p.shape))
+            # a copy: autograd may keep what is returned here as p.grad, and the engine's buffer is rewritten by the next backward
+            grads.append(eng.grads[off:off + n].view(p.shape).clone())
         return (None, None, None, None, None) + tuple(grads)
 
 
@@ -164,14 +165,12 @@ class GRUDecoder(nn.Module):
             mb = max(B, e.max_batch if e else 0)
             mt = max(T, e.max_T if e else 0)
             tr = training or (e.training_capable if e else False)
-            old_state = None
-            if e is not None and e.training_capable:
-                old_state = (e.exp_avg, e.exp_avg_sq, e.grads)
+            old = e if (e is not None and e.training_capable) else None
             self._engine = None
             e = E.Engine(self._cfg, self._flat, max_batch=mb, max_T=mt, max_label_len=500, training=tr,
-                         flat_grads=old_state[2] if old_state else None)
-            if old_state:
-                e.exp_avg.copy_(old_state[0]); e.exp_avg_sq.copy_(old_state[1])
+                         flat_grads=old.grads if old is not None else None)
+            if old is not None:
+                e.adopt_optimizer_state(old)       # moments and the per-segment AdamW step counters
             self._engine = e
             self.weights_synced = True
         return e
@@ -205,7 +204,9 @@ class GRUDecoder(nn.Module):
             eng.refresh_weights()
             self.weights_synced = True
         if train:
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            import os
+            # ranks of a data-parallel job share the torch seed (identical weight init): mix the rank into the dropout stream
+            seed = (int(torch.randint(0, 2 ** 62, (1,)).item()) ^ (int(os.environ.get("RANK", "0")) * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1)
             logits, hidden = _GRUDecoderFn.apply(self, x, day_idx, states, seed, *[p for _, p in self._named_flat])
         else:
             logits, hidden = eng.forward(x, day_idx, training=False, smooth_mode=0, states=states, want_hidden=True)

@@ -106,13 +106,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
         """The engine's per-segment AdamW step counters as a device int32 tensor (aliasing the engine's memory)."""
         from .engine import param_layout
         names = [n for n, _, _, _ in param_layout(self.model._cfg)]
-        ptr = N.lib.b2t_step_counters(eng.handle)
-
-        class _Wrap:
-            pass
-        w = _Wrap()
-        w.__cuda_array_interface__ = {"shape": (len(names),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
-        return names, torch.as_tensor(w, device=eng.device)
+        return names, eng.steps_tensor()
 
     def _steps(self, eng):
         names, t = self._steps_tensor(eng)
@@ -165,8 +159,10 @@ class _DevicePrefetcher:
         except StopIteration:
             self.batch = None
             return
+        max_len = int(b['phone_seq_lens'].max()) if torch.is_tensor(b.get('phone_seq_lens')) and b['phone_seq_lens'].numel() else None
         with torch.cuda.stream(self.stream):
             self.batch = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) and k != 'transcriptions' else v) for k, v in b.items()}
+            self.batch['max_phone_seq_len'] = max_len      # the reference pads seq_class_ids to a fixed width; the CTC kernels want the real one
             self.event = torch.cuda.Event()
             self.event.record(self.stream)
 
@@ -251,6 +247,9 @@ class BrainToTextDecoder_Trainer:
             np.random.seed(self.args['seed'])
             random.seed(self.args['seed'])
             torch.manual_seed(self.args['seed'])
+        # augmentation draws (random_cut, device RNG seed of noise and dropout): one host stream per rank, so that data-parallel
+        # ranks apply different noise/dropout patterns while the weight init above stays identical (and is broadcast anyway)
+        self._aug_rng = np.random.RandomState(None if self.args['seed'] == -1 else (int(self.args['seed']) * 9973 + 17 + self.rank) % (2 ** 31))
 
         self.model = GRUDecoder(
             neural_dim=self.args['model']['n_input_features'],
@@ -467,17 +466,18 @@ class BrainToTextDecoder_Trainer:
                 features = torch.matmul(features, warp)
             if ta['random_walk_std'] > 0:
                 features = features + torch.cumsum(torch.randn_like(features) * ta['random_walk_std'], dim=ta['random_walk_axis'])
-        cut = int(np.random.randint(0, ta['random_cut'])) if ta['random_cut'] > 0 else 0
+        cut = int(self._aug_rng.randint(0, ta['random_cut'])) if ta['random_cut'] > 0 else 0
         eng = self.model.engine(B, T, training=True)
         self.model.fused_updates = True
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        seed = int(self._aug_rng.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(self._aug_rng.randint(0, 2 ** 31 - 1))
         eng.forward(features, day_indicies, training=True, smooth_mode=1 if ta['smooth_data'] else 0,
                     smooth_std=float(ta['smooth_kernel_std']), smooth_size=int(ta['smooth_kernel_size']), cut=cut,
                     white_noise_std=float(ta['white_noise_std']), offset_noise_std=float(ta['constant_offset_std']), seed=seed,
                     want_logits=False)
         ps, st = self.args['model']['patch_size'], self.args['model']['patch_stride']
         adjusted_lens = (((n_time_steps - cut) - ps) / st + 1).to(torch.int32)
-        loss_vec = eng.ctc_loss(labels, adjusted_lens, phone_seq_lens, grad_scale=1.0 / (B * self.world_size))
+        loss_vec = eng.ctc_loss(labels, adjusted_lens, phone_seq_lens, grad_scale=1.0 / (B * self.world_size),
+                                max_target_len=batch.get('max_phone_seq_len'))
         eng.backward()
         if self.world_size > 1:
             dist.all_reduce(eng.grads)              # one all-reduce: flat gradients + day-touched flags
@@ -589,8 +589,9 @@ class BrainToTextDecoder_Trainer:
                                         smooth_std=float(ta['smooth_kernel_std']), smooth_size=int(ta['smooth_kernel_size']),
                                         want_logits=return_logits)
                 adjusted_lens = ((n_time_steps - ps) / st + 1).to(torch.int32)
-                loss = eng.ctc_loss(labels, adjusted_lens, phone_seq_lens, grad_scale=1.0, want_grad=False).mean()
-                dec, dlen, ed = eng.greedy_edit(labels, adjusted_lens, phone_seq_lens)
+                max_len = int(batch['phone_seq_lens'].max()) if not batch['phone_seq_lens'].is_cuda else None
+                loss = eng.ctc_loss(labels, adjusted_lens, phone_seq_lens, grad_scale=1.0, want_grad=False, max_target_len=max_len).mean()
+                dec, dlen, ed = eng.greedy_edit(labels, adjusted_lens, phone_seq_lens, max_target_len=max_len)
             metrics['losses'].append(loss.cpu().detach().numpy())
             dec_h, dlen_h, ed_h = dec.cpu().numpy(), dlen.cpu().numpy(), ed.cpu().numpy()
             decoded_seqs = [dec_h[b, :dlen_h[b]] for b in range(dec_h.shape[0])]
