@@ -14,6 +14,7 @@
 #include "gemm.h"
 #include "gru_rec.cuh"
 #include "gru_rec_bwd2.cuh"
+#include "gru_stack.cuh"
 #include "optim.cuh"
 #include "tmap.h"
 
@@ -179,6 +180,12 @@ struct b2t_engine {
   const int* day_idx = nullptr;
   bool states_given = false;
   long long* trace = nullptr;   // optional device buffer [2][T'][8] for the recurrence cycle trace
+  // whole-stack persistent recurrence (gru_stack.cuh): one cooperative launch per direction, gated GEMMs beside it
+  int stack = 0, stk_BG = 32, stk_NSUB = 2, stk_ncg = 1, stk_grid = 0, stk_need = 0, stk_gemm_ctas = 1;
+  int* ctr = nullptr;           // [4][L][ctr_stride] progress / completion counters: fwd_prog, gx_done, bwd_prog, dy_done
+  int ctr_stride = 0;
+  cudaStream_t gstream[STACK_MAX_LAYERS] = {};
+  cudaEvent_t ev_g[STACK_MAX_LAYERS] = {};
 };
 
 // Optional timeline (B2T_TIMELINE=1): CUDA events around every task of a step, dumped by b2t_debug_dump_timeline.
@@ -247,6 +254,8 @@ static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
       b.dh_state = c.take<float>((size_t)Bp * H);
     }
   }
+  e->ctr_stride = (int)r64((long long)Tq + (long long)(M + 127) / 128 + 2);
+  e->ctr = c.take<int>((size_t)4 * L * e->ctr_stride);
   e->logits = c.take<float>(M * LDL);
   e->dlog32 = c.take<float>(M * LDL);
   e->dlog16 = c.take<__nv_bfloat16>(M * LDL);
@@ -284,6 +293,10 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
   for (int i = 0; i <= MAX_LANES + 1; ++i) {
     if (e->lane[i]) cudaStreamDestroy(e->lane[i]);
     if (e->ev_lane_end[i]) cudaEventDestroy(e->ev_lane_end[i]);
+  }
+  for (int i = 0; i < STACK_MAX_LAYERS; ++i) {
+    if (e->gstream[i]) cudaStreamDestroy(e->gstream[i]);
+    if (e->ev_g[i]) cudaEventDestroy(e->ev_g[i]);
   }
   if (e->ev_start) cudaEventDestroy(e->ev_start);
   if (e->ev_top) cudaEventDestroy(e->ev_top);
@@ -324,6 +337,9 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
   for (int i = 0; i <= MAX_LANES + 1 && ok; ++i)
     ok = cudaStreamCreateWithPriority(&e->lane[i], cudaStreamNonBlocking, (i < MAX_LANES) != (env_int("B2T_BULK_PRIO", 0) != 0) ? prio_hi : prio_lo) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_lane_end[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < STACK_MAX_LAYERS && ok; ++i)
+    ok = cudaStreamCreateWithPriority(&e->gstream[i], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->ev_g[i], cudaEventDisableTiming) == cudaSuccess;
   e->ev_r.assign((size_t)e->L * MAX_CHUNKS, nullptr);
   e->ev_dx.assign((size_t)e->L * MAX_CHUNKS, nullptr);
   for (size_t i = 0; i < e->ev_r.size() && ok; ++i)
@@ -431,6 +447,25 @@ static int build_plans(b2t_engine* e) {
   int nch = env_int("B2T_REC_CHUNKS", 0);
   if (nch <= 0) nch = (std::max(e->n_lanes, e->n_lanes_b) > 1 && Tp >= 48) ? (std::max(e->n_lanes, e->n_lanes_b) >= 5 ? 6 : 3) : 1;
   nch = std::max(1, std::min(std::min(nch, MAX_CHUNKS), Tp));
+  // ---- whole-stack persistent recurrence: every layer resident at once, two batch groups per CTA when the group count is even
+  {
+    const int bg = (Bp % 32 == 0) ? 32 : 16;
+    const int ng = Bp / bg;
+    const int nsub = (ng % 2 == 0) ? 2 : 1;
+    const int grid = L * (H / 32) * (ng / nsub);
+    const size_t smem_f = bg == 32 ? (nsub == 2 ? StackCfg<32, 2>::fwd_smem_bytes(H) : StackCfg<32, 1>::fwd_smem_bytes(H))
+                                   : StackCfg<16, 1>::fwd_smem_bytes(H);
+    bool ok = env_int("B2T_STACK", 1) != 0 && L <= STACK_MAX_LAYERS && grid + std::max(L - 1, 0) <= num_sms() && smem_f <= 227 * 1024 &&
+              128 % bg == 0 && (nsub * bg) <= 128 && (128 % (nsub * bg) == 0);
+    if (tr) ok = ok && (H % 256 == 0);          // backward uses the two-dimensional decomposition (H/128 x 4 CTAs per batch group)
+    e->stack = ok ? 1 : 0;
+    if (ok) {
+      e->stk_BG = bg; e->stk_NSUB = nsub; e->stk_ncg = ng / nsub; e->stk_grid = grid;
+      e->stk_need = (H / 32) * ng * (bg / 4);   // epilogue warps of a layer: CTAs x groups per CTA x warps per group
+      e->stk_gemm_ctas = L > 1 ? std::max(1, (num_sms() - grid) / (L - 1)) : 1;
+      nch = 1;                                  // no time chunking: the GEMMs beside the recurrence are gated per 128-row tile instead
+    }
+  }
   e->n_tchunks = nch;
   for (int c = 0; c <= nch; ++c) e->tc_begin[c] = (int)((long long)c * Tp / nch);
   e->p_dwih.assign(L, GemmPlan());
@@ -486,6 +521,10 @@ static int build_plans(b2t_engine* e) {
         s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
         s.C = e->lay[l].gx + r0 * 3 * H; s.ldc = 3 * H;
         s.bias = e->params + seg_off(e, "gru.bias_ih_l" + sl);
+        if (e->stack) {   // follows the recurrence of layer l-1 tile by tile and reports to the recurrence of layer l
+          s.gate = e->ctr + (size_t)(0 * L + (l - 1)) * e->ctr_stride; s.gate_need = e->stk_need; s.gate_rows_per_step = Bp; s.gate_steps = Tp;
+          s.done = e->ctr + (size_t)(1 * L + l) * e->ctr_stride; s.max_ctas = e->stk_gemm_ctas;
+        }
         if ((rc = gemm_plan_build(&e->p_in[l][c], s))) return fail(B2T_ERR_CUDA, "input plan %d/%d failed (%d)", l, c, rc);
       }
     }
@@ -562,7 +601,13 @@ static int build_plans(b2t_engine* e) {
       s.M = rows; s.K = 3 * H; s.A = e->lay[l].dGx + r0 * 3 * H; s.lda = 3 * H;
       s.B = e->shadow + seg_off(e, "gru.weight_ih_l" + sl);
       if (l == 0) { s.N = K0; s.ldb = K0; s.out_bf16 = 1; s.C = e->dxu + r0 * K0; s.ldc = K0; }
-      else { s.N = H; s.ldb = H; s.out_bf16 = 0; s.C = e->lay[l - 1].dY + r0 * H; s.ldc = H; }
+      else {
+        s.N = H; s.ldb = H; s.out_bf16 = 0; s.C = e->lay[l - 1].dY + r0 * H; s.ldc = H;
+        if (e->stack) {   // follows the backward recurrence of layer l (time descending) and reports to the one of layer l-1
+          s.gate = e->ctr + (size_t)(2 * L + l) * e->ctr_stride; s.gate_need = e->stk_need; s.gate_rows_per_step = Bp; s.gate_steps = Tp;
+          s.done = e->ctr + (size_t)(3 * L + (l - 1)) * e->ctr_stride; s.tm_reverse = 1; s.max_ctas = e->stk_gemm_ctas;
+        }
+      }
       if ((rc = gemm_plan_build(&e->p_dx[l][c], s))) return fail(B2T_ERR_CUDA, "dX plan %d/%d failed (%d)", l, c, rc);
     }
   }
@@ -656,6 +701,33 @@ static cudaError_t launch_rec_bwd(int BG, int nsub, const RecBwdParams& p, int g
   return BG == 64 ? launch_rec_bwd_t<64, 1>(p, grid, st) : BG == 32 ? launch_rec_bwd_t<32, 1>(p, grid, st) : launch_rec_bwd_t<16, 1>(p, grid, st);
 }
 
+template <int BG, int NSUB>
+static cudaError_t launch_stack_fwd_t(const StackFwdParams& p, int grid, cudaStream_t st) {
+  const size_t smem = std::max(REC_SMEM_BYTES, StackCfg<BG, NSUB>::fwd_smem_bytes(p.H));
+  cudaError_t err = cudaFuncSetAttribute(gru_stack_fwd_kernel<BG, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  void* args[1] = {(void*)&p};
+  ++g_launches;
+  return cudaLaunchCooperativeKernel((const void*)gru_stack_fwd_kernel<BG, NSUB>, dim3(grid), dim3(RecCfg<BG>::kFwdThreads), args, smem, st);
+}
+template <int BG, int NSUB>
+static cudaError_t launch_stack_bwd_t(const StackBwdParams& p, int grid, cudaStream_t st) {
+  const size_t smem = std::max(REC_SMEM_BYTES, StackCfg<BG, NSUB>::bwd_smem_bytes(p.H));
+  cudaError_t err = cudaFuncSetAttribute(gru_stack_bwd_kernel<BG, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  void* args[1] = {(void*)&p};
+  ++g_launches;
+  return cudaLaunchCooperativeKernel((const void*)gru_stack_bwd_kernel<BG, NSUB>, dim3(grid), dim3(RecCfg<BG>::kFwdThreads), args, smem, st);
+}
+static cudaError_t launch_stack_fwd(int BG, int NSUB, const StackFwdParams& p, int grid, cudaStream_t st) {
+  if (BG == 32) return NSUB == 2 ? launch_stack_fwd_t<32, 2>(p, grid, st) : launch_stack_fwd_t<32, 1>(p, grid, st);
+  return NSUB == 1 ? launch_stack_fwd_t<16, 1>(p, grid, st) : cudaErrorInvalidValue;   // 16-trial groups only arise for an odd group count
+}
+static cudaError_t launch_stack_bwd(int BG, int NSUB, const StackBwdParams& p, int grid, cudaStream_t st) {
+  if (BG == 32) return NSUB == 2 ? launch_stack_bwd_t<32, 2>(p, grid, st) : launch_stack_bwd_t<32, 1>(p, grid, st);
+  return NSUB == 1 ? launch_stack_bwd_t<16, 1>(p, grid, st) : cudaErrorInvalidValue;
+}
+
 // Gradient regions that backward accumulates into with atomics (biases, h0, day layers): cleared ahead of time.  GEMM-stored
 // gradients are fully overwritten.  Untouched day segments are cleared too -- cheap, and keeps the gradient-norm reduction free
 // of stale values.
@@ -724,6 +796,11 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
       CK(LAUNCHED());
     }
     if (a->training) { const int rc = zero_accumulated_grads(e, ss); if (rc) return rc; }
+    if (e->stack) {
+      CK(cudaMemsetAsync(e->ctr, 0, (size_t)4 * L * e->ctr_stride * sizeof(int), ss));
+      if (a->training)   // the dGh arrays double as the exchange medium of the backward stack kernel: "not written yet" sentinel
+        for (int l = 0; l < L; ++l) CK(cudaMemsetAsync(e->lay[l].dGh, 0xFF, (size_t)e->M * 3 * H * sizeof(__nv_bfloat16), ss));
+    }
     CK(cudaEventRecord(e->ev_init, ss));
   }
   pp.x = a->x; pp.out = e->xs; pp.out_f32 = nullptr; pp.B = a->B; pp.Bpad = Bp; pp.T_in = a->T; pp.T_alloc = a->T; pp.D = D;
@@ -744,6 +821,43 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
     unfold_kernel<<<num_sms() * 4, 256, 0, st>>>(e->xd, e->xu, Bp, a->T, D, Tp, e->patch, e->stride);
     CK(LAUNCHED());
   }
+  const bool save = a->training != 0;
+  if (e->stack) {
+    // ---- whole-stack schedule: layer-0 input projection on the whole chip, then ONE persistent recurrence kernel for all layers
+    //      with the input projections of layers >= 1 as gated GEMMs on the SMs it leaves free (gru_stack.cuh)
+    CK(cudaStreamWaitEvent(st, e->ev_init, 0));
+    { TlScope tl("G0", 9, st); CK(gemm_run(e->p_in[0][0], st)); ++g_launches; }
+    CK(cudaEventRecord(e->ev_start, st));
+    cudaStream_t rs = e->lane[0];
+    CK(cudaStreamWaitEvent(rs, e->ev_start, 0));
+    StackFwdParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.H = H; sp.Bpad = Bp; sp.T = Tp; sp.n_slices = H / 32; sp.n_layers = L; sp.n_cgroups = e->stk_ncg;
+    sp.poll_delay = e->poll_delay; sp.seed = a->seed; sp.trace = e->trace;
+    for (int l = 0; l < L; ++l) {
+      const std::string sl = std::to_string(l);
+      StackFwdLayer& y = sp.lay[l];
+      y.gx = e->lay[l].gx; y.bhh = e->params + seg_off(e, "gru.bias_hh_l" + sl); y.whh = e->shadow + seg_off(e, "gru.weight_hh_l" + sl);
+      y.hseq = e->lay[l].hseq; y.h_state = e->lay[l].h_state;
+      y.hdrop = save ? e->lay[l].hdrop : nullptr;
+      y.R = save ? e->lay[l].R : nullptr; y.Z = save ? e->lay[l].Z : nullptr; y.Nn = save ? e->lay[l].Nn : nullptr; y.HN = save ? e->lay[l].HN : nullptr;
+      y.keep = keep_rnn; y.rng_offset = (unsigned long long)(l + 1) << 40;
+      if (!save && e->lay[l].hdrop) { y.hdrop = e->lay[l].hdrop; y.keep = 1.0f; }   // eval through a training engine: the next layer reads hdrop
+      y.gx_done = l > 0 ? e->ctr + (size_t)(1 * L + l) * e->ctr_stride : nullptr;
+      y.gx_need = 4 * e->p_in[l][0].p.tiles_n;
+      y.prog = l < L - 1 ? e->ctr + (size_t)(0 * L + l) * e->ctr_stride : nullptr;
+    }
+    { TlScope tl("SR", 0, rs); CK(launch_stack_fwd(e->stk_BG, e->stk_NSUB, sp, e->stk_grid, rs)); }
+    CK(cudaEventRecord(e->ev_lane_end[0], rs));
+    for (int l = 1; l < L; ++l) {
+      cudaStream_t gs = e->gstream[l];
+      CK(cudaStreamWaitEvent(gs, e->ev_start, 0));
+      { TlScope tl(("G" + std::to_string(l)).c_str(), l, gs); CK(gemm_run(e->p_in[l][0], gs)); ++g_launches; }
+      CK(cudaEventRecord(e->ev_g[l], gs));
+      CK(cudaStreamWaitEvent(st, e->ev_g[l], 0));
+    }
+    CK(cudaStreamWaitEvent(st, e->ev_lane_end[0], 0));
+  } else {
   CK(cudaEventRecord(e->ev_start, st));
   for (int i = 0; i <= MAX_LANES; ++i) {
     CK(cudaStreamWaitEvent(e->lane[i], e->ev_start, 0));
@@ -760,7 +874,6 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
   // 4. GRU stack: wave-front over (layer, chunk).  Task (l, c) = input projection of chunk c (l > 0: needs chunk c of the layer
   //    below) + recurrence over chunk c (needs chunk c-1 of the same layer).  Tasks are list-scheduled onto the lane that
   //    frees first (estimated durations), dependencies are CUDA events, issue order is diagonal by diagonal.
-  const bool save = a->training != 0;
   double lane_free[MAX_LANES] = {};
   std::vector<double> t_end((size_t)L * MAX_CHUNKS, 0.0);
   const double dur_g = 40.0, dur_r = 135.0;
@@ -803,6 +916,7 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
     CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
     CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));
   }
+  }   // !stack
   // 5. head
   { TlScope tl("head", 9, st); CK(gemm_run(e->p_head, st)); ++g_launches; }
   if (a->logits_out) {
@@ -933,15 +1047,18 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   CK(cudaMemsetAsync(e->touched, 0, r64(e->cfg.n_days) * sizeof(float), st));
   mark_days_kernel<<<(e->B + 127) / 128, 128, 0, st>>>(e->day_idx, e->B, e->touched);
   CK(LAUNCHED());
-  if (e->bwd2) {   // the dGh arrays double as the exchange medium of gru_rec_bwd2_kernel: "not written yet" sentinel
+  if (e->bwd2 && !e->stack) {   // the dGh arrays double as the exchange medium of gru_rec_bwd2_kernel: "not written yet" sentinel
     for (int l = 0; l < L; ++l) CK(cudaMemsetAsync(e->lay[l].dGh, 0xFF, (size_t)e->M * 3 * H * sizeof(__nv_bfloat16), st));
   }
-  if (e->part_geom != (Bp * 64 + BG) * 2 + e->bwd2) {   // partial-exchange buffers: (re)start the generation tags (gru_rec.cuh) for this geometry
-    for (int l = 0; l < L; ++l) {
-      CK(cudaMemsetAsync(e->lay[l].part, 0xFF, (size_t)2 * Bp * (H / 32) * (H / 32) * 32 * sizeof(float), st));
-      e->lay[l].gen = 0;
+  {
+    const int geom = e->stack ? 1000000 + (Bp * 64 + e->stk_BG) * 2 : (Bp * 64 + BG) * 2 + e->bwd2;
+    if (e->part_geom != geom) {   // partial-exchange buffers: (re)start the generation tags (gru_rec.cuh) for this geometry
+      for (int l = 0; l < L; ++l) {
+        CK(cudaMemsetAsync(e->lay[l].part, 0xFF, (size_t)2 * Bp * (H / 32) * (H / 32) * 32 * sizeof(float), st));
+        e->lay[l].gen = 0;
+      }
+      e->part_geom = geom;
     }
-    e->part_geom = (Bp * 64 + BG) * 2 + e->bwd2;
   }
 
   // head
@@ -950,6 +1067,69 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   { TlScope tl("dWout", 9, st); CK(gemm_run(e->p_dwout, st)); ++g_launches; }
   { TlScope tl("dYtop", 9, st); CK(gemm_run(e->p_dytop, st)); ++g_launches; }
   CK(cudaEventRecord(e->ev_top, st));
+  if (e->stack) {
+    // ---- whole-stack schedule: ONE persistent backward recurrence for all layers; the data-gradient GEMMs dY_{l-1} = dGx_l W_ih_l
+    //      follow it as gated GEMMs (time descending) on the free SMs; weight gradients, layer-0 data gradient, fold and day layer after it
+    cudaStream_t rs = e->lane[0], bs = e->lane[MAX_LANES], bw = e->lane[MAX_LANES + 1];
+    CK(cudaStreamWaitEvent(rs, e->ev_top, 0));
+    StackBwdParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.H = H; sp.Bpad = Bp; sp.T = Tp; sp.n_layers = L; sp.n_cgroups = e->stk_ncg; sp.n_valid = e->B;
+    sp.poll_delay = e->poll_delay_b; sp.seed = e->seed; sp.trace = e->trace;
+    for (int l = 0; l < L; ++l) {
+      const std::string sl = std::to_string(l);
+      StackBwdLayer& y = sp.lay[l];
+      y.dY = e->lay[l].dY; y.hseq = e->lay[l].hseq; y.R = e->lay[l].R; y.Z = e->lay[l].Z; y.Nn = e->lay[l].Nn; y.HN = e->lay[l].HN;
+      y.whh = e->shadow + seg_off(e, "gru.weight_hh_l" + sl);
+      y.dGx = e->lay[l].dGx; y.dGh = e->lay[l].dGh; y.part = e->lay[l].part;
+      y.dbih = e->grads + seg_off(e, "gru.bias_ih_l" + sl); y.dbhh = e->grads + seg_off(e, "gru.bias_hh_l" + sl);
+      y.dh_state = e->lay[l].dh_state;
+      y.dy_done = l < L - 1 ? e->ctr + (size_t)(3 * L + l) * e->ctr_stride : nullptr;
+      y.dy_need = l < L - 1 ? 4 * e->p_dx[l + 1][0].p.tiles_n : 0;
+      y.prog = l > 0 ? e->ctr + (size_t)(2 * L + l) * e->ctr_stride : nullptr;
+      y.gen_base = e->lay[l].gen; e->lay[l].gen = (e->lay[l].gen + Tp) & 7;
+      y.keep = (l < L - 1) ? keep_rnn : 1.0f;
+      y.rng_offset = (unsigned long long)(l + 1) << 40;
+    }
+    { TlScope tl("SRB", 0, rs); CK(launch_stack_bwd(e->stk_BG, e->stk_NSUB, sp, e->stk_grid, rs)); }
+    CK(cudaEventRecord(e->ev_r[0], rs));
+    for (int l = L - 1; l >= 1; --l) {
+      cudaStream_t gs = e->gstream[l];
+      CK(cudaStreamWaitEvent(gs, e->ev_top, 0));
+      { TlScope tl(("DX" + std::to_string(l)).c_str(), l, gs); CK(gemm_run(e->p_dx[l][0], gs)); ++g_launches; }
+      CK(cudaEventRecord(e->ev_g[l], gs));
+      CK(cudaStreamWaitEvent(st, e->ev_g[l], 0));
+    }
+    CK(cudaStreamWaitEvent(bs, e->ev_r[0], 0));
+    CK(cudaStreamWaitEvent(bw, e->ev_r[0], 0));
+    // chain on the first bulk stream: layer-0 data gradient -> patch fold -> day layer; everything else on the second one
+    { TlScope tl("DX0", 8, bs); CK(gemm_run(e->p_dx[0][0], bs)); ++g_launches; }
+    {
+      FoldParams fp;
+      fp.dxu = e->dxu; fp.xd = e->xd; fp.dpre = e->dpre; fp.dbias_day = e->grads + seg_off(e, "day_biases.0"); fp.bias_pitch = (int)r64(D);
+      fp.day_idx = e->day_idx; fp.B = e->B; fp.Bpad = Bp; fp.T_alloc = e->T_in; fp.T_valid = e->T_out; fp.D = D; fp.Tp = Tp;
+      fp.patch = e->patch; fp.stride = e->stride; fp.keep = keep_in; fp.seed = e->seed; fp.rng_offset = 0;
+      dim3 g((e->T_in + FOLD_TT - 1) / FOLD_TT, Bp);
+      { TlScope tl("fold", 8, bs); fold_dpre_kernel<<<g, D / 4, 0, bs>>>(fp); CK(LAUNCHED()); }
+      { TlScope tl("daydW", 8, bs); CK(gemm_run(e->p_daydw, bs)); ++g_launches; }
+    }
+    { TlScope tl("dWih0", 7, bw); CK(gemm_run(e->p_dwih0[0], bw)); ++g_launches; }
+    for (int l = L - 1; l >= 0; --l) {
+      const std::string sl = std::to_string(l);
+      if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwih[l], bw)); ++g_launches; }
+      { TlScope tl(("dWhh" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwhh[l], bw)); ++g_launches; }
+      if (!e->states_given) {
+        reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bw>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
+        CK(LAUNCHED());
+      }
+    }
+    for (int i = MAX_LANES; i <= MAX_LANES + 1; ++i) {
+      CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
+      CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));
+    }
+    e->have_dlogits = false;
+    return 0;
+  }
   for (int i = 0; i < NL; ++i) CK(cudaStreamWaitEvent(e->lane[i], e->ev_top, 0));
   CK(cudaStreamWaitEvent(e->lane[MAX_LANES], e->ev_top, 0));
   CK(cudaStreamWaitEvent(e->lane[MAX_LANES + 1], e->ev_top, 0));

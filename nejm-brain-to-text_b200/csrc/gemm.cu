@@ -27,7 +27,8 @@ static cudaError_t launch_variant(const GemmPlan& pl, cudaStream_t st) {
   }
   const int total = pl.p.tiles_m * pl.p.tiles_n * pl.p.nz;
   if (total <= 0) return cudaSuccess;
-  const int grid = total < num_sms() ? total : num_sms();
+  int grid = total < num_sms() ? total : num_sms();
+  if (pl.max_ctas > 0 && grid > pl.max_ctas) grid = pl.max_ctas;
   kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(pl.ta, pl.tb, pl.p);
   return cudaGetLastError();
 }
@@ -65,6 +66,10 @@ int gemm_plan_build(GemmPlan* pl, const GemmSpec& s) {
   p.C = s.C; p.ldc = s.ldc; p.c_zstride = s.c_zstride;
   p.bias = s.bias; p.bias_zstride = s.bias_zstride; p.z_map = s.z_map; p.zmap_b = s.zmap_b;
   p.keep = s.keep > 0 ? s.keep : 1.0f; p.seed = s.seed; p.rng_offset = s.rng_offset;
+  p.gate = s.gate; p.gate_need = s.gate_need; p.gate_rows_per_step = s.gate_rows_per_step > 0 ? s.gate_rows_per_step : 1;
+  p.gate_steps = s.gate_steps; p.done = s.done; p.tm_reverse = s.tm_reverse;
+  pl->max_ctas = s.max_ctas;
+  if ((s.gate || s.done) && (s.a_mn || s.a_rin > 0 || p.nz != 1)) return -20;   // gating is defined for plain K-major A (time-major rows) only
   p.tiles_n = ceil_div(s.N, GEMM_BN);
   p.k_bin = 1; p.k_rin_blocks = 1; p.a_bin = 1; p.a_rin_blocks = 1; p.a_rin = 1; p.a_rout = s.M;
 

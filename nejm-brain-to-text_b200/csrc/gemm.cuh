@@ -106,9 +106,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int tn = tile % p.tiles_n;
-        const int tm = (tile / p.tiles_n) % p.tiles_m;
+        const int tm0 = (tile / p.tiles_n) % p.tiles_m;
+        const int tm = p.tm_reverse ? p.tiles_m - 1 - tm0 : tm0;
         const int z = tile / (p.tiles_n * p.tiles_m);
         const int zb = (p.z_map && p.zmap_b) ? p.z_map[z] : z;
+        if (p.gate) {
+          // rows of this tile exist once the producer has passed the tile's last (first, when walking backwards) time step
+          int ts = p.tm_reverse ? (tm * GEMM_BM) / p.gate_rows_per_step : (tm * GEMM_BM + GEMM_BM - 1) / p.gate_rows_per_step;
+          if (ts > p.gate_steps - 1) ts = p.gate_steps - 1;
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(p.gate + ts) < p.gate_need) {
+            __nanosleep(64);
+            if (++spins > (1u << 26)) __trap();
+          }
+          asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy writes of the producer -> TMA (async proxy) reads
+        }
         for (int kc = 0; kc < p.k_iters; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * GEMM_STAGE_BYTES;
@@ -170,7 +182,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tn = tile % p.tiles_n;
-      const int tm = (tile / p.tiles_n) % p.tiles_m;
+      const int tm0 = (tile / p.tiles_n) % p.tiles_m;
+      const int tm = p.tm_reverse ? p.tiles_m - 1 - tm0 : tm0;
       const int z = tile / (p.tiles_n * p.tiles_m);
       const int zb = p.z_map ? p.z_map[z] : z;
       long long m;
@@ -254,8 +267,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
       tc_fence_before();
+      if (p.done) __threadfence();             // this lane's stores of the tile are visible at gpu scope before the count below
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        mbar_arrive(&tempty_bar[acc]);
+        if (p.done) red_release_add(p.done + tm, 1);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -35,12 +35,18 @@ struct GemmSpec {
   long long bias_zstride = 0;
   float keep = 1.0f;
   unsigned long long seed = 0, rng_offset = 0;
+  // gating (see gemm_params.h); max_ctas > 0 caps the grid (a gated GEMM runs beside a persistent recurrence kernel on spare SMs)
+  const int* gate = nullptr;
+  int gate_need = 0, gate_rows_per_step = 0, gate_steps = 0;
+  int* done = nullptr;
+  int tm_reverse = 0, max_ctas = 0;
 };
 
 struct GemmPlan {
   CUtensorMap ta, tb;
   GemmParams p;
   int a_mn, b_mn, epi, out_bf16;
+  int max_ctas;
 };
 
 int gemm_plan_build(GemmPlan* pl, const GemmSpec& s);

@@ -20,6 +20,16 @@ struct GemmParams {
   int zmap_b;               // ... and also the B-operand problem index
   float keep;               // EPI_DAY dropout keep probability (1 => no dropout)
   unsigned long long seed, rng_offset;
+  // Gating against a concurrently running producer / consumer (the whole-stack recurrence kernels, gru_stack.cuh).  Rows of
+  // a K-major A operand are time-major (row = t * gate_rows_per_step + trial).  Before loading M-tile tm the TMA producer
+  // waits until gate[t] >= gate_need for the LAST time step the tile touches (first one when tm_reverse: the backward
+  // recurrence walks time downwards); after an M-tile's output is stored every epilogue warp adds 1 to done[tm].
+  const int* gate;          // nullable: per-time-step progress counters of the producer
+  int gate_need;
+  int gate_rows_per_step;   // Bpad
+  int gate_steps;           // T'
+  int* done;                // nullable: per-M-tile completion counters (consumer waits for 4 * tiles_n)
+  int tm_reverse;           // walk the M-tiles from the last to the first
 };
 
 }  // namespace b2t

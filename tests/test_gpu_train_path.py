@@ -166,18 +166,23 @@ def _random_params(E, cfg, seed):
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,bg_cap,chunks,nsub,H", [(64, 64, 3, 1, 192), (64, 32, 2, 0, 192), (64, 32, 2, 1, 192), (64, 32, 1, 2, 192), (64, 16, 1, 1, 192),
                                                     (64, 16, 3, 4, 192), (32, 64, 2, 0, 192), (128, 64, 3, 1, 192), (128, 32, 2, 0, 192), (40, 64, 2, 0, 192),
-                                                    (64, 32, 3, 0, 256), (64, 16, 2, 0, 256), (24, 32, 1, 0, 256), (32, 32, 2, 0, 512)])
+                                                    (64, 32, 3, 0, 256), (64, 16, 2, 0, 256), (24, 32, 1, 0, 256), (32, 32, 2, 0, 512),
+                                                    # whole-stack persistent kernels (gru_stack.cuh; default when H % 256 == 0): bg_cap < 0 selects them
+                                                    (64, -1, 0, 0, 256), (128, -1, 0, 0, 256), (24, -1, 0, 0, 256), (40, -1, 0, 0, 256), (96, -1, 0, 0, 256),
+                                                    (16, -1, 0, 0, 512), (64, -1, 0, 0, 512)])
 def test_wide_batch_train_step_vs_oracle(E, monkeypatch, B, bg_cap, chunks, nsub, H):
     """Batch-group widths 16 / 32 / 64 of the recurrence kernels (forward: trials per CTA = MMA N; backward: partial
     exchange geometry), several time chunks, against the numpy oracle evaluated on the same inputs.  H = 192 runs the
     contraction-split backward kernel (two 128-row output blocks, the second one partial); H = 256 / 512 run the
     two-dimensional one (gru_rec_bwd2.cuh: dG all-gather + 4-way partial reduction)."""
     import gru_ctc_oracle as O
-    monkeypatch.setenv("B2T_REC_BG_FWD", str(bg_cap)); monkeypatch.setenv("B2T_REC_BG_BWD", str(bg_cap))
-    monkeypatch.setenv("B2T_REC_CHUNKS", str(chunks))
+    monkeypatch.setenv("B2T_STACK", "1" if bg_cap < 0 else "0")       # bg_cap >= 0: the per-(layer, time chunk) launches of gru_rec.cuh
+    if bg_cap >= 0:
+        monkeypatch.setenv("B2T_REC_BG_FWD", str(bg_cap)); monkeypatch.setenv("B2T_REC_BG_BWD", str(bg_cap))
+        monkeypatch.setenv("B2T_REC_CHUNKS", str(chunks))
     if nsub:                                                     # batch groups sharing one CTA in the backward recurrence (0 = default choice)
         monkeypatch.setenv("B2T_REC_NSUB_BWD", str(nsub))
-    if H % 256 == 0:                                             # opt-in two-dimensional backward kernel
+    if H % 256 == 0 and bg_cap >= 0:                             # opt-in two-dimensional backward kernel
         monkeypatch.setenv("B2T_REC_BWD2", "1")
     D, L, n_days, T = 32, 3, 4, 74
     cfg = E.make_config(D, H, L, n_days, 41, 14, 4, 0.0, 0.0)
