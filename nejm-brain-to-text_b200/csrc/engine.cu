@@ -133,6 +133,7 @@ struct Carver {
 
 constexpr int LDL = 64;        // pitch (elements) of logits / dlogits rows: 128 B in bf16, TMA friendly
 constexpr int MAX_CHUNKS = 8;  // time chunks of the layer wave-front
+constexpr size_t REC_SMEM_BYTES = 120 * 1024;   // recurrence kernels request at least this much shared memory: one CTA per SM (they own the TMEM)
 constexpr int MAX_LANES = 5;   // concurrent recurrence launches (side streams)
 
 struct LayerBuf {
@@ -347,6 +348,19 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
          cudaEventCreateWithFlags(&e->ev_dx[i], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; i < MAX_CHUNKS && ok; ++i) ok = cudaEventCreateWithFlags(&e->ev_g0[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { fail(B2T_ERR_CUDA, "stream/event creation failed"); b2t_engine_destroy(e); return nullptr; }
+  // kernels that wait on each other while running must all be loaded beforehand (lazy module loading would dead-lock them)
+  {
+    cudaError_t pe = gemm_preload();
+    if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_fwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::fwd_smem_bytes(e->H)));
+    if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_fwd_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 1>::fwd_smem_bytes(e->H)));
+    if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_fwd_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<16, 1>::fwd_smem_bytes(e->H)));
+    if (pe == cudaSuccess && e->H % 256 == 0) {
+      pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::bwd_smem_bytes(e->H)));
+      if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 1>::bwd_smem_bytes(e->H)));
+      if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<16, 1>::bwd_smem_bytes(e->H)));
+    }
+    if (pe != cudaSuccess) { fail(B2T_ERR_CUDA, "kernel preload failed: %s", cudaGetErrorString(pe)); b2t_engine_destroy(e); return nullptr; }
+  }
   if (training) {
     std::vector<Segment> hs;
     std::vector<ChunkRef> hc;
@@ -657,7 +671,6 @@ extern "C" int b2t_output_frames(const b2t_config* cfg, int T, int smooth_mode, 
 // The recurrence kernels allocate all 512 TMEM columns, so two CTAs must never share an SM: requesting more than
 // half of the shared memory forces one CTA per SM.  Cooperative launch guarantees that every CTA of the grid is
 // co-resident (they spin on each other's flags).
-constexpr size_t REC_SMEM_BYTES = 120 * 1024;
 template <int BG>
 static cudaError_t launch_rec_fwd_t(const RecFwdParams& p, int grid, cudaStream_t st) {
   const size_t smem = std::max(REC_SMEM_BYTES, RecCfg<BG>::fwd_smem_bytes(p.H));
@@ -833,7 +846,7 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
     StackFwdParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.H = H; sp.Bpad = Bp; sp.T = Tp; sp.n_slices = H / 32; sp.n_layers = L; sp.n_cgroups = e->stk_ncg;
-    sp.poll_delay = e->poll_delay; sp.seed = a->seed; sp.trace = e->trace;
+    sp.poll_delay = e->poll_delay; sp.seed = a->seed; sp.trace = e->trace; sp.trace_cta = env_int("B2T_TRACE_CTA_FWD", 0);
     for (int l = 0; l < L; ++l) {
       const std::string sl = std::to_string(l);
       StackFwdLayer& y = sp.lay[l];
@@ -1075,7 +1088,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     StackBwdParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.H = H; sp.Bpad = Bp; sp.T = Tp; sp.n_layers = L; sp.n_cgroups = e->stk_ncg; sp.n_valid = e->B;
-    sp.poll_delay = e->poll_delay_b; sp.seed = e->seed; sp.trace = e->trace;
+    sp.poll_delay = e->poll_delay_b; sp.seed = e->seed; sp.trace = e->trace; sp.trace_cta = env_int("B2T_TRACE_CTA_BWD", (L - 1) * (H / 32) * e->stk_ncg);
     for (int l = 0; l < L; ++l) {
       const std::string sl = std::to_string(l);
       StackBwdLayer& y = sp.lay[l];
@@ -1280,6 +1293,13 @@ extern "C" int b2t_gemm_bf16(const void* A, const void* B, void* C, int M, int N
   s.A = A; s.lda = a_mn ? M : K;
   s.B = B; s.ldb = b_mn ? N : K;
   s.C = C; s.ldc = N; s.bias = bias;
+  // bring-up knobs of the test hook: cap the grid like a gated GEMM beside the recurrence, and exercise the completion counters
+  s.max_ctas = env_int("B2T_GEMM_MAXCTAS", 0);
+  static int* dbg_done = nullptr;
+  if (env_int("B2T_GEMM_DONE", 0) && !a_mn) {
+    if (!dbg_done) { cudaMalloc(&dbg_done, 1 << 20); cudaMemset(dbg_done, 0, 1 << 20); }
+    s.done = dbg_done;
+  }
   GemmPlan pl;
   int rc = gemm_plan_build(&pl, s);
   if (rc) return fail(B2T_ERR_CUDA, "gemm plan failed (%d)", rc);

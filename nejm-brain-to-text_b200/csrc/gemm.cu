@@ -16,9 +16,10 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <bool A_MN, bool B_MN, int EPI, typename OutT>
-static cudaError_t launch_variant(const GemmPlan& pl, cudaStream_t st) {
-  auto kern = gemm_bf16_kernel<A_MN, B_MN, EPI, OutT>;
+template <bool A_MN, bool B_MN, int EPI, typename OutT, int BN>
+static cudaError_t launch_bn(const GemmPlan& pl, cudaStream_t st) {
+  auto kern = gemm_bf16_kernel<A_MN, B_MN, EPI, OutT, BN>;
+  constexpr int GEMM_SMEM_BYTES = GemmTile<BN>::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
@@ -31,6 +32,35 @@ static cudaError_t launch_variant(const GemmPlan& pl, cudaStream_t st) {
   if (pl.max_ctas > 0 && grid > pl.max_ctas) grid = pl.max_ctas;
   kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(pl.ta, pl.tb, pl.p);
   return cudaGetLastError();
+}
+template <bool A_MN, bool B_MN, int EPI, typename OutT>
+static cudaError_t launch_variant(const GemmPlan& pl, cudaStream_t st) {
+  return pl.bn == 256 ? launch_bn<A_MN, B_MN, EPI, OutT, 256>(pl, st) : launch_bn<A_MN, B_MN, EPI, OutT, 128>(pl, st);
+}
+
+// With lazy module loading (the CUDA 12 default) the first launch of a kernel loads it, which can need a device-wide
+// synchronisation: a gated GEMM launched for the first time while the persistent recurrence kernel is already waiting for its
+// output would then dead-lock.  Touch every variant once, up front (cudaFuncSetAttribute loads the function).
+template <bool A_MN, bool B_MN, int EPI, typename OutT>
+static cudaError_t preload_variant() {
+  cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, EPI, OutT, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTile<128>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, EPI, OutT, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTile<256>::kSmemBytes);
+}
+cudaError_t gemm_preload() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e;
+  if ((e = preload_variant<false, false, EPI_STORE, float>()) != cudaSuccess) return e;
+  if ((e = preload_variant<false, false, EPI_STORE, __nv_bfloat16>()) != cudaSuccess) return e;
+  if ((e = preload_variant<false, true, EPI_STORE, float>()) != cudaSuccess) return e;
+  if ((e = preload_variant<false, true, EPI_STORE, __nv_bfloat16>()) != cudaSuccess) return e;
+  if ((e = preload_variant<false, true, EPI_DAY, __nv_bfloat16>()) != cudaSuccess) return e;
+  if ((e = preload_variant<true, true, EPI_STORE, float>()) != cudaSuccess) return e;
+  if ((e = preload_variant<true, true, EPI_ATOMIC, float>()) != cudaSuccess) return e;
+  if ((e = preload_variant<true, true, EPI_ACCUM, float>()) != cudaSuccess) return e;
+  done = true;
+  return cudaSuccess;
 }
 
 cudaError_t gemm_run(const GemmPlan& pl, cudaStream_t st) {
@@ -70,7 +100,17 @@ int gemm_plan_build(GemmPlan* pl, const GemmSpec& s) {
   p.gate_steps = s.gate_steps; p.done = s.done; p.tm_reverse = s.tm_reverse;
   pl->max_ctas = s.max_ctas;
   if ((s.gate || s.done) && (s.a_mn || s.a_rin > 0 || p.nz != 1)) return -20;   // gating is defined for plain K-major A (time-major rows) only
-  p.tiles_n = ceil_div(s.N, GEMM_BN);
+  // tile width: 256 when the columns divide evenly and (after the M decomposition below) enough tiles remain to fill the chip
+  int bn = 128;
+  {
+    const int force = getenv("B2T_GEMM_BN") ? atoi(getenv("B2T_GEMM_BN")) : 0;   // bring-up / test override
+    const long long rows = s.a_mn ? s.M : (s.a_rin > 0 ? (long long)s.a_rin * s.a_rout : s.M);
+    const long long tiles256 = (long long)ceil_div(rows, GEMM_BM) * ceil_div(s.N, 256) * p.nz;
+    if (s.N % 256 == 0 && s.epi != EPI_ATOMIC && (tiles256 >= num_sms() || s.gate || s.done)) bn = 256;
+    if (force == 128 || (force == 256 && s.N % 256 == 0)) bn = force;
+  }
+  pl->bn = bn;
+  p.tiles_n = ceil_div(s.N, bn);
   p.k_bin = 1; p.k_rin_blocks = 1; p.a_bin = 1; p.a_rin_blocks = 1; p.a_rin = 1; p.a_rout = s.M;
 
   // ---- contraction decomposition (MN-major operands index the contraction by stored rows)
@@ -125,7 +165,7 @@ int gemm_plan_build(GemmPlan* pl, const GemmSpec& s) {
   if (!s.b_mn) {
     dims[0] = s.K; dims[1] = 1; dims[2] = s.N; dims[3] = nzb;
     str[0] = s.ldb; str[1] = s.ldb; str[2] = s.b_zstride > 0 ? s.b_zstride : 8;
-    box[0] = 64; box[1] = 1; box[2] = GEMM_BN; box[3] = 1;
+    box[0] = 64; box[1] = 1; box[2] = bn; box[3] = 1;
   } else {
     dims[0] = s.N; dims[1] = k_rin; dims[2] = k_rout; dims[3] = nzb;
     str[0] = s.k_rin > 0 ? s.b_rin_stride : s.ldb;

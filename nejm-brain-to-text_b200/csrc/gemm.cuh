@@ -22,53 +22,39 @@
 namespace b2t {
 
 
-constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64, GEMM_STAGES = 6;
-constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2, GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;
-constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_BM = 128, GEMM_BK = 64;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
+// Tile width BN = 128 (6-stage ring) or 256 (4-stage ring).  The main loop is bound by what one SM can pull out of L2
+// (~65 B/clk measured): a 128 x 256 tile needs 48 KB per 64-deep slice for twice the MMA work of a 128 x 128 tile's 32 KB.
+template <int BN> struct GemmTile {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kBBytes = BN * GEMM_BK * 2;
+  static constexpr int kStageBytes = GEMM_A_BYTES + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/ + 4 * BN * 4 /*bias*/;
+};
+constexpr int GEMM_EPI_PITCH = 36;      // floats per row of an epilogue warp's 32 x 32 staging tile (16-byte aligned rows, conflict-free float4 access)
 constexpr int GEMM_THREADS = 192;
 
 
-template <typename OutT>
-__device__ __forceinline__ void store_row32(OutT* dst, const float (&f)[32], int ncols, bool vec_ok);
-
-template <>
-__device__ __forceinline__ void store_row32<float>(float* dst, const float (&f)[32], int ncols, bool vec_ok) {
-  if (ncols >= 32 && vec_ok) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) dst[i] = f[i];
-  }
+template <typename OutT> __device__ __forceinline__ void store_vec4(OutT* dst, const float (&w)[4]);
+template <> __device__ __forceinline__ void store_vec4<float>(float* dst, const float (&w)[4]) {
+  *reinterpret_cast<float4*>(dst) = make_float4(w[0], w[1], w[2], w[3]);
 }
-template <>
-__device__ __forceinline__ void store_row32<__nv_bfloat16>(__nv_bfloat16* dst, const float (&f)[32], int ncols, bool vec_ok) {
-  if (ncols >= 32 && vec_ok) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(f[8 * i], f[8 * i + 1]);
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(f[8 * i + 2], f[8 * i + 3]);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(f[8 * i + 4], f[8 * i + 5]);
-      __nv_bfloat162 p3 = __floats2bfloat162_rn(f[8 * i + 6], f[8 * i + 7]);
-      u.x = *reinterpret_cast<uint32_t*>(&p0);
-      u.y = *reinterpret_cast<uint32_t*>(&p1);
-      u.z = *reinterpret_cast<uint32_t*>(&p2);
-      u.w = *reinterpret_cast<uint32_t*>(&p3);
-      reinterpret_cast<uint4*>(dst)[i] = u;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) dst[i] = __float2bfloat16_rn(f[i]);
-  }
+template <> __device__ __forceinline__ void store_vec4<__nv_bfloat16>(__nv_bfloat16* dst, const float (&w)[4]) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(w[0], w[1]), hi = __floats2bfloat162_rn(w[2], w[3]);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = u;
 }
+template <typename OutT> __device__ __forceinline__ void store_one(OutT* dst, float w);
+template <> __device__ __forceinline__ void store_one<float>(float* dst, float w) { *dst = w; }
+template <> __device__ __forceinline__ void store_one<__nv_bfloat16>(__nv_bfloat16* dst, float w) { *dst = __float2bfloat16_rn(w); }
 
-template <bool A_MN, bool B_MN, int EPI, typename OutT>
+template <bool A_MN, bool B_MN, int EPI, typename OutT, int GEMM_BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  constexpr int GEMM_STAGES = GemmTile<GEMM_BN>::kStages, GEMM_STAGE_BYTES = GemmTile<GEMM_BN>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
@@ -135,8 +121,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * GEMM_BK, rb * p.a_bin, ro * (GEMM_BM / p.a_bin), z);
           }
           if (B_MN) {
-            tma_load_4d(sb, &tmap_b, &full_bar[stage], tn * GEMM_BN, kb * p.k_bin, ko * (64 / p.k_bin), zb);
-            tma_load_4d(sb + 8192, &tmap_b, &full_bar[stage], tn * GEMM_BN + 64, kb * p.k_bin, ko * (64 / p.k_bin), zb);
+#pragma unroll
+            for (int nb = 0; nb < GEMM_BN / 64; ++nb)      // 64-column blocks, 8 KB apart (the MN-major descriptor's leading-dimension stride)
+              tma_load_4d(sb + nb * 8192, &tmap_b, &full_bar[stage], tn * GEMM_BN + nb * 64, kb * p.k_bin, ko * (64 / p.k_bin), zb);
           } else {
             tma_load_4d(sb, &tmap_b, &full_bar[stage], kc * GEMM_BK, 0, tn * GEMM_BN, zb);
           }
@@ -176,8 +163,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
+    // Phase 1 (thread = accumulator row, tcgen05.ld gives 32 consecutive columns of it): bias / activation / dropout, then the
+    // 32 x 32 block of the warp goes through a padded shared-memory tile.  Phase 2 (8 lanes = 128 contiguous bytes of one output
+    // row, 4 rows per instruction): coalesced stores.  Writing rows straight from phase 1 touches 32 different lines per store
+    // instruction (one 16-byte piece each) and made K = 768 GEMMs epilogue-bound: 7.6 us per 128 x 128 tile against 1.6 us of MMAs.
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;             // row inside the 128-row tile
+    const int r = q * 32 + lane;             // row inside the 128-row tile (phase 1)
+    float* stg = reinterpret_cast<float*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES + 256) + q * (32 * GEMM_EPI_PITCH);
+    float* bias_s = reinterpret_cast<float*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES + 256) + 4 * 32 * GEMM_EPI_PITCH + q * GEMM_BN;
+    const int sub_row = lane >> 3, cg = (lane & 7) * 4;   // phase 2: row within a group of four, first of this lane's four columns
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -186,92 +180,133 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int tm = p.tm_reverse ? p.tiles_m - 1 - tm0 : tm0;
       const int z = tile / (p.tiles_n * p.tiles_m);
       const int zb = p.z_map ? p.z_map[z] : z;
-      long long m;
-      bool row_ok;
-      if (A_MN) {
-        m = (long long)tm * GEMM_BM + r;
-        row_ok = m < p.M;
-      } else {
+      auto out_row = [&](int rr, bool& ok) -> long long {   // output row (and validity) of tile row rr
+        if (A_MN) {
+          const long long m = (long long)tm * GEMM_BM + rr;
+          ok = m < p.M;
+          return m;
+        }
         const int rb = tm % p.a_rin_blocks, ro = tm / p.a_rin_blocks;
-        const int rin = rb * p.a_bin + (r % p.a_bin);
-        const int rout = ro * (GEMM_BM / p.a_bin) + (r / p.a_bin);
-        m = (long long)rout * p.a_rin + rin;
-        row_ok = rout < p.a_rout;
-      }
+        const int rin = rb * p.a_bin + (rr % p.a_bin);
+        const int rout = ro * (GEMM_BM / p.a_bin) + (rr / p.a_bin);
+        ok = rout < p.a_rout;
+        return (long long)rout * p.a_rin + rin;
+      };
+      bool row_ok;
+      const long long m = out_row(r, row_ok);
       const int zc = (EPI == EPI_ATOMIC) ? zb : z;
-      OutT* crow = reinterpret_cast<OutT*>(p.C) + (long long)zc * p.c_zstride + m * p.ldc;
+      OutT* cbase = reinterpret_cast<OutT*>(p.C) + (long long)zc * p.c_zstride;
       const float* bias = p.bias ? p.bias + (long long)zb * p.bias_zstride : nullptr;
-      const bool vec_ok = (p.ldc % (16 / (int)sizeof(OutT))) == 0 &&
-                          ((reinterpret_cast<uintptr_t>(p.C) + (size_t)zc * p.c_zstride * sizeof(OutT)) & 15) == 0;
+      const bool vec_ok = (p.ldc % (16 / (int)sizeof(OutT))) == 0 && (reinterpret_cast<uintptr_t>(cbase) & 15) == 0;
+      // phase-2 rows of this lane: tile row q*32 + 4*i + sub_row, i = 0..7
+      long long m2[8];
+      uint32_t ok2 = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        bool ok;
+        m2[i] = out_row(q * 32 + 4 * i + sub_row, ok);
+        ok2 |= (ok ? 1u : 0u) << i;
+      }
 
+      // this tile's bias row -> the warp's shared-memory slice while the MMAs still run (a per-chunk global load sat on the
+      // epilogue's critical path: ~600 cycles of L2 latency for each of the 4-8 chunks of a tile)
+      if (bias) {
+#pragma unroll
+        for (int i = 0; i < GEMM_BN / 32; ++i) {
+          const int n = tn * GEMM_BN + i * 32 + lane;
+          bias_s[i * 32 + lane] = n < p.N ? __ldg(bias + n) : 0.0f;
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < GEMM_BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BN + c0, v);
-        tmem_ld_wait();
+      __syncwarp();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BN;
+      uint32_t va[32], vb[32];
+      tmem_ld32(tacc, va);
+#pragma unroll
+      for (int ci = 0; ci < GEMM_BN / 32; ++ci) {
+        const int c0 = ci * 32;
+        uint32_t (&v)[32] = (ci & 1) ? vb : va;
+        tmem_ld_wait32(v);
+        if (ci + 1 < GEMM_BN / 32) tmem_ld32(tacc + c0 + 32, (ci & 1) ? va : vb);   // next chunk in flight during this one's stores
+        if (c0 + 32 == GEMM_BN) {            // accumulator fully read: hand it back to the MMA issuer before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
         const int n0 = tn * GEMM_BN + c0;
         const int ncols = p.N - n0;          // columns of this 32-chunk that exist
-        if (row_ok && ncols > 0) {
-          float f[32];
+        if (ncols <= 0) continue;            // (warp-uniform)
+        float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (bias) {
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (bias) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncols) f[i] += __ldg(bias + n0 + i);
+          for (int i = 0; i < 8; ++i) {       // broadcast reads of the prefetched row
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * i);
+            f[4 * i] += bv.x; f[4 * i + 1] += bv.y; f[4 * i + 2] += bv.z; f[4 * i + 3] += bv.w;
           }
-          if (EPI == EPI_DAY) {
-            // softsign (rnn_model.py:99) then inverted dropout (rnn_model.py:102-103)
-            const float inv_keep = 1.0f / p.keep;
-            const unsigned long long e0 = (unsigned long long)zc * p.c_zstride + (unsigned long long)m * p.ldc + n0;
+        }
+        if (EPI == EPI_DAY) {
+          // softsign (rnn_model.py:99) then inverted dropout (rnn_model.py:102-103)
+          const float inv_keep = 1.0f / p.keep;
+          const unsigned long long e0 = (unsigned long long)zc * p.c_zstride + (unsigned long long)m * p.ldc + n0;
 #pragma unroll
-            for (int i4 = 0; i4 < 8; ++i4) {
-              uint4 rnd = make_uint4(0, 0, 0, 0);
-              if (p.keep < 1.0f) {
-                const unsigned long long c = (e0 >> 2) + i4 + p.rng_offset;
-                rnd = philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x0da1u, 0), make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
-              }
-              const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+          for (int i4 = 0; i4 < 8; ++i4) {
+            uint4 rnd = make_uint4(0, 0, 0, 0);
+            if (p.keep < 1.0f) {
+              const unsigned long long c = (e0 >> 2) + i4 + p.rng_offset;
+              rnd = philox4x32(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x0da1u, 0), make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32)));
+            }
+            const uint32_t rr[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float y = f[4 * i4 + j];
-                y = y / (1.0f + fabsf(y));
-                if (p.keep < 1.0f) y = (u32_to_unit(rr[j]) < p.keep) ? y * inv_keep : 0.0f;
-                f[4 * i4 + j] = y;
-              }
+            for (int j = 0; j < 4; ++j) {
+              float y = f[4 * i4 + j];
+              y = y / (1.0f + fabsf(y));
+              if (p.keep < 1.0f) y = (u32_to_unit(rr[j]) < p.keep) ? y * inv_keep : 0.0f;
+              f[4 * i4 + j] = y;
             }
           }
-          if (EPI == EPI_ACCUM) {
-            float* cf = reinterpret_cast<float*>(crow) + n0;
-            if (ncols >= 32 && vec_ok) {
+        }
+        // ---- through the warp's staging tile
+        __syncwarp();                        // the previous chunk's phase-2 reads are done
+        {
+          float4* dst = reinterpret_cast<float4*>(stg + lane * GEMM_EPI_PITCH);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 o = reinterpret_cast<const float4*>(cf)[i];
-                f[4 * i] += o.x; f[4 * i + 1] += o.y; f[4 * i + 2] += o.z; f[4 * i + 3] += o.w;
-              }
-            } else {
+          for (int i = 0; i < 8; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        }
+        __syncwarp();
+        const int nc4 = ncols - cg;          // columns left from this lane's first column
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < ncols) f[i] += cf[i];
-            }
-          }
+        for (int i = 0; i < 8; ++i) {
+          if (!((ok2 >> i) & 1u) || nc4 <= 0) continue;
+          const float4 o = *reinterpret_cast<const float4*>(stg + (4 * i + sub_row) * GEMM_EPI_PITCH + cg);
+          float w[4] = {o.x, o.y, o.z, o.w};
+          OutT* dst = cbase + m2[i] * p.ldc + n0 + cg;
           if (EPI == EPI_ATOMIC) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncols) atomicAdd(reinterpret_cast<float*>(crow) + n0 + i, f[i]);
+            for (int k = 0; k < 4; ++k)
+              if (k < nc4) atomicAdd(reinterpret_cast<float*>(dst) + k, w[k]);
+          } else if (nc4 >= 4 && vec_ok) {
+            if (EPI == EPI_ACCUM) {
+              const float4 old = *reinterpret_cast<const float4*>(dst);
+              w[0] += old.x; w[1] += old.y; w[2] += old.z; w[3] += old.w;
+            }
+            store_vec4<OutT>(dst, w);
           } else {
-            store_row32<OutT>(crow + n0, f, ncols, vec_ok);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < nc4) {
+                if (EPI == EPI_ACCUM) w[k] += reinterpret_cast<const float*>(dst)[k];
+                store_one<OutT>(dst + k, w[k]);
+              }
           }
         }
       }
-      tc_fence_before();
-      if (p.done) __threadfence();             // this lane's stores of the tile are visible at gpu scope before the count below
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&tempty_bar[acc]);
-        if (p.done) red_release_add(p.done + tm, 1);
+      if (p.done) {
+        __threadfence();                     // this lane's stores of the tile are visible at gpu scope before the count below
+        __syncwarp();
+        if (lane == 0) red_release_add(p.done + tm, 1);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }

@@ -46,11 +46,12 @@ struct GemmPlan {
   CUtensorMap ta, tb;
   GemmParams p;
   int a_mn, b_mn, epi, out_bf16;
-  int max_ctas;
+  int max_ctas, bn;
 };
 
 int gemm_plan_build(GemmPlan* pl, const GemmSpec& s);
 cudaError_t gemm_run(const GemmPlan& pl, cudaStream_t st);
+cudaError_t gemm_preload();   // load every kernel variant now (see gemm.cu)
 int num_sms();
 
 }  // namespace b2t

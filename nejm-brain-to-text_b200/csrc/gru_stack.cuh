@@ -46,6 +46,7 @@ struct StackFwdLayer {
 struct StackFwdParams {
   int H, Bpad, T, n_slices, n_layers, n_cgroups;   // n_cgroups: CTA-level batch groups (each CTA hosts NSUB groups of BG trials)
   int poll_delay;
+  int trace_cta;                  // CTA whose group 0 writes the cycle trace
   unsigned long long seed;
   long long* trace;
   StackFwdLayer lay[STACK_MAX_LAYERS];
@@ -91,6 +92,23 @@ __device__ __forceinline__ float4 ldcg_f4(const float* p) {
   return v;
 }
 
+// Probe before staging.  A full polling round moves the whole operand (48 KB per CTA at BG = 32) through L2 whether or not the
+// peers have published; with every layer resident that wasted traffic starves the gated GEMMs.  So the loader threads first
+// poll one 16-byte unit per (producer CTA, producer epilogue warp[, gate]) -- a few KB per round -- and only when every probe
+// has been seen (named barrier over the loader warps) do they stage the operand, which still checks every word.
+template <int NLOAD_THREADS, typename AddrF>
+__device__ __forceinline__ void probe_until_published(int n_probe, int lt, AddrF addr) {
+  for (int i = lt; i < n_probe; i += NLOAD_THREADS) {
+    const uint8_t* a = addr(i);
+    uint32_t spins = 0;
+    while (has_sentinel(ld_l2_v4(a))) {
+      __nanosleep(40);
+      if (++spins > REC_MAX_SPINS) __trap();
+    }
+  }
+  asm volatile("bar.sync 2, %0;" ::"n"(NLOAD_THREADS) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 template <int BG, int NSUB>
 __global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads, 1)
@@ -118,7 +136,7 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
   const int j0 = slice * REC_US;
   const int a_cols = p.H / 2;
   const bool is_loader = warp == 0 || warp >= 2 + Cfg::kEpiWarps;
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_cta;
 #define STK_TRACE(step, slot) do { if (tracing) p.trace[(step) * 8 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
@@ -175,6 +193,12 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
             const long long t0 = clock64();
             while (clock64() - t0 < p.poll_delay) {}
           }
+        }
+        if (t > 0) {   // probe (producer slice, producer epilogue warp): its lanes 0..1 own units 0..7 of trial 4 * warp
+          const __nv_bfloat16* hrow = L.hseq + ((size_t)t * p.Bpad + b0) * p.H;
+          probe_until_published<Cfg::kLoadThreads>(p.n_slices * Cfg::kEpiWarps, lt, [&](int i) {
+            return reinterpret_cast<const uint8_t*>(hrow + (size_t)(4 * (i % Cfg::kEpiWarps)) * p.H + (i / Cfg::kEpiWarps) * REC_US);
+          });
         }
         const uint8_t* g = reinterpret_cast<const uint8_t*>(L.hseq + ((size_t)t * p.Bpad + b0 + row) * p.H) + seg * 16;   // slot t = h_{t-1}
         uint8_t* sdst = sH + sub * SH_SUB + (size_t)buf * KC * CHUNK_BYTES + soff;
@@ -351,6 +375,7 @@ struct StackBwdLayer {
 struct StackBwdParams {
   int H, Bpad, T, n_layers, n_cgroups, n_valid;
   int poll_delay;
+  int trace_cta;
   unsigned long long seed;
   long long* trace;
   StackBwdLayer lay[STACK_MAX_LAYERS];
@@ -389,7 +414,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
   const StackBwdLayer& L = p.lay[layer];
   const int j0 = mb * 128 + kq * REC_US;
   const bool is_loader = warp == 0 || warp >= 2 + Cfg::kEpiWarps;
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_cta;
 #define STK_TRACE(step, slot) do { if (tracing) p.trace[((size_t)p.T + (step)) * 8 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
@@ -448,6 +473,14 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
           const long long t0 = clock64();
           while (clock64() - t0 < p.poll_delay) {}
         }
+        {   // probe (producer CTA of this contraction quarter, its epilogue warp, gate)
+          const __nv_bfloat16* grow = L.dGh + ((size_t)t * p.Bpad + b0) * 3 * p.H + kq * KQ;
+          const int npc = KQ / REC_US;
+          probe_until_published<Cfg::kLoadThreads>(npc * Cfg::kEpiWarps * 3, lt, [&](int i) {
+            const int gate = i % 3, w = (i / 3) % Cfg::kEpiWarps, pc = i / (3 * Cfg::kEpiWarps);
+            return reinterpret_cast<const uint8_t*>(grow + (size_t)(4 * w) * 3 * p.H + (size_t)gate * p.H + pc * REC_US);
+          });
+        }
         const uint8_t* g = reinterpret_cast<const uint8_t*>(L.dGh + ((size_t)t * p.Bpad + b0 + row) * 3 * p.H + kq * KQ) + seg * 16;
         auto chunk_addr = [&](int cc) {
           const int gate = cc / CPG, ci = cc - gate * CPG;
@@ -498,7 +531,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
   } else {
     // ---------------- epilogue.  Per (step, group): phase A = reduce partials of the previous step, gate math, publish dG_t;
     // phase B = drain the accumulator of the group's MMA into the four partial blocks.  The phases of the two groups are
-    // interleaved A(s,0) B(s-1,1) A(s,1) B(s,0) so that the wait inside B (dG all-gather + MMA) is covered by the other group's A.
+    // interleaved A(s,0) B(s-1,1) B(s,0) A(s,1).
     const int e = threadIdx.x - 64;
     const int ew = e >> 5;
     const int q = warp & 3;
@@ -673,10 +706,12 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
         phase_a(s, 0);
         phase_b(s, 0);
       } else {
+        // In the steady state the two groups run half a period apart: A(s,0) and B(s-1,1) are due together, then B(s,0) and A(s,1).
+        // (A phase right behind the B phase it depends on -- B(s-1,1) A(s,1) -- would stall for a full L2 hand-over.)
         phase_a(s, 0);
         if (s > 0) phase_b(s - 1, 1);
-        phase_a(s, 1);
         phase_b(s, 0);
+        phase_a(s, 1);
       }
     }
     if constexpr (NSUB == 2) phase_b(p.T - 1, 1);

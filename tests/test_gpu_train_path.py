@@ -19,9 +19,13 @@ def E(pkg):
     return b2t_pkg.submodule("engine")
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 41, 768), (97 * 16, 192, 448), (130, 136, 72)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 41, 768), (97 * 16, 192, 448), (130, 136, 72),
+                                   # 128 x 256 tiles (forced below): few / many contraction slices, ragged row count
+                                   (256, 256, 256), (1024, 768, 256), (200, 512, 768), (6208, 768, 2304)])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
-def test_gemm_vs_torch(E, M, N, K, a_mn, b_mn):
+def test_gemm_vs_torch(E, M, N, K, a_mn, b_mn, monkeypatch):
+    if N % 256 == 0:
+        monkeypatch.setenv("B2T_GEMM_BN", "256")
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
     B = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
