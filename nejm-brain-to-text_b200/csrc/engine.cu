@@ -475,7 +475,7 @@ static int build_plans(b2t_engine* e) {
     e->stack = ok ? 1 : 0;
     if (ok) {
       e->stk_BG = bg; e->stk_NSUB = nsub; e->stk_ncg = ng / nsub; e->stk_grid = grid;
-      e->stk_need = (H / 32) * ng * (bg / 4);   // epilogue warps of a layer: CTAs x groups per CTA x warps per group
+      e->stk_need = (H / 32) * ng;              // one signal per CTA and batch group of a layer
       e->stk_gemm_ctas = L > 1 ? std::max(1, (num_sms() - grid) / (L - 1)) : 1;
       nch = 1;                                  // no time chunking: the GEMMs beside the recurrence are gated per 128-row tile instead
     }
@@ -721,7 +721,7 @@ static cudaError_t launch_stack_fwd_t(const StackFwdParams& p, int grid, cudaStr
   if (err != cudaSuccess) return err;
   void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_stack_fwd_kernel<BG, NSUB>, dim3(grid), dim3(RecCfg<BG>::kFwdThreads), args, smem, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_stack_fwd_kernel<BG, NSUB>, dim3(grid), dim3(StackCfg<BG, NSUB>::kThreads), args, smem, st);
 }
 template <int BG, int NSUB>
 static cudaError_t launch_stack_bwd_t(const StackBwdParams& p, int grid, cudaStream_t st) {
@@ -730,7 +730,7 @@ static cudaError_t launch_stack_bwd_t(const StackBwdParams& p, int grid, cudaStr
   if (err != cudaSuccess) return err;
   void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_stack_bwd_kernel<BG, NSUB>, dim3(grid), dim3(RecCfg<BG>::kFwdThreads), args, smem, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_stack_bwd_kernel<BG, NSUB>, dim3(grid), dim3(StackCfg<BG, NSUB>::kThreads), args, smem, st);
 }
 static cudaError_t launch_stack_fwd(int BG, int NSUB, const StackFwdParams& p, int grid, cudaStream_t st) {
   if (BG == 32) return NSUB == 2 ? launch_stack_fwd_t<32, 2>(p, grid, st) : launch_stack_fwd_t<32, 1>(p, grid, st);
@@ -846,7 +846,7 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
     StackFwdParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.H = H; sp.Bpad = Bp; sp.T = Tp; sp.n_slices = H / 32; sp.n_layers = L; sp.n_cgroups = e->stk_ncg;
-    sp.poll_delay = e->poll_delay; sp.seed = a->seed; sp.trace = e->trace; sp.trace_cta = env_int("B2T_TRACE_CTA_FWD", 0);
+    sp.poll_delay = env_int("B2T_STACK_POLL_DELAY", 0); sp.seed = a->seed; sp.trace = e->trace; sp.trace_cta = env_int("B2T_TRACE_CTA_FWD", 0);
     for (int l = 0; l < L; ++l) {
       const std::string sl = std::to_string(l);
       StackFwdLayer& y = sp.lay[l];
@@ -1088,7 +1088,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     StackBwdParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.H = H; sp.Bpad = Bp; sp.T = Tp; sp.n_layers = L; sp.n_cgroups = e->stk_ncg; sp.n_valid = e->B;
-    sp.poll_delay = e->poll_delay_b; sp.seed = e->seed; sp.trace = e->trace; sp.trace_cta = env_int("B2T_TRACE_CTA_BWD", (L - 1) * (H / 32) * e->stk_ncg);
+    sp.poll_delay = env_int("B2T_STACK_POLL_DELAY_BWD", 0); sp.seed = e->seed; sp.trace = e->trace; sp.trace_cta = env_int("B2T_TRACE_CTA_BWD", (L - 1) * (H / 32) * e->stk_ncg);
     for (int l = 0; l < L; ++l) {
       const std::string sl = std::to_string(l);
       StackBwdLayer& y = sp.lay[l];

@@ -247,7 +247,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             f[4 * i] += bv.x; f[4 * i + 1] += bv.y; f[4 * i + 2] += bv.z; f[4 * i + 3] += bv.w;
           }
         }
-        if (EPI == EPI_DAY) {
+        if (EPI == EPI_DAY && row_ok) {      // (rows beyond the trial's length are never stored: skip their Philox draws)
           // softsign (rnn_model.py:99) then inverted dropout (rnn_model.py:102-103)
           const float inv_keep = 1.0f / p.keep;
           const unsigned long long e0 = (unsigned long long)zc * p.c_zstride + (unsigned long long)m * p.ldc + n0;

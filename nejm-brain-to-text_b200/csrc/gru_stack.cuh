@@ -54,12 +54,12 @@ struct StackFwdParams {
 
 template <int BG, int NSUB> struct StackCfg {
   using Base = RecCfg<BG>;
-  static constexpr int kFwdThreads = Base::kFwdThreads;
+  static constexpr int kThreads = Base::kFwdThreads + 32;      // + one warp whose lane 0 publishes the layer's progress
   static constexpr size_t fwd_smem_bytes(int H) {
-    return (size_t)NSUB * ((size_t)2 * (H / 64) * BG * 128 + (size_t)3 * 32 * Base::kXPitch * 4) + (size_t)(NSUB * 32 + 2 * NSUB) * 8 + 64 + 1024;
+    return (size_t)NSUB * ((size_t)2 * (H / 64) * BG * 128 + (size_t)3 * 32 * Base::kXPitch * 4) + (size_t)(NSUB * 32 + 3 * NSUB) * 8 + 64 + 1024;
   }
   static constexpr size_t bwd_smem_bytes(int H) {
-    return (size_t)(3 * H / 4 / 64) * (128 * 128 + (size_t)NSUB * BG * 128) + (size_t)(NSUB * 16 + 2 * NSUB) * 8 + 64 + 1024;
+    return (size_t)(3 * H / 4 / 64) * (128 * 128 + (size_t)NSUB * BG * 128) + (size_t)(NSUB * 16 + 3 * NSUB) * 8 + 64 + 1024;
   }
 };
 
@@ -86,6 +86,15 @@ __device__ __forceinline__ void warp_signal(int* ctr, int lane) {
   __syncwarp();
   if (lane == 0) red_release_add(ctr, 1);
 }
+// CTA-local monotonic counter in shared memory (no phase parity to alias when the waiter falls behind)
+__device__ __forceinline__ void smem_release_inc(uint32_t* ctr) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(ctr)) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_acquire_ld(const uint32_t* ctr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ctr)) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 ldcg_f4(const float* p) {
   float4 v;
   asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
@@ -111,7 +120,7 @@ __device__ __forceinline__ void probe_until_published(int n_probe, int lt, AddrF
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int BG, int NSUB>
-__global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads, 1)
+__global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads + 32, 1)
 gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
   using Cfg = RecCfg<BG>;
   constexpr int XP = Cfg::kXPitch;
@@ -126,7 +135,8 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
   uint64_t* bar_h = reinterpret_cast<uint64_t*>(sX + NSUB * 3 * 32 * XP);   // [NSUB][2][16]
   uint64_t* bar_d = bar_h + NSUB * 32;                      // [NSUB]
   uint64_t* bar_s = bar_d + NSUB;                           // [NSUB]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + NSUB);
+  uint32_t* cnt_p = reinterpret_cast<uint32_t*>(bar_s + NSUB);   // [NSUB] epilogue warps that have stored a step's outputs (monotonic)
+  uint32_t* tmem_slot = cnt_p + 2 * NSUB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_layer = p.n_slices * p.n_cgroups;
@@ -135,13 +145,14 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
   const StackFwdLayer& L = p.lay[layer];
   const int j0 = slice * REC_US;
   const int a_cols = p.H / 2;
-  const bool is_loader = warp == 0 || warp >= 2 + Cfg::kEpiWarps;
+  const bool is_signaller = warp == Cfg::kFwdThreads / 32;
+  const bool is_loader = warp == 0 || (warp >= 2 + Cfg::kEpiWarps && !is_signaller);
   const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_cta;
 #define STK_TRACE(step, slot) do { if (tracing) p.trace[(step) * 8 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
     for (int c = 0; c < NSUB * 32; ++c) mbar_init(&bar_h[c], Cfg::kLoadWarps);
-    for (int s = 0; s < NSUB; ++s) { mbar_init(&bar_d[s], 1); mbar_init(&bar_s[s], Cfg::kEpiWarps); }
+    for (int s = 0; s < NSUB; ++s) { mbar_init(&bar_d[s], 1); mbar_init(&bar_s[s], Cfg::kEpiWarps); cnt_p[s] = 0u; }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
@@ -219,6 +230,24 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
         if (lt == 0 && sub == 0) STK_TRACE(t, 1);
       }
     }
+  } else if (is_signaller) {
+    if (lane == 0 && L.prog) {
+      // ---------------- progress signaller: once every epilogue warp has stored a step's outputs (cnt_p), make them visible at
+      // gpu scope and bump the layer's progress counter.  The membar costs ~1 us when stores are still in flight; here it
+      // delays nobody (in the epilogue warps it sat in front of every step of both groups).
+      for (int t = 0; t < p.T; ++t) {
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+          uint32_t spins = 0;
+          while (smem_acquire_ld(&cnt_p[sub]) < (uint32_t)(t + 1) * Cfg::kEpiWarps) {
+            __nanosleep(40);
+            if (++spins > (1u << 27)) __trap();
+          }
+          __threadfence();
+          red_release_add(L.prog + t, 1);
+        }
+      }
+    }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BG, 0, 0);
@@ -271,8 +300,6 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
         const int b0 = (cgrp * NSUB + sub) * BG;
         const int b = b0 + bl;
         const size_t row = (size_t)t * p.Bpad + b;
-        // outputs of this group's previous step are long stored: tell the next layer's input GEMM (release; off the critical path)
-        if (L.prog && t > 0) warp_signal(L.prog + (t - 1), lane);
         if (L.gx_done) {                                     // the input projection of this step's rows must have landed
           const int tile = (int)(((size_t)t * p.Bpad + b0) / 128);   // BG divides 128 and Bpad: the group's rows lie in one tile
           if (tile > ready_tile) { warp_wait_ge(L.gx_done + tile, L.gx_need, lane); ready_tile = tile; }
@@ -333,13 +360,16 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
           }
           st_bf16x4(L.hdrop + off, d[0], d[1], d[2], d[3]);
         }
+        if (L.prog) {                                        // outputs of (t, group) stored by this warp: hand over to the signaller thread
+          __syncwarp();
+          if (lane == 0) smem_release_inc(&cnt_p[sub]);
+        }
       }
     }
 #pragma unroll
     for (int sub = 0; sub < NSUB; ++sub) {
       const int b = (cgrp * NSUB + sub) * BG + bl;
       *reinterpret_cast<float4*>(L.h_state + (size_t)b * p.H + j) = make_float4(h[sub][0], h[sub][1], h[sub][2], h[sub][3]);
-      if (L.prog) warp_signal(L.prog + (p.T - 1), lane);     // the last step of each group
     }
   }
 #undef STK_TRACE
@@ -382,13 +412,13 @@ struct StackBwdParams {
 };
 
 template <int BG, int NSUB>
-__global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads, 1)
+__global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads + 32, 1)
 gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
   using Cfg = RecCfg<BG>;
   constexpr int CHUNK_BYTES = BG * 128;
   constexpr int A_CHUNK = 128 * 128;
   constexpr int UNITS = BG * 8;
-  constexpr int NTHREADS = Cfg::kFwdThreads;
+  constexpr int NTHREADS = Cfg::kFwdThreads + 32;
   constexpr uint32_t TMEM_COLS = NSUB * BG < 32 ? 32 : NSUB * BG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -402,7 +432,8 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
   uint64_t* bar_h = reinterpret_cast<uint64_t*>(sB + NSUB * SB_SUB);   // [NSUB][16]
   uint64_t* bar_d = bar_h + NSUB * 16;                     // [NSUB]
   uint64_t* bar_s = bar_d + NSUB;                          // [NSUB]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + NSUB);
+  uint32_t* cnt_p = reinterpret_cast<uint32_t*>(bar_s + NSUB);   // [NSUB] epilogue warps that have stored dGx of a step (monotonic)
+  uint32_t* tmem_slot = cnt_p + 2 * NSUB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_group = MB * 4;
@@ -413,13 +444,14 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
   const int NG = p.n_cgroups * NSUB;                       // batch groups of the layer
   const StackBwdLayer& L = p.lay[layer];
   const int j0 = mb * 128 + kq * REC_US;
-  const bool is_loader = warp == 0 || warp >= 2 + Cfg::kEpiWarps;
+  const bool is_signaller = warp == Cfg::kFwdThreads / 32;
+  const bool is_loader = warp == 0 || (warp >= 2 + Cfg::kEpiWarps && !is_signaller);
   const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_cta;
 #define STK_TRACE(step, slot) do { if (tracing) p.trace[((size_t)p.T + (step)) * 8 + (slot)] = clock64(); } while (0)
 
   if (threadIdx.x == 0) {
     for (int c = 0; c < NSUB * 16; ++c) mbar_init(&bar_h[c], Cfg::kLoadWarps);
-    for (int s = 0; s < NSUB; ++s) { mbar_init(&bar_d[s], 1); mbar_init(&bar_s[s], Cfg::kEpiWarps); }
+    for (int s = 0; s < NSUB; ++s) { mbar_init(&bar_d[s], 1); mbar_init(&bar_s[s], Cfg::kEpiWarps); cnt_p[s] = 0u; }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -502,6 +534,22 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
           }
         }
         if (lt == 0 && sub == 0) STK_TRACE(s, 1);
+      }
+    }
+  } else if (is_signaller) {
+    if (lane == 0 && L.prog) {
+      // ---------------- progress signaller: dGx of (step, group) stored by every epilogue warp -> visible -> counter (see forward)
+      for (int s = 0; s < p.T; ++s) {
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+          uint32_t spins = 0;
+          while (smem_acquire_ld(&cnt_p[sub]) < (uint32_t)(s + 1) * Cfg::kEpiWarps) {
+            __nanosleep(40);
+            if (++spins > (1u << 27)) __trap();
+          }
+          __threadfence();
+          red_release_add(L.prog + (p.T - 1 - s), 1);
+        }
       }
     }
   } else if (warp == 1) {
@@ -666,6 +714,10 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       st_bf16x4(L.dGx + goff, gr[0], gr[1], gr[2], gr[3]);
       st_bf16x4(L.dGx + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
       st_bf16x4(L.dGx + goff + 2 * p.H, gn[0], gn[1], gn[2], gn[3]);
+      if (L.prog) {                                          // dGx of (s, group) stored by this warp: hand over to the signaller thread
+        __syncwarp();
+        if (lane == 0) smem_release_inc(&cnt_p[sub]);
+      }
       // next step's operands: the forward stash always; dY only if its tile has already landed (never block here)
       if (s + 1 < p.T) {
         load_fwd_stash(b, t - 1, cur[sub]);
@@ -683,9 +735,6 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
     };
     auto phase_b = [&](int s, int sub) {
       const int grp = cgrp * NSUB + sub;
-      // dGx of (s, group) was stored in phase A, at least one phase ago: tell the data-gradient GEMM of this layer (release).  The
-      // fence sits in front of the wait for the group's MMA, i.e. where this warp has nothing else to do.
-      if (L.prog) warp_signal(L.prog + (p.T - 1 - s), lane);
       mbar_wait(&bar_d[sub], (uint32_t)s & 1u);
       if (e == 0 && sub == 0) STK_TRACE(s, 7);
       tc_fence_after();
