@@ -34,7 +34,7 @@ print("  per-step deltas (h_t stored), steps 0..96:", " ".join(f"{t[s+1,5]-t[s,5
 print("BWD cta", os.environ.get("B2T_TRACE_CTA_BWD", "top layer"), "(group 0 of the CTA)")
 t = tr[1]
 print(f"  cycles per step: {np.mean([t[s + 1, 6] - t[s, 6] for s in steps]):.0f}   (total {(t[96, 6] - t[0, 6]):.0f} cycles = {(t[96,6]-t[0,6])/1.965e3:.0f} us)")
-for a, b, nxt in ((6, 0, False), (0, 1, False), (0, 2, False), (2, 3, False), (3, 7, False), (7, 4, True), (4, 5, False), (5, 6, False)):
+for a, b, nxt in ((6, 0, False), (0, 1, False), (0, 2, False), (2, 3, False), (3, 7, False), (7, 5, True), (5, 6, False)):
     d = np.mean([t[s + 1, b] - t[s, a] if nxt else t[s, b] - t[s, a] for s in steps])
     print(f"  {bw[a]:>16s} -> {('next ' if nxt else '') + bw[b]:<22s}: {d:8.0f}")
 print("  per-step deltas (dG published), steps 0..96:", " ".join(f"{t[s+1,6]-t[s,6]:.0f}" for s in range(0, 96, 6)))
