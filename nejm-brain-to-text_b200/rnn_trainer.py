@@ -311,11 +311,7 @@ class BrainToTextDecoder_Trainer:
             self.val_dataset = SyntheticBrainToTextDataset(n_batches=_get(synth, 'val_batches', 8), days_per_batch=1, seed=ds['seed'],
                                                            split="test", **common)
         else:
-            try:
-                from dataset import BrainToTextDataset, train_test_split_indicies      # the reference's own loader, if on sys.path
-            except Exception as e:  # noqa: BLE001
-                raise ImportError("no data source: put the reference's model_training/dataset.py (needs h5py) on sys.path, "
-                                  "or set args['dataset']['synthetic'] = {...}") from e
+            from .dataset import BrainToTextDataset, train_test_split_indicies      # hdf5 through h5py when importable, .npz shards otherwise
             train_paths = [os.path.join(ds["dataset_dir"], s, 'data_train.hdf5') for s in ds['sessions']]
             val_paths = [os.path.join(ds["dataset_dir"], s, 'data_val.hdf5') for s in ds['sessions']]
             if len(set(train_paths)) != len(train_paths):
@@ -331,8 +327,15 @@ class BrainToTextDecoder_Trainer:
                                                     must_include_days=None, random_seed=ds['seed'] + self.rank, feature_subset=fs)
             self.val_dataset = BrainToTextDataset(trial_indicies=val_trials, split='test', days_per_batch=None, n_batches=None,
                                                   batch_size=ds['batch_size'], must_include_days=None, random_seed=ds['seed'], feature_subset=fs)
-        self.train_loader = DataLoader(self.train_dataset, batch_size=None, shuffle=ds['loader_shuffle'],
-                                       num_workers=ds['num_dataloader_workers'], pin_memory=True)
+        if synth is None and _get(ds, 'pinned_prefetch', True):
+            # batches assembled inside pinned host buffers on a background thread (dataset.py: PinnedBatchLoader)
+            from .dataset import PinnedBatchLoader
+            self.train_loader = PinnedBatchLoader(self.train_dataset, max_T=int(_get(ds, 'max_time_steps', 2048)),
+                                                  neural_dim=self.args['model']['n_input_features'] if not _get(ds, 'feature_subset', None) else len(ds['feature_subset']),
+                                                  shuffle=ds['loader_shuffle'])
+        else:
+            self.train_loader = DataLoader(self.train_dataset, batch_size=None, shuffle=ds['loader_shuffle'],
+                                           num_workers=ds['num_dataloader_workers'], pin_memory=True)
         self.val_loader = DataLoader(self.val_dataset, batch_size=None, shuffle=False, num_workers=0, pin_memory=True)
         self.logger.info("Successfully initialized datasets")
 

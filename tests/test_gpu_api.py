@@ -141,6 +141,39 @@ def test_trainer_learns_synthetic_corpus(mods, tmp_path):
         assert k in m
 
 
+def test_trainer_on_session_files(mods, tmp_path, pkg):
+    """The reference's data path: per-session files (here .npz shards of the hdf5 layout) -> BrainToTextDataset with the reference's
+    day / trial sampling -> pinned prefetch -> fused training step; labels arrive padded to 500 like the reference's files."""
+    import b2t_pkg
+    DS = b2t_pkg.submodule("dataset")
+    synth = b2t_pkg.submodule("datasets").SyntheticBrainToTextDataset(n_batches=1, batch_size=24, days_per_batch=1, n_days=4, neural_dim=64,
+                                                                      T=120, min_len=3, max_len=6, noise=0.3, seed=3)
+    args = _trainer_args(str(tmp_path), 120)
+    del args["dataset"]["synthetic"]
+    args["dataset"]["sessions"] = [f"t15.2023.08.{10 + d}" for d in range(4)]
+    args["dataset"]["dataset_probability_val"] = [1] * 4
+    args["dataset"]["dataset_dir"] = str(tmp_path / "data")
+    args["dataset"]["max_time_steps"] = 128
+    args["batches_per_val_step"] = 119
+    rng = np.random.RandomState(0)
+    for d, sess in enumerate(args["dataset"]["sessions"]):
+        os.makedirs(os.path.join(args["dataset"]["dataset_dir"], sess))
+        for split, n in (("train", 40), ("val", 10)):
+            trials = []
+            for t in range(n):
+                x, lab, nst = synth._trial(rng, d)
+                ids = np.zeros(500, dtype=np.int64); ids[:len(lab)] = lab
+                trials.append({"input_features": x[:nst], "seq_class_ids": ids, "transcription": np.zeros(500, dtype=np.int64),
+                               "n_time_steps": nst, "seq_len": len(lab), "block_num": 1, "trial_num": t})
+            DS.write_session_npz(os.path.join(args["dataset"]["dataset_dir"], sess, f"data_{split}.npz"), trials)
+    tr = mods["rnn_trainer"].BrainToTextDecoder_Trainer(args)
+    stats = tr.train()
+    assert len(stats["train_losses"]) == 120
+    assert np.mean(stats["train_losses"][-10:]) < 0.7 * np.mean(stats["train_losses"][:10])
+    assert 0.0 <= stats["val_PERs"][-1] <= stats["val_PERs"][0]
+    assert os.path.exists(os.path.join(args["output_dir"], "train_val_trials.json"))
+
+
 def test_run_single_decoding_step(mods):
     m, params, grads, rest = _model_from_golden(mods, "train_small.npz")
     m.eval()
