@@ -195,7 +195,12 @@ int b2t_decoder_decode_logprobs(b2t_decoder* d, int slot, const float* logp, int
 /* FinishDecoding: final costs, lattice pruning within lattice_beam (on the device), n-best (nbest > 1: top-n distinct word
  * sequences; nbest == 1: back-pointer best path on the device).  Idempotent: a second call keeps the first call's results. */
 int b2t_decoder_finish(b2t_decoder* d, int slot);
-int b2t_decoder_rescore(b2t_decoder* d, int slot);                                    /* Rescore: not wired yet (next row N1), see below */
+/* DecodeResource.lm_fst_path / rescore_lm_fst_path (brain_speech_decoder.h:57-79): the LM the graph was built from and the
+ * rescoring LM as OpenFST acceptors, loaded once; empty paths leave rescoring unavailable. */
+int b2t_decoder_set_rescore_lms(b2t_decoder* d, const char* lm_fst_path, const char* rescore_lm_fst_path);
+/* Rescore (brain_speech_decoder.cc:61-101), after finish: every distinct word sequence of the pruned lattice is re-scored as
+ * graph' = graph - c_old + c_new (see b2t_lm_rescore_sequences); the result list keeps its first-pass length, best first. */
+int b2t_decoder_rescore(b2t_decoder* d, int slot);
 /* Host core of Rescore() (brain_speech_decoder.cc:47-101), no GPU involved: n word sequences (ids concatenated in `words`,
  * lengths in `lens`) with first-pass (graph, acoustic) costs are re-scored as graph' = graph - c_old + c_new, where c is the
  * cheapest path through the LM acceptor (OpenFST file; back-off arcs taken as epsilons, final cost included), and ordered by

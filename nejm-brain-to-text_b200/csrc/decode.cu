@@ -730,6 +730,7 @@ struct Slot {
   std::vector<float> fed;           // fed frames [n][C]
   int n_fed = 0, num_frames = 0, last_best = 0;
   bool last_blank = false, decoded_any = false, finished = false;
+  bool pruned_on_gpu = false;       // the device copy of the lattice has been pruned and compacted (finish or rescore)
   std::vector<float> last_frame;
   std::vector<HResult> results;
 };
@@ -754,6 +755,7 @@ struct b2t_decoder {
   std::vector<Slot> slots;
   cudaStream_t stream = nullptr;
   double last_kernel_ms = 0.0;
+  void *lm_old = nullptr, *lm_new = nullptr;   // LmAcceptor*: the LM the graph was built from / the rescoring LM (DecodeResource lm_fst_path, rescore_lm_fst_path)
 };
 
 namespace {
@@ -971,9 +973,11 @@ inline bool hyp_better(const Hyp& x, const Hyp& y) {
   return x.g < y.g;
 }
 
-void nbest_from_lattice(b2t_decoder* d, Slot& s, const Lattice& L, const std::vector<float>& extra, const std::vector<char>& keep) {
+struct NbOut { std::vector<int> words; float g, a; };
+// The K cheapest distinct word sequences of a pruned lattice with the (graph, acoustic) costs of their best alignments.
+void collect_nbest(b2t_decoder* d, const Lattice& L, const std::vector<float>& extra, const std::vector<char>& keep, int K, std::vector<NbOut>* out) {
   const int nt = (int)L.state.size();
-  const int K = std::max(1, d->opt.nbest);
+  K = std::max(1, K);
   // topological order inside each level with respect to epsilon links (Kahn)
   std::vector<int> order; order.reserve(nt);
   std::vector<int> indeg(nt, 0);
@@ -1064,9 +1068,15 @@ void nbest_from_lattice(b2t_decoder* d, Slot& s, const Lattice& L, const std::ve
     std::stable_sort(finals.begin(), finals.end(), hyp_better);
     const bool complete = margin >= full || ((int)finals.size() >= K && finals[K - 1].g + finals[K - 1].a <= beta[0] + margin);
     if (!complete) continue;
-    for (size_t i = 0; i < finals.size() && (int)i < K; ++i) push_result(d, s, trie.words(finals[i].seq), finals[i].g, finals[i].a);
+    for (size_t i = 0; i < finals.size() && (int)i < K; ++i) out->push_back(NbOut{trie.words(finals[i].seq), finals[i].g, finals[i].a});
     break;
   }
+}
+
+void nbest_from_lattice(b2t_decoder* d, Slot& s, const Lattice& L, const std::vector<float>& extra, const std::vector<char>& keep) {
+  std::vector<NbOut> nb;
+  collect_nbest(d, L, extra, keep, d->opt.nbest, &nb);
+  for (const NbOut& e : nb) push_result(d, s, e.words, e.g, e.a);
 }
 
 void log_softmax_row(const float* x, int C, float* out) {
@@ -1297,6 +1307,7 @@ int finish_slot(b2t_decoder* d, int slot) {
   const bool gpu_prune = d->opt.nbest != 1 && use_gpu_prune();
   int rc = gpu_prune ? prune_slots_on_gpu(d, std::vector<int>{slot}) : 0;
   if (rc) return rc;
+  if (gpu_prune) s.pruned_on_gpu = true;
   rc = gpu_prune ? fetch_pruned_lattice(d, slot, &L) : fetch_lattice(d, slot, &L);
   if (rc) return rc;
   finish_from_lattice(d, slot, L, now() - t0, gpu_prune);
@@ -1344,6 +1355,7 @@ int finish_slots(b2t_decoder* d, int N) {
     for (int n = 0; n < N; ++n)
       if (d->slots[n].n_fed > 0) ids.push_back(n);
     if ((rc = prune_slots_on_gpu(d, ids))) return rc;
+    for (int n : ids) d->slots[n].pruned_on_gpu = true;
   }
   for (int i = 0; i < std::min(n_workers, N); ++i) workers.emplace_back(work);
   for (int n = 0; n < N && !rc; ++n) {
@@ -1482,6 +1494,7 @@ b2t_decoder* b2t_decoder_create(const char* fst_path, const char* words_path, co
 }
 
 void b2t_decoder_destroy(b2t_decoder* d) {
+  if (d) { delete (LmAcceptor*)d->lm_old; delete (LmAcceptor*)d->lm_new; d->lm_old = d->lm_new = nullptr; }
   if (!d) return;
   void* ptrs[] = {d->d_arcs, d->d_off, d->d_has_eps, d->d_best, d->d_tokidx, d->d_tok_state, d->d_tok_cost, d->d_tok_bp, d->d_dirty, d->d_links,
                   d->d_ftok, d->d_flink, d->d_coff, d->d_counters, d->d_nfed, d->d_slot_ids, d->d_logp, d->d_fin, d->d_extra, d->d_newidx, d->d_cftok, d->d_ccounts, d->d_bp_words, d->d_bp_cost, d->d_bp_hop, d->d_bp_ol};
@@ -1535,9 +1548,60 @@ int b2t_decoder_finish(b2t_decoder* d, int slot) {
   return finish_slot(d, slot);
 }
 
+// DecodeResource.lm_fst_path / rescore_lm_fst_path (brain_speech_decoder.h:57-79): the LM the decoding graph was built from and the
+// (unpruned) rescoring LM, loaded once.  Either path empty: rescoring stays unavailable, like a null LM pointer in the reference.
+int b2t_decoder_set_rescore_lms(b2t_decoder* d, const char* lm_fst_path, const char* rescore_lm_fst_path) {
+  if (!d) return dfail(B2T_ERR_ARG, "null decoder");
+  delete (LmAcceptor*)d->lm_old; delete (LmAcceptor*)d->lm_new;
+  d->lm_old = d->lm_new = nullptr;
+  if (!lm_fst_path || !rescore_lm_fst_path || !lm_fst_path[0] || !rescore_lm_fst_path[0]) return 0;
+  LmAcceptor* a = new LmAcceptor();
+  LmAcceptor* b = new LmAcceptor();
+  if (a->load(lm_fst_path) || b->load(rescore_lm_fst_path)) { delete a; delete b; return B2T_ERR_ARG; }
+  d->lm_old = a; d->lm_new = b;
+  return 0;
+}
+
+// Rescore() (brain_speech_decoder.cc:61-101) after FinishDecoding: every distinct word sequence W of the pruned lattice (what
+// CtcWfstBeamSearch::Lattice() holds after determinisation) gets graph' = g_W - c_old(W) + c_new(W); the result list keeps its
+// first-pass length and is re-filled best first.  The lattice is read back from the device, where it stays until Reset.
 int b2t_decoder_rescore(b2t_decoder* d, int slot) {
-  (void)d; (void)slot;
-  return dfail(B2T_ERR_UNSUPPORTED, "Rescore() is not wired into the decoder yet (next row N1); its host core is b2t_lm_rescore_sequences");
+  if (!d || slot < 0 || slot >= d->max_slots) return dfail(B2T_ERR_ARG, "bad slot");
+  if (!d->lm_old || !d->lm_new) return dfail(B2T_ERR_STATE, "Rescore() needs DecodeResource.lm_fst_path and rescore_lm_fst_path (b2t_decoder_set_rescore_lms)");
+  Slot& s = d->slots[slot];
+  if (!s.finished) return dfail(B2T_ERR_STATE, "Rescore() needs a preceding FinishDecoding()");
+  const size_t keep_n = s.results.size();
+  if (keep_n == 0 || s.n_fed == 0) return 0;
+  Lattice L;
+  std::vector<float> extra; std::vector<char> keep;
+  int rc;
+  if (use_gpu_prune()) {
+    if (!s.pruned_on_gpu) {                       // nbest == 1 finished through the back-pointer walk: prune now
+      if ((rc = prune_slots_on_gpu(d, std::vector<int>{slot}))) return rc;
+      s.pruned_on_gpu = true;
+    }
+    if ((rc = fetch_pruned_lattice(d, slot, &L))) return rc;
+    extra.assign(L.state.size(), 0.0f); keep.assign(L.links.size(), 1);
+  } else {
+    if ((rc = fetch_lattice(d, slot, &L))) return rc;
+    prune_final(d, L, &extra, &keep);
+  }
+  static const int cap = getenv("B2T_RESCORE_MAX_SEQS") ? atoi(getenv("B2T_RESCORE_MAX_SEQS")) : 20000;   // distinct sequences considered (cheapest first)
+  std::vector<NbOut> all;
+  collect_nbest(d, L, extra, keep, cap, &all);
+  const LmAcceptor* lo = (const LmAcceptor*)d->lm_old;
+  const LmAcceptor* ln = (const LmAcceptor*)d->lm_new;
+  struct R { size_t idx; float g, a; };
+  std::vector<R> scored;
+  for (size_t i = 0; i < all.size(); ++i) {
+    const float c_old = lo->cost(all[i].words.data(), (int)all[i].words.size()), c_new = ln->cost(all[i].words.data(), (int)all[i].words.size());
+    if (c_old == INFINITY || c_new == INFINITY) continue;      // a sequence an LM rejects leaves the lattice in the composition
+    scored.push_back({i, -(-all[i].g + c_old) + c_new, all[i].a});
+  }
+  std::stable_sort(scored.begin(), scored.end(), [](const R& x, const R& y) { return hyp_better(Hyp{0, x.g, x.a}, Hyp{0, y.g, y.a}); });
+  s.results.clear();
+  for (size_t i = 0; i < scored.size() && i < keep_n; ++i) push_result(d, s, all[scored[i].idx].words, scored[i].g, scored[i].a);
+  return 0;
 }
 
 // Host core of Rescore(), usable on its own (no GPU involved): n word sequences (ids concatenated in `words`, lengths in `lens`)

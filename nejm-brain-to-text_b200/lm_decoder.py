@@ -8,7 +8,7 @@ used by ``language-model-standalone.py``: same class names, constructor argument
 
 backed by the GPU token-passing decoder in libb2t_b200.so (C ABI b2t_decoder_*).  Differences: errors raise
 Python exceptions instead of aborting the process through glog; ``DecodeBatch`` is an extension that decodes many
-utterances concurrently (one CTA each); ``Rescore`` (lattice LM rescoring) is not implemented yet.
+utterances concurrently (one CTA each).
 """
 from __future__ import annotations
 
@@ -38,6 +38,7 @@ _lib.b2t_decoder_decode_logits.argtypes = [_vp, _ci, _vp, _vp, _ci, _ci, _cf]
 _lib.b2t_decoder_decode_logprobs.argtypes = [_vp, _ci, _vp, _ci, _ci]
 _lib.b2t_decoder_finish.argtypes = [_vp, _ci]
 _lib.b2t_decoder_rescore.argtypes = [_vp, _ci]
+_lib.b2t_decoder_set_rescore_lms.argtypes = [_vp, C.c_char_p, C.c_char_p]
 _lib.b2t_decoder_num_results.argtypes = [_vp, _ci]
 _lib.b2t_decoder_get_result.argtypes = [_vp, _ci, _ci, C.POINTER(_cf), C.POINTER(_cf), C.c_char_p, _ci]
 _lib.b2t_decoder_decode_batch.argtypes = [_vp, _vp, _vp, _ci, _ci, _ci, _cf, _ci]
@@ -81,6 +82,8 @@ class BrainSpeechDecoder:
                                           self.max_slots)
         if not self._h:
             raise N.B2TError("BrainSpeechDecoder: " + _lib.b2t_decoder_last_error().decode("utf-8", "replace"))
+        if resource.lm_fst_path and resource.rescore_lm_fst_path:     # lattice LM rescoring (brain_speech_decoder.h:57-79)
+            _check(_lib.b2t_decoder_set_rescore_lms(self._h, resource.lm_fst_path.encode(), resource.rescore_lm_fst_path.encode()), "DecodeResource LMs")
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -278,3 +278,57 @@ def test_product_rescore_core_matches_oracle(compiled, tmp_path, pkg):
     assert [every[order_out[i]][2] for i in range(m)] == [r[2] for r in want]
     assert all(abs(-graph_out[i] - want[i][1]) < 1e-4 * max(1.0, abs(want[i][1])) for i in range(m))
     assert lib.b2t_lm_rescore_sequences(b"/nonexistent.fst", g_new.encode(), 0, None, None, None, None, 1, order_out.ctypes.data, graph_out.ctypes.data) < 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nbest", [30, 1])
+def test_decoder_rescore_gpu_vs_oracle(compiled, tmp_path, pkg, nbest):
+    """BrainSpeechDecoder.Rescore() end to end (brain_speech_decoder.cc:61-101): DecodeResource carries the LM the graph was built from
+    and the rescoring LM; after FinishDecoding the GPU decoder's pruned lattice is re-scored and the list re-ranked.  Checker: the
+    oracle's Facade::Rescore on the same posteriors and acceptors."""
+    import b2t_pkg
+    LM = b2t_pkg.submodule("lm_decoder")
+    fst, words, info, lm = compiled
+    order, grams_old = GC.parse_arpa(os.path.join(os.path.dirname(fst), "lm.arpa"))
+    arpa_new = tmp_path / "new.arpa"
+    arpa_new.write_text(ARPA_NEW)
+    _, grams_new = GC.parse_arpa(str(arpa_new))
+    word_ids = {}
+    for line in open(words):
+        w, i = line.split()
+        if int(i) > 0:
+            word_ids[w] = int(i)
+    g_old, g_new = str(tmp_path / "G.fst"), str(tmp_path / "G_new.fst")
+    GC.write_g_fst(order, grams_old, word_ids, g_old)
+    GC.write_g_fst(order, grams_new, word_ids, g_new)
+    ids = {p: 3 + i for i, p in enumerate(PHONES)}
+    opts = (7000, 200, 20.0, 8.0, 0.5, 1.0, 0.0, nbest)
+    for seed, sentence in ((5, ["alpha", "beta", "gamma"]), (8, ["beater", "alpha", "beta"])):
+        logits = TLG.render_logits([[ids[p] for p in LEXICON[w][0].split()] for w in sentence], T=90, seed=seed, peak=5.0, noise=1.2)
+        ref = D.OracleDecoder(fst, words, *opts)
+        ref.decode_logits(logits, np.zeros_like(logits), 0.0)
+        ref.finish()
+        first = ref.results()
+        ref.rescore(g_old, g_new)
+        want = ref.results()
+        dec = LM.BrainSpeechDecoder(LM.DecodeResource(fst, g_old, g_new, words, ""), LM.DecodeOptions(*opts), max_frames=128)
+        dec.Reset()
+        LM.DecodeNumpy(dec, logits, np.zeros_like(logits), 0.0)
+        dec.FinishDecoding()
+        assert [r.sentence for r in dec.result()] == [r[2] for r in first]
+        dec.Rescore()
+        got = dec.result()
+        assert len(got) == len(want) >= 1
+        assert [r.sentence for r in got] == [r[2] for r in want]
+        for a, b in zip(got, want):
+            assert abs(a.lm_score - b[1]) < 1e-3 * max(1.0, abs(b[1])) and abs(a.ac_score - b[0]) < 1e-3 * max(1.0, abs(b[0]))
+        # a second utterance through the same decoder object
+        dec.Reset()
+    # rescoring with the LM the graph was built from leaves the first pass as it was
+    dec = LM.BrainSpeechDecoder(LM.DecodeResource(fst, g_old, g_old, words, ""), LM.DecodeOptions(*opts), max_frames=128)
+    LM.DecodeNumpy(dec, logits, np.zeros_like(logits), 0.0)
+    dec.FinishDecoding()
+    before = [(r.sentence, r.lm_score) for r in dec.result()]
+    dec.Rescore()
+    after = [(r.sentence, r.lm_score) for r in dec.result()]
+    assert [s for s, _ in before] == [s for s, _ in after] and all(abs(a[1] - b[1]) < 1e-3 * max(1.0, abs(b[1])) for a, b in zip(after, before))
