@@ -161,7 +161,8 @@ def run_ours(args):
     if strong and (B % world or Bl < 1):
         raise SystemExit("--scaling strong needs a world size that divides 64")
     gscale = 1.0 / (Bl * world)
-    loss_host = torch.empty(Bl, pin_memory=True)
+    loss_host = [torch.empty(Bl, pin_memory=True) for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
     stage = [{k: torch.empty_like(v[:Bl], device=dev) for k, v in host[0].items()} for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -170,9 +171,11 @@ def run_ours(args):
         res = [{k: v[:Bl].contiguous() for k, v in r.items()} for r in res]
         host = [{k: v[:Bl].contiguous().pin_memory() for k, v in hb.items()} for hb in host]
 
+    e2e_losses = []
+
     def prefetch(i):
         """Host -> device copy of step i's batch (pinned memory) on the copy stream, into the staging buffer the step
-        before last has finished with (every e2e step ends with a stream synchronize)."""
+        before last has finished with (the copy stream waits for the compute stream's work issued so far)."""
         hb, d = host[i % N_ROT], stage[i % 2]
         copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(copy_stream):
@@ -197,11 +200,19 @@ def run_ours(args):
         loss = eng.ctc_loss(d["labels"], in_len, d["lens"], grad_scale=gscale, max_target_len=45)
         eng.backward()
         if world > 1:
-            dist.all_reduce(eng.grads)                      # ONE NCCL all-reduce: gradients + day-touched flags
+            eng.all_reduce_grads()                          # the step's gradient all-reduce (gradients + day-touched flags), issued bucket by bucket behind backward
         eng.optimizer_step(lr, wd, 0.9, 0.999, 0.1, 10.0)
         if from_host:
-            loss_host.copy_(loss, non_blocking=True)
-            torch.cuda.current_stream().synchronize()       # the reference reads loss.item() every step (rnn_trainer.py:562)
+            # the reference reads loss.item() every step (rnn_trainer.py:562): every step's per-trial losses are copied to pinned host
+            # memory and read on the host -- one step late, so that the read of step i-1 overlaps the device work of step i
+            loss_host[i % 2].copy_(loss, non_blocking=True)
+            loss_ready[i % 2].record()
+            if i > 0:
+                loss_ready[(i - 1) % 2].synchronize()
+                e2e_losses.append(float(loss_host[(i - 1) % 2][0]))
+            if last:
+                loss_ready[i % 2].synchronize()
+                e2e_losses.append(float(loss_host[i % 2][0]))
         return loss
 
     def timed(n, from_host, sample_clocks=False):

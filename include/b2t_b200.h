@@ -128,6 +128,14 @@ int b2t_set_dlogits(b2t_engine* e, const float* dlogits, void* stream);
  * Gradients of day layers absent from the batch are left untouched (their "touched" flag stays 0). */
 int b2t_backward(b2t_engine* e, void* stream);
 
+/* Gradient buckets for data parallelism: contiguous ranges of the gradient buffer together with the point of b2t_backward after
+ * which each is final, so that the caller's all-reduce of one bucket overlaps the rest of backward (the reference is single-GPU;
+ * one all-reduce per step is the north-star's collective, here issued bucket by bucket).  After b2t_backward: bucket i in
+ * completion order has the range [*offset, *offset + *count); b2t_grad_bucket_wait makes a stream wait for it. */
+int b2t_grad_buckets(b2t_engine* e);
+int b2t_grad_bucket(b2t_engine* e, int i, long long* offset, long long* count);
+int b2t_grad_bucket_wait(b2t_engine* e, int i, void* stream);
+
 typedef struct b2t_adamw_args {
   float lr[3];            /* per group: 0 biases, 1 day layers, 2 everything else */
   float weight_decay[3];

@@ -64,6 +64,9 @@ def _load():
         "b2t_set_dlogits": (ci, [vp, vp, vp]),
         "b2t_backward": (ci, [vp, vp]),
         "b2t_optimizer_step": (ci, [vp, C.POINTER(AdamWArgs), vp, vp]),
+        "b2t_grad_buckets": (ci, [vp]),
+        "b2t_grad_bucket": (ci, [vp, ci, C.POINTER(ll), C.POINTER(ll)]),
+        "b2t_grad_bucket_wait": (ci, [vp, ci, vp]),
         "b2t_step_counters": (vp, [vp]),
         "b2t_debug_set_trace": (ci, [vp, vp]),
         "b2t_debug_buffer": (ci, [vp, C.c_char_p, ci, C.POINTER(vp), C.POINTER(ll)]),

@@ -187,6 +187,11 @@ struct b2t_engine {
   int ctr_stride = 0;
   cudaStream_t gstream[STACK_MAX_LAYERS] = {};
   cudaEvent_t ev_g[STACK_MAX_LAYERS] = {};
+  // gradient buckets (contiguous ranges of the flat gradient buffer) with the event after which each is final: lets a data-parallel
+  // caller start the all-reduce of a bucket while backward is still producing the others (b2t_grad_bucket*)
+  std::vector<cudaEvent_t> ev_bucket;
+  std::vector<std::pair<long long, long long>> bucket_range;   // [offset, count)
+  std::vector<int> bucket_order;                                // buckets in the order they become final
 };
 
 // Optional timeline (B2T_TIMELINE=1): CUDA events around every task of a step, dumped by b2t_debug_dump_timeline.
@@ -295,6 +300,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
     if (e->lane[i]) cudaStreamDestroy(e->lane[i]);
     if (e->ev_lane_end[i]) cudaEventDestroy(e->ev_lane_end[i]);
   }
+  for (cudaEvent_t ev : e->ev_bucket) if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < STACK_MAX_LAYERS; ++i) {
     if (e->gstream[i]) cudaStreamDestroy(e->gstream[i]);
     if (e->ev_g[i]) cudaEventDestroy(e->ev_g[i]);
@@ -362,6 +368,20 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
     if (pe != cudaSuccess) { fail(B2T_ERR_CUDA, "kernel preload failed: %s", cudaGetErrorString(pe)); b2t_engine_destroy(e); return nullptr; }
   }
   if (training) {
+    // buckets: 0 = day layers; 1 = layer-0 input weights; 2 + l = rest of layer l (layer 0: W_hh + biases); L + 2 = head, h0, touched flags
+    const long long n_grad = e->n_params + r64(e->cfg.n_days);
+    auto off = [&](const std::string& n) { return seg_off(e, n); };
+    e->bucket_range.push_back({0, off("gru.weight_ih_l0")});
+    e->bucket_range.push_back({off("gru.weight_ih_l0"), off("gru.weight_hh_l0") - off("gru.weight_ih_l0")});
+    for (int l = 0; l < e->L; ++l) {
+      const long long b = l == 0 ? off("gru.weight_hh_l0") : off("gru.weight_ih_l" + std::to_string(l));
+      const long long en = l + 1 < e->L ? off("gru.weight_ih_l" + std::to_string(l + 1)) : off("out.weight");
+      e->bucket_range.push_back({b, en - b});
+    }
+    e->bucket_range.push_back({off("out.weight"), n_grad - off("out.weight")});
+    e->ev_bucket.assign(e->bucket_range.size(), nullptr);
+    for (auto& ev : e->ev_bucket)
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { fail(B2T_ERR_CUDA, "event creation failed"); b2t_engine_destroy(e); return nullptr; }
     std::vector<Segment> hs;
     std::vector<ChunkRef> hc;
     for (size_t i = 0; i < e->segs.size(); ++i) {
@@ -1125,8 +1145,11 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       dim3 g((e->T_in + FOLD_TT - 1) / FOLD_TT, Bp);
       { TlScope tl("fold", 8, bs); fold_dpre_kernel<<<g, D / 4, 0, bs>>>(fp); CK(LAUNCHED()); }
       { TlScope tl("daydW", 8, bs); CK(gemm_run(e->p_daydw, bs)); ++g_launches; }
+      CK(cudaEventRecord(e->ev_bucket[0], bs));                 // day layers final
     }
+    e->bucket_order.clear();
     { TlScope tl("dWih0", 7, bw); CK(gemm_run(e->p_dwih0[0], bw)); ++g_launches; }
+    CK(cudaEventRecord(e->ev_bucket[1], bw)); e->bucket_order.push_back(1);
     for (int l = L - 1; l >= 0; --l) {
       const std::string sl = std::to_string(l);
       if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwih[l], bw)); ++g_launches; }
@@ -1135,7 +1158,10 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
         reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bw>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
         CK(LAUNCHED());
       }
+      CK(cudaEventRecord(e->ev_bucket[2 + l], bw)); e->bucket_order.push_back(2 + l);    // (bias gradients were final when the recurrence ended)
     }
+    CK(cudaEventRecord(e->ev_bucket[L + 2], bw)); e->bucket_order.push_back(L + 2);      // head (before the recurrence), h0 (all layers), touched flags
+    e->bucket_order.push_back(0);
     for (int i = MAX_LANES; i <= MAX_LANES + 1; ++i) {
       CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
       CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));
@@ -1224,7 +1250,26 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
     CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));
   }
+  e->bucket_order.clear();
+  for (size_t k = 0; k < e->ev_bucket.size(); ++k) { CK(cudaEventRecord(e->ev_bucket[k], st)); e->bucket_order.push_back((int)k); }
   e->have_dlogits = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ gradient buckets (data parallelism)
+extern "C" int b2t_grad_buckets(b2t_engine* e) { return e ? (int)e->bucket_range.size() : fail(B2T_ERR_ARG, "null engine"); }
+// The i-th bucket to become final in the last b2t_backward: its element range in the gradient buffer.
+extern "C" int b2t_grad_bucket(b2t_engine* e, int i, long long* offset, long long* count) {
+  if (!e || i < 0 || i >= (int)e->bucket_order.size()) return fail(B2T_ERR_ARG, "bucket index out of range (call after b2t_backward)");
+  const int k = e->bucket_order[i];
+  if (offset) *offset = e->bucket_range[k].first;
+  if (count) *count = e->bucket_range[k].second;
+  return k;
+}
+// Make `stream` wait until the i-th bucket (same numbering) of the last b2t_backward is final.
+extern "C" int b2t_grad_bucket_wait(b2t_engine* e, int i, void* stream) {
+  if (!e || i < 0 || i >= (int)e->bucket_order.size()) return fail(B2T_ERR_ARG, "bucket index out of range (call after b2t_backward)");
+  CK(cudaStreamWaitEvent((cudaStream_t)stream, e->ev_bucket[e->bucket_order[i]], 0));
   return 0;
 }
 

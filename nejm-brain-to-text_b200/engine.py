@@ -218,6 +218,25 @@ class Engine:
     def backward(self):
         N.check(N.lib.b2t_backward(self.handle, _stream()), "b2t_backward")
 
+    def all_reduce_grads(self, group=None):
+        """Data-parallel gradient exchange: SUM all-reduce of the flat gradient buffer (gradients + day-touched flags), issued
+        bucket by bucket in the order backward finishes them, on a side stream, so that the collective of the early buckets
+        (layer-0 input weights, the upper layers) runs while backward still computes the late ones.  The current stream
+        continues only when every bucket has been reduced.  Call right after backward()."""
+        import torch.distributed as dist
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        n = N.check(N.lib.b2t_grad_buckets(self.handle), "b2t_grad_buckets")
+        off, cnt = C.c_longlong(), C.c_longlong()
+        works = []
+        with torch.cuda.stream(self._comm_stream):
+            for i in range(n):
+                N.check(N.lib.b2t_grad_bucket(self.handle, i, C.byref(off), C.byref(cnt)), "b2t_grad_bucket")
+                N.check(N.lib.b2t_grad_bucket_wait(self.handle, i, self._comm_stream.cuda_stream), "b2t_grad_bucket_wait")
+                works.append(dist.all_reduce(self.grads[off.value:off.value + cnt.value], group=group, async_op=True))
+        for w in works:
+            w.wait()                                     # current stream waits for the collective
+
     def optimizer_step(self, lr, weight_decay, beta1, beta2, eps, max_grad_norm) -> torch.Tensor:
         a = N.AdamWArgs()
         for i in range(3):

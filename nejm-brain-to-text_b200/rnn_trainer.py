@@ -483,7 +483,7 @@ class BrainToTextDecoder_Trainer:
                                 max_target_len=batch.get('max_phone_seq_len'))
         eng.backward()
         if self.world_size > 1:
-            dist.all_reduce(eng.grads)              # one all-reduce: flat gradients + day-touched flags
+            eng.all_reduce_grads()                  # the step's gradient all-reduce (flat gradients + day-touched flags), bucket by bucket behind backward
         self.optimizer.step()
         self.learning_rate_scheduler.step()
         loss = loss_vec.mean()
