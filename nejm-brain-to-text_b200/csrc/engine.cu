@@ -489,7 +489,12 @@ static int build_plans(b2t_engine* e) {
     const int grid = L * (H / 32) * (ng / nsub);
     const size_t smem_f = bg == 32 ? (nsub == 2 ? StackCfg<32, 2>::fwd_smem_bytes(H) : StackCfg<32, 1>::fwd_smem_bytes(H))
                                    : StackCfg<16, 1>::fwd_smem_bytes(H);
-    bool ok = env_int("B2T_STACK", 1) != 0 && L <= STACK_MAX_LAYERS && grid + std::max(L - 1, 0) <= num_sms() && smem_f <= 227 * 1024 &&
+    // Tools that serialise kernel execution (Nsight Compute's kernel replay, compute-sanitizer) would dead-lock kernels that wait
+    // for each other while running (the persistent recurrence and its gated GEMMs): under them the stack schedule is off unless
+    // B2T_STACK=1 forces it (single-layer models have no cross-kernel dependency and can be profiled with it).
+    static const bool serialising_tool = getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
+                                         getenv("NV_SANITIZER_INJECTION_PORT_BASE");
+    bool ok = env_int("B2T_STACK", serialising_tool ? 0 : 1) != 0 && L <= STACK_MAX_LAYERS && grid + std::max(L - 1, 0) <= num_sms() && smem_f <= 227 * 1024 &&
               128 % bg == 0 && (nsub * bg) <= 128 && (128 % (nsub * bg) == 0);
     if (tr) ok = ok && (H % 256 == 0);          // backward uses the two-dimensional decomposition (H/128 x 4 CTAs per batch group)
     e->stack = ok ? 1 : 0;

@@ -5,11 +5,12 @@ sys.path.insert(0, ROOT)
 import torch, b2t_pkg
 E = b2t_pkg.submodule("engine")
 B = int(os.environ.get("SB", "64")); H = int(os.environ.get("SH", "256")); train = os.environ.get("STRAIN", "0") == "1"
-cfg = E.make_config(32, H, 1, 3, 41, 14, 4, 0.0, 0.0)
+Dn = int(os.environ.get("SD", "32")); Tn = int(os.environ.get("ST", "74"))
+cfg = E.make_config(Dn, H, 1, 3, 41, 14, 4, 0.0, 0.0)
 torch.manual_seed(0)
 flat = (torch.randn(E.param_elems(cfg)) * 0.05).cuda()
-eng = E.Engine(cfg, flat, max_batch=B, max_T=74, max_label_len=8, training=train)
-x = torch.randn(B, 74, 32, device="cuda")
+eng = E.Engine(cfg, flat, max_batch=B, max_T=Tn, max_label_len=8, training=train)
+x = torch.randn(B, Tn, Dn, device="cuda")
 days = torch.zeros(B, dtype=torch.int32)
 N = b2t_pkg.load()._native
 dbg = torch.zeros(4096 + 148 * 32 * 4, dtype=torch.int64).pin_memory()
