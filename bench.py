@@ -240,6 +240,17 @@ def run_ours(args):
 
     for i in range(max(args.warmup, 3)):
         step(i, False)
+    if args.profile_range:
+        # ncu --replay-mode app-range: the kernels of the range run concurrently, as they do in production (the per-kernel mode
+        # serialises launches, which the whole-stack recurrence and its gated GEMMs cannot survive)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for i in range(args.profile_range):
+            step(i, False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile_range_steps": args.profile_range}))
+        return
     ms, launches, clocks = timed(args.steps, False, sample_clocks=True)
     for i in range(2):
         step(i, True, last=(i == 1))
@@ -583,6 +594,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 64 trials per GPU (default); strong: global batch 64 split over the GPUs (the reference's batch, parity config)")
+    ap.add_argument("--profile-range", type=int, default=0,
+                    help="run N steps between cudaProfilerStart/Stop and exit (for ncu --replay-mode app-range); not a bench value")
     ap.add_argument("--no-extras", action="store_true", help="skip the context sections (GPU incumbent, config-4 decode pipeline)")
     a = ap.parse_args()
     if a.impl == "reference":
