@@ -194,7 +194,14 @@ b2t_decoder* b2t_decoder_create(const char* fst_path, const char* words_path, co
                                 int max_slots);
 void b2t_decoder_destroy(b2t_decoder* d);
 int b2t_decoder_set_options(b2t_decoder* d, const b2t_decode_options* opt);          /* SetOpt */
+/* Search order.  0 (default): the two-pass parallel search, identical to the reference whenever max_active does not bind.
+ * 1: strict serial order -- Kaldi's token-list order (HashList, hash-list-inl.h:124-171) and the online tightening of
+ * next_cutoff (lattice-faster-decoder.cc:785-822) are reproduced, so token counts, 1-best and n-best equal the reference's
+ * also when max_active binds; slower.  Switch between utterances only.  Env B2T_DECODER_STRICT=1 sets the default. */
+int b2t_decoder_set_strict_order(b2t_decoder* d, int on);
 int b2t_decoder_reset(b2t_decoder* d, int slot);                                      /* Reset */
+/* Test hook: states and costs of the tokens of frame_plus_one fp1, in list order (strict mode) -- before finish only. */
+int b2t_decoder_debug_frame_tokens(b2t_decoder* d, int slot, int fp1, int* states, float* costs, int cap);
 /* DecodeNumpy: host logits [T][C] (+ optional log_priors [T][C]); log_softmax, minus priors, blank column minus
  * blank_penalty, then Decode().  After the call the slot's result list holds the partial 1-best. */
 int b2t_decoder_decode_logits(b2t_decoder* d, int slot, const float* logits, const float* log_priors, int T, int C,

@@ -96,7 +96,23 @@ struct DecParams {
   const int* n_fed;             // [slots]
   const int* slot_ids;          // [gridDim.x] slot handled by each CTA
   int tok_cap, link_cap, max_frames, C;
+  // strict serial-order mode (decode_strict.cuh); all per slot
+  const long long* eps_off;     // compact CSR of the input-epsilon arcs, in arc order
+  const struct EArc* eps_arcs;
+  int* first_rank;              // [slots][nstates] insertion rank of the state's token in the frame being built
+  int* eps_bp;                  // [slots][nstates] source state of the epsilon arc that last lowered the token's cost
+  int* bucket_min;              // [slots][hcap]    rank of the first token of each hash bucket
+  int* s_cum;                   // [slots][fc + 1]  exclusive prefix sum of out-degrees in list order
+  float* s_premin;              // [slots][fc]      exclusive prefix min of the tokens' best emitting arc
+  unsigned int *s_k0, *s_k1;    // [slots][fc]      radix-sort keys (ping-pong)
+  int *s_v0, *s_v1;             // [slots][fc]      radix-sort values
+  int* s_byrank;                // [slots][fc]      states of the new frame in insertion order
+  int* s_queue;                 // [slots][qcap]    ProcessNonemitting's LIFO
+  int* s_hash;                  // [slots]          HashList size
+  int fc, qcap, hcap;
 };
+
+struct EArc { int next; float w; int ol; int orig; };
 
 __device__ float block_min(float v, float* sred) {
   for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -398,6 +414,8 @@ wfst_decode_kernel(const DecParams p) {
     __syncthreads();
   }
 }
+
+#include "decode_strict.cuh"
 
 // ------------------------------------------------------------------------------------------------ lattice pruning on the GPU
 // FinalizeDecoding / PruneForwardLinksFinal / PruneForwardLinks / PruneTokensForFrame (lattice-faster-decoder.cc:632-647,
@@ -752,6 +770,13 @@ struct b2t_decoder {
   float *d_coff = nullptr, *d_logp = nullptr;
   float* d_fin = nullptr; unsigned int* d_extra = nullptr; int *d_newidx = nullptr, *d_cftok = nullptr, *d_ccounts = nullptr;   // GPU lattice pruning
   int* d_bp_words = nullptr; float *d_bp_cost = nullptr, *d_bp_hop = nullptr; int* d_bp_ol = nullptr;                                                    // GPU best path
+  // strict serial-order mode (decode_strict.cuh), allocated on first use
+  bool strict = false;
+  int strict_fc = 0, strict_qcap = 0, strict_hcap = 0;
+  long long* d_eps_off = nullptr; EArc* d_eps_arcs = nullptr;
+  int *d_first_rank = nullptr, *d_eps_bp = nullptr, *d_bucket_min = nullptr, *d_s_cum = nullptr, *d_s_v0 = nullptr, *d_s_v1 = nullptr, *d_s_byrank = nullptr,
+      *d_s_queue = nullptr, *d_s_hash = nullptr;
+  float* d_s_premin = nullptr; unsigned int *d_s_k0 = nullptr, *d_s_k1 = nullptr;
   std::vector<Slot> slots;
   cudaStream_t stream = nullptr;
   double last_kernel_ms = 0.0;
@@ -810,6 +835,7 @@ int fetch_lattice(b2t_decoder* d, int slot, Lattice* L) {
   DCK(cudaStreamSynchronize(d->stream));
   if (counters[3] == 1) return dfail(B2T_ERR_WORKSPACE, "decoder token pool overflow (capacity %d): raise max_active-derived capacity or lower beam", d->tok_cap);
   if (counters[3] == 2) return dfail(B2T_ERR_WORKSPACE, "decoder link pool overflow (capacity %d)", d->link_cap);
+  if (counters[3] == 3) return dfail(B2T_ERR_WORKSPACE, "strict-order decoder scratch overflow (frame capacity %d tokens)", d->strict_fc);
   const int nf = counters[2], nt = counters[0], nl = counters[1];
   L->F = nf + 1;
   L->ftok.resize(L->F + 1); L->flink.resize(L->F + 1);
@@ -1130,10 +1156,14 @@ int launch_slots(b2t_decoder* d, const std::vector<int>& ids) {
   p.tok_dirty = d->d_dirty; p.links = d->d_links; p.frame_tok_off = d->d_ftok; p.frame_link_off = d->d_flink; p.cost_offsets = d->d_coff;
   p.counters = d->d_counters; p.logp = d->d_logp; p.n_fed = d->d_nfed; p.slot_ids = d->d_slot_ids;
   p.tok_cap = d->tok_cap; p.link_cap = d->link_cap; p.max_frames = d->max_frames; p.C = d->C;
+  p.eps_off = d->d_eps_off; p.eps_arcs = d->d_eps_arcs; p.first_rank = d->d_first_rank; p.eps_bp = d->d_eps_bp; p.bucket_min = d->d_bucket_min;
+  p.s_cum = d->d_s_cum; p.s_premin = d->d_s_premin; p.s_k0 = d->d_s_k0; p.s_k1 = d->d_s_k1; p.s_v0 = d->d_s_v0; p.s_v1 = d->d_s_v1;
+  p.s_byrank = d->d_s_byrank; p.s_queue = d->d_s_queue; p.s_hash = d->d_s_hash; p.fc = d->strict_fc; p.qcap = d->strict_qcap; p.hcap = d->strict_hcap;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, d->stream);
-  wfst_decode_kernel<<<(int)ids.size(), DEC_THREADS, 0, d->stream>>>(p);
+  if (d->strict) wfst_decode_strict_kernel<<<(int)ids.size(), DEC_THREADS, 0, d->stream>>>(p);
+  else wfst_decode_kernel<<<(int)ids.size(), DEC_THREADS, 0, d->stream>>>(p);
   cudaEventRecord(e1, d->stream);
   DCK(cudaGetLastError());
   DCK(cudaStreamSynchronize(d->stream));
@@ -1173,6 +1203,7 @@ int best_path_on_gpu(b2t_decoder* d, int slot, bool use_final, std::vector<int>*
   DCK(cudaStreamSynchronize(d->stream));
   if (counters[3] == 1) return dfail(B2T_ERR_WORKSPACE, "decoder token pool overflow (capacity %d): raise max_active-derived capacity or lower beam", d->tok_cap);
   if (counters[3] == 2) return dfail(B2T_ERR_WORKSPACE, "decoder link pool overflow (capacity %d)", d->link_cap);
+  if (counters[3] == 3) return dfail(B2T_ERR_WORKSPACE, "strict-order decoder scratch overflow (frame capacity %d tokens)", d->strict_fc);
   BestPathParams p;
   p.fin = d->d_fin; p.tok_state = d->d_tok_state; p.tok_cost = d->d_tok_cost; p.tok_bp = d->d_tok_bp; p.links = d->d_links;
   p.frame_tok_off = d->d_ftok; p.frame_link_off = d->d_flink; p.cost_offsets = d->d_coff; p.counters = d->d_counters; p.slot_ids = d->d_slot_ids;
@@ -1250,6 +1281,7 @@ int fetch_pruned_lattice(b2t_decoder* d, int slot, Lattice* L, bool index_now = 
   DCK(cudaStreamSynchronize(d->stream));
   if (counters[3] == 1) return dfail(B2T_ERR_WORKSPACE, "decoder token pool overflow (capacity %d): raise max_active-derived capacity or lower beam", d->tok_cap);
   if (counters[3] == 2) return dfail(B2T_ERR_WORKSPACE, "decoder link pool overflow (capacity %d)", d->link_cap);
+  if (counters[3] == 3) return dfail(B2T_ERR_WORKSPACE, "strict-order decoder scratch overflow (frame capacity %d tokens)", d->strict_fc);
   const int nf = counters[2], nt = cc[0], nl = cc[1];
   L->F = nf + 1;
   L->ftok.resize(L->F + 1); L->flink.assign(L->F + 1, 0);
@@ -1490,6 +1522,8 @@ b2t_decoder* b2t_decoder_create(const char* fst_path, const char* words_path, co
   d->slots.resize(max_slots);
   for (int i = 0; i < max_slots; ++i) reset_slot(d, i);
   cudaStreamSynchronize(d->stream);
+  if (const char* v = getenv("B2T_DECODER_STRICT"))
+    if (atoi(v) != 0 && b2t_decoder_set_strict_order(d, 1)) { b2t_decoder_destroy(d); return nullptr; }
   return d;
 }
 
@@ -1499,6 +1533,9 @@ void b2t_decoder_destroy(b2t_decoder* d) {
   void* ptrs[] = {d->d_arcs, d->d_off, d->d_has_eps, d->d_best, d->d_tokidx, d->d_tok_state, d->d_tok_cost, d->d_tok_bp, d->d_dirty, d->d_links,
                   d->d_ftok, d->d_flink, d->d_coff, d->d_counters, d->d_nfed, d->d_slot_ids, d->d_logp, d->d_fin, d->d_extra, d->d_newidx, d->d_cftok, d->d_ccounts, d->d_bp_words, d->d_bp_cost, d->d_bp_hop, d->d_bp_ol};
   for (void* p : ptrs) if (p) cudaFree(p);
+  void* sptrs[] = {d->d_eps_off, d->d_eps_arcs, d->d_first_rank, d->d_eps_bp, d->d_bucket_min, d->d_s_cum, d->d_s_premin, d->d_s_k0, d->d_s_k1, d->d_s_v0, d->d_s_v1,
+                   d->d_s_byrank, d->d_s_queue, d->d_s_hash};
+  for (void* p : sptrs) if (p) cudaFree(p);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -1508,6 +1545,43 @@ int b2t_decoder_set_options(b2t_decoder* d, const b2t_decode_options* opt) {
   // NOTE: the reference's SetOpt only reaches acoustic_scale / nbest / blank_skip (the Kaldi config copy is never
   // updated).  Here every field takes effect from the next Reset().
   d->opt = *opt;
+  return 0;
+}
+
+int b2t_decoder_set_strict_order(b2t_decoder* d, int on) {
+  if (!d) return dfail(B2T_ERR_ARG, "null decoder");
+  for (const Slot& s : d->slots)
+    if (s.n_fed > 0 && !s.finished) return dfail(B2T_ERR_STATE, "the search order can only be switched between utterances (Reset() first)");
+  if (on && !d->d_first_rank) {
+    const size_t ns = d->g.fin.size(), S = (size_t)d->max_slots;
+    std::vector<long long> eoff(ns + 1, 0);
+    std::vector<EArc> earcs;
+    for (size_t st = 0; st < ns; ++st) {
+      eoff[st] = (long long)earcs.size();
+      if (d->g.has_eps[st])
+        for (long long a = d->g.off[st]; a < d->g.off[st + 1]; ++a)
+          if (d->g.arcs[a].il == 0) earcs.push_back(EArc{d->g.arcs[a].next, d->g.arcs[a].w, d->g.arcs[a].ol, (int)a});
+    }
+    eoff[ns] = (long long)earcs.size();
+    const long long per_frame = std::min<long long>((long long)std::max(d->opt.max_active, 1000) * 6, 200000);
+    d->strict_fc = (int)std::min<long long>(d->tok_cap, per_frame * 4);
+    d->strict_qcap = d->strict_fc * 4;
+    d->strict_hcap = std::max(2 * d->strict_fc + 16, 1024);
+    const size_t fc = (size_t)d->strict_fc;
+    bool ok = cudaMalloc(&d->d_eps_off, (ns + 1) * 8) == cudaSuccess && cudaMalloc(&d->d_eps_arcs, std::max<size_t>(earcs.size(), 1) * sizeof(EArc)) == cudaSuccess &&
+              cudaMalloc(&d->d_first_rank, S * ns * 4) == cudaSuccess && cudaMalloc(&d->d_eps_bp, S * ns * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_bucket_min, S * d->strict_hcap * 4) == cudaSuccess && cudaMalloc(&d->d_s_cum, S * (fc + 1) * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_s_premin, S * fc * 4) == cudaSuccess && cudaMalloc(&d->d_s_k0, S * fc * 4) == cudaSuccess && cudaMalloc(&d->d_s_k1, S * fc * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_s_v0, S * fc * 4) == cudaSuccess && cudaMalloc(&d->d_s_v1, S * fc * 4) == cudaSuccess && cudaMalloc(&d->d_s_byrank, S * fc * 4) == cudaSuccess &&
+              cudaMalloc(&d->d_s_queue, S * (size_t)d->strict_qcap * 4) == cudaSuccess && cudaMalloc(&d->d_s_hash, S * 4) == cudaSuccess;
+    if (!ok) return dfail(B2T_ERR_CUDA, "strict-order scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    DCK(cudaMemcpy(d->d_eps_off, eoff.data(), (ns + 1) * 8, cudaMemcpyHostToDevice));
+    if (!earcs.empty()) DCK(cudaMemcpy(d->d_eps_arcs, earcs.data(), earcs.size() * sizeof(EArc), cudaMemcpyHostToDevice));
+    DCK(cudaMemset(d->d_first_rank, 0x7f, S * ns * 4));          // RANK_NONE
+    DCK(cudaMemset(d->d_bucket_min, 0x7f, S * d->strict_hcap * 4));
+    DCK(cudaMemset(d->d_s_hash, 0, S * 4));
+  }
+  d->strict = on != 0;
   return 0;
 }
 
@@ -1693,6 +1767,22 @@ int b2t_decoder_tokens_per_frame(b2t_decoder* d, int slot, int* out, int cap) {
   if (cudaMemcpy(ft.data(), d->d_ftok + (size_t)slot * (d->max_frames + 3), (nf + 2) * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return dfail(B2T_ERR_CUDA, "copy failed");
   for (int f = 0; f < nf && f < cap; ++f) out[f] = ft[f + 2] - ft[f + 1];
   return nf;
+}
+
+// test hook: states and costs of the tokens of frame_plus_one `fp1`, in pool (= list, in strict mode) order; before finish only
+int b2t_decoder_debug_frame_tokens(b2t_decoder* d, int slot, int fp1, int* states, float* costs, int cap) {
+  if (!d || slot < 0 || slot >= d->max_slots || !states || !costs) return dfail(B2T_ERR_ARG, "bad arguments");
+  if (d->slots[slot].pruned_on_gpu) return dfail(B2T_ERR_STATE, "the pool has been pruned");
+  int c[4];
+  if (cudaMemcpy(c, d->d_counters + slot * 4, sizeof(c), cudaMemcpyDeviceToHost) != cudaSuccess) return dfail(B2T_ERR_CUDA, "copy failed");
+  if (fp1 < 0 || fp1 > std::max(c[2], 0)) return dfail(B2T_ERR_ARG, "frame out of range");
+  int ft[2];
+  if (cudaMemcpy(ft, d->d_ftok + (size_t)slot * (d->max_frames + 3) + fp1, sizeof(ft), cudaMemcpyDeviceToHost) != cudaSuccess) return dfail(B2T_ERR_CUDA, "copy failed");
+  const int n = std::min(ft[1] - ft[0], cap);
+  if (n > 0 && (cudaMemcpy(states, d->d_tok_state + (size_t)slot * d->tok_cap + ft[0], n * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(costs, d->d_tok_cost + (size_t)slot * d->tok_cap + ft[0], n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess))
+    return dfail(B2T_ERR_CUDA, "copy failed");
+  return ft[1] - ft[0];
 }
 
 }  // extern "C"

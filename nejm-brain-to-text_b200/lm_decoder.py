@@ -34,6 +34,7 @@ _lib.b2t_decoder_destroy.argtypes = [_vp]
 _lib.b2t_decoder_destroy.restype = None
 _lib.b2t_decoder_set_options.argtypes = [_vp, C.POINTER(_Opts)]
 _lib.b2t_decoder_reset.argtypes = [_vp, _ci]
+_lib.b2t_decoder_set_strict_order.argtypes = [_vp, _ci]
 _lib.b2t_decoder_decode_logits.argtypes = [_vp, _ci, _vp, _vp, _ci, _ci, _cf]
 _lib.b2t_decoder_decode_logprobs.argtypes = [_vp, _ci, _vp, _ci, _ci]
 _lib.b2t_decoder_finish.argtypes = [_vp, _ci]
@@ -44,6 +45,7 @@ _lib.b2t_decoder_get_result.argtypes = [_vp, _ci, _ci, C.POINTER(_cf), C.POINTER
 _lib.b2t_decoder_decode_batch.argtypes = [_vp, _vp, _vp, _ci, _ci, _ci, _cf, _ci]
 _lib.b2t_decoder_stats.argtypes = [_vp, _ci, C.POINTER(_ci), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
 _lib.b2t_decoder_tokens_per_frame.argtypes = [_vp, _ci, _vp, _ci]
+_lib.b2t_decoder_debug_frame_tokens.argtypes = [_vp, _ci, _ci, _vp, _vp, _ci]
 
 
 def _check(rc, what):
@@ -75,7 +77,7 @@ class DecodeResult:
 
 
 class BrainSpeechDecoder:
-    def __init__(self, resource: DecodeResource, opts: DecodeOptions, max_frames: int = 1024, max_slots: int = 1):
+    def __init__(self, resource: DecodeResource, opts: DecodeOptions, max_frames: int = 1024, max_slots: int = 1, strict_order=None):
         self._resource, self._opts = resource, opts        # the reference keeps both alive through shared_ptr
         self.max_slots = int(max_slots)
         self._h = _lib.b2t_decoder_create(resource.fst_path.encode(), resource.dict_path.encode(), C.byref(opts.c), int(max_frames),
@@ -84,6 +86,13 @@ class BrainSpeechDecoder:
             raise N.B2TError("BrainSpeechDecoder: " + _lib.b2t_decoder_last_error().decode("utf-8", "replace"))
         if resource.lm_fst_path and resource.rescore_lm_fst_path:     # lattice LM rescoring (brain_speech_decoder.h:57-79)
             _check(_lib.b2t_decoder_set_rescore_lms(self._h, resource.lm_fst_path.encode(), resource.rescore_lm_fst_path.encode()), "DecodeResource LMs")
+        if strict_order is not None:
+            self.set_strict_order(strict_order)
+
+    def set_strict_order(self, on: bool):
+        """Reproduce Kaldi's serial token-list order and online cutoff tightening (results equal the reference's also when
+        max_active binds); off = the faster two-pass search.  Between utterances only."""
+        _check(_lib.b2t_decoder_set_strict_order(self._h, 1 if on else 0), "set_strict_order")
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -142,6 +151,12 @@ class BrainSpeechDecoder:
         a = np.zeros(8192, dtype=np.int32)
         n = _check(_lib.b2t_decoder_tokens_per_frame(self._h, slot, a.ctypes.data, 8192), "tokens_per_frame")
         return a[:n]
+
+    def debug_frame_tokens(self, frame_plus_one: int, slot: int = 0, cap: int = 1 << 20):
+        """Test hook: (states, costs) of one frame's tokens in pool order (= Kaldi's list order in strict mode); before FinishDecoding."""
+        st = np.zeros(cap, dtype=np.int32); co = np.zeros(cap, dtype=np.float32)
+        n = _check(_lib.b2t_decoder_debug_frame_tokens(self._h, slot, frame_plus_one, st.ctypes.data, co.ctypes.data, cap), "debug_frame_tokens")
+        return st[:n], co[:n]
 
 
 def DecodeNumpy(decoder: BrainSpeechDecoder, logits, log_priors, blank_penalty, slot: int = 0):

@@ -1027,6 +1027,12 @@ int orc_tokens_per_frame(void* h, int* out, int cap) {
   for (int i = 0; i < n; ++i) out[i] = f->tokens_per_frame[i];
   return (int)f->tokens_per_frame.size();
 }
+int orc_token_list(void* h, int* states, float* costs, int cap) {      // debugging aid: the current token list, in list order
+  Facade* f = (Facade*)h;
+  const std::vector<Elem> l = f->dec.toks.GetList();
+  for (size_t i = 0; i < l.size() && (int)i < cap; ++i) { states[i] = l[i].key; costs[i] = l[i].val->tot_cost; }
+  return (int)l.size();
+}
 int orc_graph_info(void* h, long long* nstates, long long* narcs) {
   Facade* f = (Facade*)h;
   *nstates = (long long)f->graph.fin.size(); *narcs = (long long)f->graph.arcs.size();

@@ -27,6 +27,7 @@ def oracle_lib():
         lib.orc_num_results.argtypes = [C.c_void_p]
         lib.orc_get_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_char_p, C.c_int]
         lib.orc_tokens_per_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        lib.orc_token_list.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.orc_graph_info.argtypes = [C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         lib.orc_prefix_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         lib.orc_rescore.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
@@ -84,6 +85,12 @@ class OracleDecoder:
         a = np.zeros(4096, dtype=np.int32)
         n = self.lib.orc_tokens_per_frame(self.h, a.ctypes.data, 4096)
         return a[:n]
+
+    def token_list(self, cap=1 << 20):
+        """(states, costs) of the current token list, in Kaldi's list order."""
+        st = np.zeros(cap, dtype=np.int32); co = np.zeros(cap, dtype=np.float32)
+        n = self.lib.orc_token_list(self.h, st.ctypes.data, co.ctypes.data, cap)
+        return st[:n], co[:n]
 
 
 def prefix_search(logp, first_beam=10, second_beam=10, blank=0):

@@ -285,3 +285,93 @@ def test_prefix_beam_on_reference_logits(LM):
         assert [r[3] for r in ours[n][:k]] == [r[3] for r in ref[:k]]
         assert all(abs(a[1] - cut) < 1e-3 * abs(cut) for a in ours[n][k:])          # the rest are other members of the tie
         assert len(ours[n][0][0]) > 20
+
+
+# ---------------------------------------------------------------------------------------------- strict serial-order mode
+def _cmp_strict(dec_results, ref_results, acoustic_scale, tol=1e-3):
+    """Integer work: 1-best, the n-best set and the scores.  Only hypotheses that tie (total score) with the LAST kept entry
+    may differ: which of several equal-score homophones makes the cut is the n-shortest-paths heap order in the reference
+    (fst::ShortestPath) and creation order here and in the oracle."""
+    assert len(dec_results) == len(ref_results), (len(dec_results), len(ref_results))
+    assert dec_results[0].sentence == ref_results[0][2]
+    ours = {r.sentence: (r.ac_score, r.lm_score) for r in dec_results}
+    ref = {r[2]: (r[0], r[1]) for r in ref_results}
+    total = lambda v: v[1] + acoustic_scale * v[0]
+    worst = min(total(v) for v in ref.values())
+    cut = lambda d: {k for k, v in d.items() if total(v) > worst + tol * max(1.0, abs(worst))}
+    assert cut(ours) == cut(ref), (sorted(cut(ours) - cut(ref)), sorted(cut(ref) - cut(ours)))
+    assert all(abs(total(v) - worst) <= 2 * tol * max(1.0, abs(worst)) for k, v in ours.items() if k not in ref), "a non-tied hypothesis differs"
+    for k in set(ours) & set(ref):
+        assert abs(ours[k][0] - ref[k][0]) < tol * max(1.0, abs(ours[k][0])), k
+        assert abs(ours[k][1] - ref[k][1]) < tol * max(1.0, abs(ours[k][1])), k
+
+
+@pytest.mark.parametrize("max_active", [100, 500, 7000])
+def test_strict_order_toy_graph(LM, graph, max_active):
+    """max_active binding (noisy posteriors on the generated graph): Kaldi's result depends on its token-list order and on the
+    online next_cutoff tightening (lattice-faster-decoder.cc:785-822); the strict mode reproduces both, so per-frame token
+    counts, 1-best and the n-best set equal the oracle's."""
+    fst, words, info = graph
+    opts = (max_active, 20 if max_active <= 100 else 200, 14.0, 8.0, 0.6, 1.0, 0.0, 50)
+    dec = _ours(LM, fst, words, opts, max_frames=128, strict_order=True)
+    ref = D.OracleDecoder(fst, words, *opts)
+    bound = 0
+    for seed in range(4):
+        rng = np.random.RandomState(100 + seed)
+        seq = rng.randint(0, 300, size=rng.randint(2, 6))
+        logits = TLG.render_logits([info["prons"][w] for w in seq], T=110, seed=seed, noise=2.0)
+        ref.reset(); ref.decode_logits(logits, np.zeros_like(logits), math.log(3.0)); ref.finish()
+        dec.Reset()
+        LM.DecodeNumpy(dec, logits, np.zeros_like(logits), math.log(3.0))
+        dec.FinishDecoding()
+        assert np.array_equal(dec.tokens_per_frame(), ref.tokens_per_frame()), (seed, dec.tokens_per_frame()[:12], ref.tokens_per_frame()[:12])
+        _cmp_strict(dec.result(), ref.results(), opts[4])
+        bound += int(ref.tokens_per_frame().max() > max_active)
+    if max_active <= 500:
+        assert bound > 0, "the case is meant to exercise a binding max_active"
+
+
+def test_strict_order_switch_and_chunks(LM, graph):
+    """Switching the order between utterances and feeding in chunks gives the same strict result."""
+    fst, words, info = graph
+    opts = (300, 100, 14.0, 8.0, 0.6, 1.0, 0.0, 20)
+    logits = TLG.render_logits([info["prons"][w] for w in [5, 50, 150]], T=100, seed=3, noise=2.0)
+    lp = (logits - np.log(np.exp(logits).sum(1, keepdims=True))).astype(np.float32)
+    ref = D.OracleDecoder(fst, words, *opts)
+    ref.decode_logprobs(lp); ref.finish()
+    dec = _ours(LM, fst, words, opts, max_frames=128)
+    dec.Reset(); LM.DecodeNumpyLogProbs(dec, lp); dec.FinishDecoding()
+    fast = [r.sentence for r in dec.result()]
+    dec.set_strict_order(True)
+    dec.Reset()
+    for i in range(0, 100, 32):
+        LM.DecodeNumpyLogProbs(dec, lp[i:i + 32])
+    dec.FinishDecoding()
+    assert np.array_equal(dec.tokens_per_frame(), ref.tokens_per_frame())
+    _cmp_strict(dec.result(), ref.results(), opts[4])
+    dec.set_strict_order(False)
+    dec.Reset(); LM.DecodeNumpyLogProbs(dec, lp); dec.FinishDecoding()
+    assert [r.sentence for r in dec.result()] == fast
+
+
+@pytest.mark.skipif(D.real_graph() is None, reason="the shipped 1-gram graph is staged under oracle/_ref/ by __graft_entry__.build()")
+@pytest.mark.parametrize("max_active,n_utt", [(7000, 2), (500, 4), (100, 4)])
+def test_strict_order_shipped_1gram_graph(LM, max_active, n_utt):
+    """The reference's own graph at its shipped settings, where max_active binds: strict mode == oracle (counts, 1-best, n-best)."""
+    fst, words = D.real_graph()
+    g = D.read_fst(fst)
+    rng = np.random.RandomState(7)
+    utts = []
+    while len(utts) < n_utt:
+        u = D.random_walk_utterance(g, rng, n_words=int(rng.randint(1, 4)), peak=9.0, noise=0.6)
+        if u is not None:
+            utts.append(u[0])
+    batch = np.stack(utts)
+    opts = (max_active, 200 if max_active > 200 else 50, 17.0, 8.0, 0.325, 1.0, 0.0, 100)
+    dec = _ours(LM, fst, words, opts, max_frames=128, max_slots=n_utt, strict_order=True)
+    dec.DecodeBatch(batch, blank_penalty=math.log(90.0))
+    for n in range(n_utt):
+        ref = D.OracleDecoder(fst, words, *opts)       # every slot is a decoder of its own (the HashList size is decoder history)
+        ref.decode_logits(batch[n], np.zeros_like(batch[n]), math.log(90.0)); ref.finish()
+        assert np.array_equal(dec.tokens_per_frame(slot=n), ref.tokens_per_frame()), n
+        _cmp_strict(dec.result(slot=n), ref.results(), opts[4])
