@@ -516,6 +516,17 @@ def decode_config4(dev, n_utt=74, n_dec=2, rounds=3):
         th.join()
     dt = time.perf_counter() - t0
     hyp = [decs[0].result(slot=n) for n in range(n_utt)]
+    # the same batch through the strict serial-order search (Kaldi's token-list order reproduced; parity mode), decode only
+    decs[0].set_strict_order(True)
+    decs[0].DecodeBatch(post, blank_penalty=bp)
+    t1 = time.perf_counter()
+    decs[0].DecodeBatch(post, blank_penalty=bp)
+    dt_strict = time.perf_counter() - t1
+    strict_same = sum(int(bool(a) and bool(b) and a[0].sentence == b[0].sentence) for a, b in zip(hyp, [decs[0].result(slot=n) for n in range(n_utt)]))
+    decs[0].set_strict_order(False)
+    t1 = time.perf_counter()
+    decs[0].DecodeBatch(post, blank_penalty=bp)
+    dt_fast1 = time.perf_counter() - t1
     err = tot = 0
     for n, h in enumerate(hyp):
         ref = [w.lower() for w in sents[n]]
@@ -529,7 +540,9 @@ def decode_config4(dev, n_utt=74, n_dec=2, rounds=3):
     return {"what": f"{n_dec} x {n_utt} trials in flight: GRU logits (host in, host out) + WFST n-gram decode, shipped settings (max_active 7000, n-best 100), compiled 3-gram graph",
             "graph_states": gi["n_states"], "graph_arcs": gi["n_arcs"], "batches": n_dec * rounds, "ms_total": dt * 1e3, "gru_ms_per_batch": max(gru_ms),
             "value": n_dec * rounds * n_utt / dt, "unit": "trials/s", "ms_per_trial": dt * 1e3 / (n_dec * rounds * n_utt),
-            "wer_vs_rendered_transcripts": err / max(tot, 1), "posterior_noise": 1.0}
+            "wer_vs_rendered_transcripts": err / max(tot, 1), "posterior_noise": 1.0,
+            "strict_order": {"what": f"one decoder, {n_utt} utterances per call, decode only: strict serial-order search vs the default two-pass search",
+                             "strict_trials_per_s": n_utt / dt_strict, "fast_trials_per_s": n_utt / dt_fast1, "same_1best": f"{strict_same}/{n_utt}"}}
 
 
 def _ref_step_runner():

@@ -201,3 +201,21 @@ def random_walk_utterance(graph, rng, n_words=3, T=95, C=41, peak=7.0, noise=0.8
         t += d + int(rng.randint(0, 2))
         prev = cls
     return x, words
+
+
+def cmp_strict(dec_results, ref_results, acoustic_scale, tol=1e-3):
+    """Integer work: 1-best, the n-best set and the scores.  Only hypotheses that tie (total score) with the LAST kept entry
+    may differ: which of several equal-score homophones makes the cut is the n-shortest-paths heap order in the reference
+    (fst::ShortestPath) and creation order here and in the oracle."""
+    assert len(dec_results) == len(ref_results), (len(dec_results), len(ref_results))
+    assert dec_results[0].sentence == ref_results[0][2]
+    ours = {r.sentence: (r.ac_score, r.lm_score) for r in dec_results}
+    ref = {r[2]: (r[0], r[1]) for r in ref_results}
+    total = lambda v: v[1] + acoustic_scale * v[0]
+    worst = min(total(v) for v in ref.values())
+    cut = lambda d: {k for k, v in d.items() if total(v) > worst + tol * max(1.0, abs(worst))}
+    assert cut(ours) == cut(ref), (sorted(cut(ours) - cut(ref)), sorted(cut(ref) - cut(ours)))
+    assert all(abs(total(v) - worst) <= 2 * tol * max(1.0, abs(worst)) for k, v in ours.items() if k not in ref), "a non-tied hypothesis differs"
+    for k in set(ours) & set(ref):
+        assert abs(ours[k][0] - ref[k][0]) < tol * max(1.0, abs(ours[k][0])), k
+        assert abs(ours[k][1] - ref[k][1]) < tol * max(1.0, abs(ours[k][1])), k

@@ -288,24 +288,6 @@ def test_prefix_beam_on_reference_logits(LM):
 
 
 # ---------------------------------------------------------------------------------------------- strict serial-order mode
-def _cmp_strict(dec_results, ref_results, acoustic_scale, tol=1e-3):
-    """Integer work: 1-best, the n-best set and the scores.  Only hypotheses that tie (total score) with the LAST kept entry
-    may differ: which of several equal-score homophones makes the cut is the n-shortest-paths heap order in the reference
-    (fst::ShortestPath) and creation order here and in the oracle."""
-    assert len(dec_results) == len(ref_results), (len(dec_results), len(ref_results))
-    assert dec_results[0].sentence == ref_results[0][2]
-    ours = {r.sentence: (r.ac_score, r.lm_score) for r in dec_results}
-    ref = {r[2]: (r[0], r[1]) for r in ref_results}
-    total = lambda v: v[1] + acoustic_scale * v[0]
-    worst = min(total(v) for v in ref.values())
-    cut = lambda d: {k for k, v in d.items() if total(v) > worst + tol * max(1.0, abs(worst))}
-    assert cut(ours) == cut(ref), (sorted(cut(ours) - cut(ref)), sorted(cut(ref) - cut(ours)))
-    assert all(abs(total(v) - worst) <= 2 * tol * max(1.0, abs(worst)) for k, v in ours.items() if k not in ref), "a non-tied hypothesis differs"
-    for k in set(ours) & set(ref):
-        assert abs(ours[k][0] - ref[k][0]) < tol * max(1.0, abs(ours[k][0])), k
-        assert abs(ours[k][1] - ref[k][1]) < tol * max(1.0, abs(ours[k][1])), k
-
-
 @pytest.mark.parametrize("max_active", [100, 500, 7000])
 def test_strict_order_toy_graph(LM, graph, max_active):
     """max_active binding (noisy posteriors on the generated graph): Kaldi's result depends on its token-list order and on the
@@ -325,7 +307,7 @@ def test_strict_order_toy_graph(LM, graph, max_active):
         LM.DecodeNumpy(dec, logits, np.zeros_like(logits), math.log(3.0))
         dec.FinishDecoding()
         assert np.array_equal(dec.tokens_per_frame(), ref.tokens_per_frame()), (seed, dec.tokens_per_frame()[:12], ref.tokens_per_frame()[:12])
-        _cmp_strict(dec.result(), ref.results(), opts[4])
+        D.cmp_strict(dec.result(), ref.results(), opts[4])
         bound += int(ref.tokens_per_frame().max() > max_active)
     if max_active <= 500:
         assert bound > 0, "the case is meant to exercise a binding max_active"
@@ -348,7 +330,7 @@ def test_strict_order_switch_and_chunks(LM, graph):
         LM.DecodeNumpyLogProbs(dec, lp[i:i + 32])
     dec.FinishDecoding()
     assert np.array_equal(dec.tokens_per_frame(), ref.tokens_per_frame())
-    _cmp_strict(dec.result(), ref.results(), opts[4])
+    D.cmp_strict(dec.result(), ref.results(), opts[4])
     dec.set_strict_order(False)
     dec.Reset(); LM.DecodeNumpyLogProbs(dec, lp); dec.FinishDecoding()
     assert [r.sentence for r in dec.result()] == fast
@@ -374,4 +356,4 @@ def test_strict_order_shipped_1gram_graph(LM, max_active, n_utt):
         ref = D.OracleDecoder(fst, words, *opts)       # every slot is a decoder of its own (the HashList size is decoder history)
         ref.decode_logits(batch[n], np.zeros_like(batch[n]), math.log(90.0)); ref.finish()
         assert np.array_equal(dec.tokens_per_frame(slot=n), ref.tokens_per_frame()), n
-        _cmp_strict(dec.result(slot=n), ref.results(), opts[4])
+        D.cmp_strict(dec.result(slot=n), ref.results(), opts[4])

@@ -332,3 +332,34 @@ def test_decoder_rescore_gpu_vs_oracle(compiled, tmp_path, pkg, nbest):
     dec.Rescore()
     after = [(r.sentence, r.lm_score) for r in dec.result()]
     assert [s for s, _ in before] == [s for s, _ in after] and all(abs(a[1] - b[1]) < 1e-3 * max(1.0, abs(b[1])) for a, b in zip(after, before))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [3, 5])
+def test_strict_order_on_compiled_ngram_graphs(order, tmp_path, pkg):
+    """Graphs compiled by graph_compiler from a synthetic 3-/5-gram ARPA (back-off arcs = input epsilons, so the serial
+    epsilon-closure replay is exercised), max_active binding: strict mode == oracle (per-frame token counts, 1-best, n-best)."""
+    import b2t_pkg
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_synth_lm as SL
+    LM = b2t_pkg.submodule("lm_decoder")
+    li = SL.build(str(tmp_path), order=order, n_words=300, n_sent=4000, seed=3)
+    fst, words = str(tmp_path / "TLG.fst"), str(tmp_path / "words.txt")
+    GC.compile_to_files(li["arpa"], li["lexicon"], li["phones"], fst, words)
+    widx = {w: i for i, w in enumerate(li["words"])}
+    sents = [s[1:-1] for s in li["corpus"] if 2 <= len(s) - 2 <= 4][:3]
+    for max_active in (100, 500):
+        opts = (max_active, 50, 17.0, 8.0, 0.5, 1.0, 0.0, 30)
+        dec = LM.BrainSpeechDecoder(LM.DecodeResource(fst, "", "", words, ""), LM.DecodeOptions(*opts), max_frames=128, strict_order=True)
+        ref = D.OracleDecoder(fst, words, *opts)
+        bound = 0
+        for n, s in enumerate(sents):
+            logits = TLG.render_logits([li["prons"][widx[w]] for w in s], T=95, seed=40 + n, noise=1.5)
+            ref.reset(); ref.decode_logits(logits, np.zeros_like(logits), math.log(7.0)); ref.finish()
+            dec.Reset()
+            LM.DecodeNumpy(dec, logits, np.zeros_like(logits), math.log(7.0))
+            dec.FinishDecoding()
+            assert np.array_equal(dec.tokens_per_frame(), ref.tokens_per_frame()), (order, max_active, n)
+            D.cmp_strict(dec.result(), ref.results(), opts[4])
+            bound += int(ref.tokens_per_frame().max() > max_active)
+        assert bound > 0
