@@ -1295,7 +1295,7 @@ extern "C" int b2t_optimizer_step(b2t_engine* e, const b2t_adamw_args* a, float*
   TlScope tl_adam("adamw", 9, st);
   clip_adamw_kernel<<<e->n_chunks, 256, 0, st>>>(ap);
   CK(LAUNCHED());
-  bump_steps_kernel<<<((int)e->segs.size() + 127) / 128, 128, 0, st>>>(e->d_segs, (int)e->segs.size(), e->touched, e->steps);
+  bump_steps_kernel<<<((int)e->segs.size() + 127) / 128, 128, 0, st>>>(e->d_segs, (int)e->segs.size(), e->touched, e->steps, e->sumsq, a->max_grad_norm);
   CK(LAUNCHED());
   if (stats_out) CK(cudaMemcpyAsync(stats_out, e->stats, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;

@@ -66,6 +66,9 @@ clip_adamw_kernel(const AdamParams a) {
   float coef = 1.0f;
   if (a.max_norm > 0.f) coef = fminf(1.0f, a.max_norm / (total + 1e-6f));
   if (blockIdx.x == 0 && threadIdx.x == 0) { a.stats[0] = total; a.stats[1] = coef; }
+  // clip_grad_norm_(error_if_nonfinite=True) raises before optimizer.step(): a non-finite norm leaves parameters, moments and
+  // step counters untouched here, and the host raises on stats[0] (rnn_trainer mirror)
+  if (a.max_norm > 0.f && !isfinite(total)) return;
   const bool active = !(sg.day >= 0 && a.day_touched && !(a.day_touched[sg.day] > 0.f));
   if (!active) return;
   const int stp = a.step[cr.seg] + 1;              // every chunk of the segment reads the pre-increment value
@@ -91,9 +94,10 @@ clip_adamw_kernel(const AdamParams a) {
 
 // second tiny kernel: bump the step counters of active segments (kept separate so that all chunks of a
 // segment observe the same pre-increment value above)
-__global__ void bump_steps_kernel(const Segment* segs, int nseg, const float* day_touched, int* step) {
+__global__ void bump_steps_kernel(const Segment* segs, int nseg, const float* day_touched, int* step, const float* sumsq, float max_norm) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
+  if (max_norm > 0.f && !isfinite(sqrtf(*sumsq))) return;
   const Segment sg = segs[s];
   const bool active = !(sg.day >= 0 && day_touched && !(day_touched[sg.day] > 0.f));
   if (active) step[s] += 1;

@@ -67,7 +67,7 @@ def test_autograd_path_matches_reference_grads(mods):
     got = {n: p.grad for n, p in m.named_parameters()}
     for k, g in grads.items():
         assert got[k] is not None, k
-        assert util.rel_err(got[k].cpu().numpy().reshape(g.shape), g) < 6e-2, k
+        assert util.rel_err(got[k].cpu().numpy().reshape(g.shape), g) < util.GRAD_TOL, k
     for k, g in got.items():
         if k not in grads:
             assert g is None, k                       # day layers absent from the batch keep grad=None like the reference

@@ -116,7 +116,8 @@ def test_train_step_vs_golden(E, name, rec_schedule):
     assert util.rel_err(loss.cpu().numpy(), rest["loss_vec"]) < 2e-2      # logits carry bf16 error
     got = util.unflatten(E, cfg, eng.grads[:eng.n_params])
     errs = {k: util.rel_err(got[k].reshape(g.shape), g) for k, g in grads.items()}
-    bad = {k: round(r, 4) for k, r in errs.items() if r >= 6e-2}           # bf16 GEMM operands / bf16 activation stash
+    print("GRAD_ERR", name, rec_schedule, "max", round(max(errs.values()), 5), max(errs, key=errs.get))
+    bad = {k: round(r, 4) for k, r in errs.items() if r >= util.GRAD_TOL}           # bf16 GEMM operands / bf16 activation stash
     assert not bad, bad
     touched = eng.touched_days().cpu().numpy()
     assert sorted(np.nonzero(touched)[0].tolist()) == sorted(set(int(d) for d in rest["days"]))
@@ -132,10 +133,33 @@ def test_train_step_vs_golden(E, name, rec_schedule):
         # after one step the update is lr * m_hat/(sqrt(v_hat)+eps); compare the *delta* at bf16-gradient tolerance
         d_ref = v - params[k]
         d_got = newp[k].reshape(v.shape) - params[k]
-        assert np.abs(d_got - d_ref).max() < 6e-2 * np.abs(d_ref).max() + 1e-7, k
+        assert np.abs(d_got - d_ref).max() < util.GRAD_TOL * np.abs(d_ref).max() + 1e-7, k
     for k in newp:
         if k not in p1:
             assert np.array_equal(newp[k].reshape(params[k].shape), params[k].astype(np.float32)), k
+
+
+def test_nonfinite_gradient_norm_leaves_parameters_untouched(E):
+    """clip_grad_norm_(error_if_nonfinite=True) raises before optimizer.step() in the reference (rnn_trainer.py:550-558): with a
+    non-finite norm the fused clip+AdamW must not touch parameters, moments or step counters, and must report the norm."""
+    import gru_ctc_oracle as O
+    eng, cfg, params, grads, p1, rest = _engine_from_golden(E, "train_small.npz")
+    x = torch.from_numpy(rest["x"]).cuda()
+    eng.forward(x, torch.from_numpy(rest["days"]), training=True, smooth_mode=1)
+    eng.ctc_loss(torch.from_numpy(rest["labels"]), torch.from_numpy(O.adjusted_lens(rest["n_steps"])), torch.from_numpy(rest["lens"]), grad_scale=1.0 / x.shape[0])
+    eng.backward()
+    torch.cuda.synchronize()
+    good = eng.grads[:eng.n_params].clone()
+    before, steps = eng.params.clone(), eng.steps_tensor().clone()
+    eng.grads[7] = float("inf")
+    stats = eng.optimizer_step([1e-3] * 3, [0.0, 0.0, 1e-3], 0.9, 0.999, 0.1, 10.0)
+    torch.cuda.synchronize()
+    assert not torch.isfinite(stats[0]).item()
+    assert torch.equal(eng.params, before) and torch.equal(eng.steps_tensor(), steps)
+    eng.grads[:eng.n_params] = good                                     # the same step with finite gradients goes through
+    stats = eng.optimizer_step([1e-3] * 3, [0.0, 0.0, 1e-3], 0.9, 0.999, 0.1, 10.0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(stats[0]).item() and not torch.equal(eng.params, before)
 
 
 def test_greedy_edit_bit_exact(E):
@@ -221,7 +245,7 @@ def test_wide_batch_train_step_vs_oracle(E, monkeypatch, B, bg_cap, chunks, nsub
     bad = {}
     for k, g in ref_g.items():
         r = util.rel_err(got[k].reshape(np.asarray(g).shape), g)
-        if r >= 6e-2:
+        if r >= util.GRAD_TOL:
             bad[k] = round(r, 4)
     assert not bad, bad
     assert np.abs(got[f"day_weights.{n_days - 1}"]).max() == 0.0
