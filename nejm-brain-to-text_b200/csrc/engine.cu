@@ -169,10 +169,12 @@ struct b2t_engine {
   bool plans_ok = false, use_unfold_copy = false;
   GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw;
   std::vector<GemmPlan> p_dwih, p_dwhh, p_dwih0;   // p_dwih0: layer-0 dW_ih per time chunk (accumulating)
+  GemmPlan p_dwih_b, p_dwhh_b;                     // all layers' dW_ih (l >= 1) / dW_hh in one batched launch each (stack schedule)
+  bool dw_batched = false;
   std::vector<std::vector<GemmPlan>> p_in, p_dx;     // [layer >= 1][chunk]
   // side streams / events of the wave-front
   cudaStream_t lane[MAX_LANES + 2] = {};   // [MAX_LANES] = bulk stream (layer-0 projections / data gradients), [MAX_LANES + 1] = second bulk stream (weight gradients)
-  cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 2] = {}, ev_top = nullptr, ev_init = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 2] = {}, ev_top = nullptr, ev_init = nullptr, ev_dx0 = nullptr;
   std::vector<cudaEvent_t> ev_r, ev_dx;              // [layer * MAX_CHUNKS + chunk]
   cudaEvent_t ev_g0[MAX_CHUNKS] = {};                // layer-0 input projection chunks (issued ahead on the bulk stream)
   // state of the last forward
@@ -245,7 +247,8 @@ static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
     LayerBuf& b = e->lay[l];
     b.gx = c.take<float>(M * 3 * H);
     b.hseq = c.take<__nv_bfloat16>((M + Bp) * H);
-    b.hdrop = (tr && l < L - 1) ? c.take<__nv_bfloat16>(M * H) : nullptr;
+    __nv_bfloat16* hd = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;   // reserved for every layer so that the per-layer blocks have one stride (batched dW GEMMs)
+    b.hdrop = (l < L - 1) ? hd : nullptr;
     b.R = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
     b.Z = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
     b.Nn = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
@@ -307,6 +310,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
   }
   if (e->ev_start) cudaEventDestroy(e->ev_start);
   if (e->ev_top) cudaEventDestroy(e->ev_top);
+  if (e->ev_dx0) cudaEventDestroy(e->ev_dx0);
   if (e->ev_init) cudaEventDestroy(e->ev_init);
   for (cudaEvent_t ev : e->ev_r) if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->ev_dx) if (ev) cudaEventDestroy(ev);
@@ -337,6 +341,7 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
   e->touched = grads ? grads + e->n_params : nullptr;
   bool ok = cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_top, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_dx0, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_init, cudaEventDisableTiming) == cudaSuccess;
   // recurrence lanes outrank the bulk stream: when SMs free up, the latency-critical cooperative launches are placed first
   int prio_lo = 0, prio_hi = 0;
@@ -648,6 +653,32 @@ static int build_plans(b2t_engine* e) {
         }
       }
       if ((rc = gemm_plan_build(&e->p_dx[l][c], s))) return fail(B2T_ERR_CUDA, "dX plan %d/%d failed (%d)", l, c, rc);
+    }
+  }
+  // All layers' dW_ih (l >= 1) and dW_hh have one shape (3H x H over K = T'*Bpad rows): one batched launch each keeps every SM
+  // busy for ~3 waves of tiles instead of nine single-wave GEMMs on 108 of the SMs.  Needs one stride between the layers' buffers.
+  e->dw_batched = false;
+  if (e->stack && L >= 3 && env_int("B2T_DW_BATCHED", 1) != 0) {
+    const long long za = e->lay[1].dGx - e->lay[0].dGx;
+    const long long zc_ih = seg_off(e, "gru.weight_ih_l2") - seg_off(e, "gru.weight_ih_l1");
+    const long long zc_hh = seg_off(e, "gru.weight_hh_l1") - seg_off(e, "gru.weight_hh_l0");
+    bool uniform = za > 0 && zc_ih > 0 && zc_hh > 0 && za % 8 == 0;
+    for (int l = 0; l + 1 < L && uniform; ++l) {
+      const std::string a = std::to_string(l), b = std::to_string(l + 1);
+      uniform = e->lay[l + 1].dGx - e->lay[l].dGx == za && e->lay[l + 1].dGh - e->lay[l].dGh == za && e->lay[l + 1].hseq - e->lay[l].hseq == za &&
+                (l + 2 >= L || e->lay[l + 1].hdrop - e->lay[l].hdrop == za) && seg_off(e, "gru.weight_hh_l" + b) - seg_off(e, "gru.weight_hh_l" + a) == zc_hh &&
+                (l == 0 || seg_off(e, "gru.weight_ih_l" + b) - seg_off(e, "gru.weight_ih_l" + a) == zc_ih);
+    }
+    if (uniform) {
+      GemmSpec s;
+      s.a_mn = 1; s.b_mn = 1; s.epi = EPI_STORE; s.bn = 128;
+      s.M = 3 * H; s.N = H; s.K = M; s.lda = 3 * H; s.ldb = H; s.ldc = H;
+      s.a_zstride = za; s.b_zstride = za;
+      GemmSpec ih = s;
+      ih.nz = L - 1; ih.A = e->lay[1].dGx; ih.B = e->lay[0].hdrop; ih.C = e->grads + seg_off(e, "gru.weight_ih_l1"); ih.c_zstride = zc_ih;
+      GemmSpec hh = s;
+      hh.nz = L; hh.A = e->lay[0].dGh; hh.B = e->lay[0].hseq; hh.C = e->grads + seg_off(e, "gru.weight_hh_l0"); hh.c_zstride = zc_hh;
+      if (gemm_plan_build(&e->p_dwih_b, ih) == 0 && gemm_plan_build(&e->p_dwhh_b, hh) == 0) e->dw_batched = true;
     }
   }
   {  // dW_day[day_b] += xs[b]^T dpre[b]
@@ -1142,6 +1173,8 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     CK(cudaStreamWaitEvent(bw, e->ev_r[0], 0));
     // chain on the first bulk stream: layer-0 data gradient -> patch fold -> day layer; everything else on the second one
     { TlScope tl("DX0", 8, bs); CK(gemm_run(e->p_dx[0][0], bs)); ++g_launches; }
+    static const int dx0_first = env_int("B2T_TAIL_DX0_FIRST", 0);
+    if (dx0_first) { CK(cudaEventRecord(e->ev_dx0, bs)); CK(cudaStreamWaitEvent(bw, e->ev_dx0, 0)); }   // the fold -> day-layer chain hangs off DX0: let it own the chip first
     {
       FoldParams fp;
       fp.dxu = e->dxu; fp.xd = e->xd; fp.dpre = e->dpre; fp.dbias_day = e->grads + seg_off(e, "day_biases.0"); fp.bias_pitch = (int)r64(D);
@@ -1155,10 +1188,16 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     e->bucket_order.clear();
     { TlScope tl("dWih0", 7, bw); CK(gemm_run(e->p_dwih0[0], bw)); ++g_launches; }
     CK(cudaEventRecord(e->ev_bucket[1], bw)); e->bucket_order.push_back(1);
+    if (e->dw_batched) {
+      { TlScope tl("dWihB", 7, bw); CK(gemm_run(e->p_dwih_b, bw)); ++g_launches; }
+      { TlScope tl("dWhhB", 7, bw); CK(gemm_run(e->p_dwhh_b, bw)); ++g_launches; }
+    }
     for (int l = L - 1; l >= 0; --l) {
       const std::string sl = std::to_string(l);
-      if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwih[l], bw)); ++g_launches; }
-      { TlScope tl(("dWhh" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwhh[l], bw)); ++g_launches; }
+      if (!e->dw_batched) {
+        if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwih[l], bw)); ++g_launches; }
+        { TlScope tl(("dWhh" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwhh[l], bw)); ++g_launches; }
+      }
       if (!e->states_given) {
         reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bw>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
         CK(LAUNCHED());

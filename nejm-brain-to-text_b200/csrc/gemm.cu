@@ -107,6 +107,7 @@ int gemm_plan_build(GemmPlan* pl, const GemmSpec& s) {
     const long long rows = s.a_mn ? s.M : (s.a_rin > 0 ? (long long)s.a_rin * s.a_rout : s.M);
     const long long tiles256 = (long long)ceil_div(rows, GEMM_BM) * ceil_div(s.N, 256) * p.nz;
     if (s.N % 256 == 0 && s.epi != EPI_ATOMIC && s.epi != EPI_DAY && (tiles256 >= num_sms() || s.gate || s.done)) bn = 256;   // (the day layer's Philox epilogue is slower when unrolled over 8 chunks: measured 258 vs 105 us)
+    if (s.bn == 128 || (s.bn == 256 && s.N % 256 == 0)) bn = s.bn;
     if (force == 128 || (force == 256 && s.N % 256 == 0)) bn = force;
   }
   pl->bn = bn;

@@ -40,6 +40,7 @@ struct GemmSpec {
   int gate_need = 0, gate_rows_per_step = 0, gate_steps = 0;
   int* done = nullptr;
   int tm_reverse = 0, max_ctas = 0;
+  int bn = 0;                 // force the tile width (128 / 256); 0 = chosen by the planner
 };
 
 struct GemmPlan {
