@@ -23,9 +23,12 @@
 
 namespace {
 
-constexpr int PB_MAX_BEAM = 64;       // second_beam_size limit
+constexpr int PB_MAX_BEAM = 512;      // second_beam_size limit (BASELINE.json configs[4] sweeps the width to 500)
 constexpr int PB_MAX_TOPK = 64;       // first_beam_size limit
-constexpr int PB_MAX_CAND = 704;      // >= second_beam * (first_beam + 1) (checked by the host entry point)
+constexpr int PB_MAX_BUCKETS = 1109;  // largest bucket count the emulated unordered_map can reach with <= 512 elements (13 -> ... -> 541), one step spare
+constexpr int PB_SMEM_LIMIT = 227 * 1024;
+// The per-utterance working set lives in dynamic shared memory sized from the beams (second_beam * (first_beam + 1) candidates of
+// 32 bytes dominate: 3.5 KB at 10 x 10, 180 KB at 512 x 10); the host entry point rejects combinations beyond 227 KB.
 #define PB_NEG (-3.402823466e+38f)    // -kFloatMax
 
 struct Hyp;
@@ -33,11 +36,12 @@ struct PbParams {
   const float* logp;   // [N][T][C]
   const int* lens;     // [N]
   int N, T, C, blank, first_beam, second_beam, max_len;
+  int cand_cap, chash_cap;                             // candidates per frame; candidate hash size (power of two)
   // per-utterance scratch
   int* trie_parent; int* trie_token; int trie_cap;     // [N][trie_cap]
   int* trie_hash; int trie_hash_cap;                   // [N][trie_hash_cap] (power of two) -> trie node or -1
   unsigned long long* trie_h64;                        // [N][trie_cap] PrefixHash of the node's prefix (ctc_prefix_beam_search.h:44-53)
-  int* times;          // [N][2 buffers][PB_MAX_CAND][2 (s, ns)][max_len]
+  int* times;          // [N][2 buffers][cand_cap][2 (s, ns)][max_len]
   // outputs
   int* out_ids; int* out_len; float* out_score; float* out_viterbi; int* out_times; int* out_n;
   int* status;
@@ -48,8 +52,8 @@ struct Hyp {
   float s, ns, v_s, v_ns, cur_token_prob;
 };
 
-constexpr int PB_HASH_CAND = 2048;  // >= 2 * PB_MAX_CAND, power of two
 constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned short CH_EMPTY = 0xffffu;
 
 __device__ inline float log_add(float x, float y) {
   if (x <= PB_NEG) return y;
@@ -80,12 +84,12 @@ __device__ inline void warp_argmax(float& v, int& idx) {
 // writers are visited in the map's order, not in score order.  libstdc++ keeps all nodes in one forward list; a node whose
 // bucket is empty goes to the head of the list, otherwise to the beginning of its bucket's run; growing the table re-inserts
 // the nodes in list order by the same rule; clear() keeps the bucket count (13 after the first insertion, then the next
-// prime >= twice the old count: 29, 59, 127).  Emulated serially for the <= PB_MAX_BEAM hypotheses of a frame.
+// prime >= twice the old count in libstdc++'s table: 29, 59, 127, 257, 541).  Emulated serially for the hypotheses of a frame.
 struct UMapOrder {
   int B, next_resize, head, n;
-  int* nxt;                  // [PB_MAX_BEAM] successor in the list (-1 = end)
-  int* before;               // [128] per bucket: -2 = empty, -1 = the list head sentinel, >= 0 = node preceding the bucket's run
-  unsigned long long* h;     // [PB_MAX_BEAM] hash of the node's prefix
+  int* nxt;                  // [second_beam] successor in the list (-1 = end)
+  int* before;               // [PB_MAX_BUCKETS] per bucket: -2 = empty, -1 = the list head sentinel, >= 0 = node preceding the bucket's run
+  unsigned long long* h;     // [second_beam] hash of the node's prefix
   __device__ void clear() {
     head = -1; n = 0;
     for (int b = 0; b < B; ++b) before[b] = -2;
@@ -108,7 +112,7 @@ struct UMapOrder {
       const int minb = max(n + 1, next_resize ? 0 : 11);
       if (minb >= B) {
         const int want = max(minb + 1, 2 * B);
-        const int nb = want <= 13 ? 13 : want <= 29 ? 29 : want <= 59 ? 59 : 127;
+        const int nb = want <= 13 ? 13 : want <= 29 ? 29 : want <= 59 ? 59 : want <= 127 ? 127 : want <= 257 ? 257 : want <= 541 ? 541 : 1109;
         int cnt = 0;                                       // re-insert in the current list order
         for (int q = head; q >= 0; q = nxt[q]) scratch[cnt++] = q;
         head = -1;
@@ -123,15 +127,19 @@ struct UMapOrder {
 };
 
 __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
-  // the state lane 0 walks with dependent accesses lives in shared memory (33 KB); the trie, its hash and the time vectors stay
+  // the state lane 0 walks with dependent accesses lives in (dynamic) shared memory; the trie, its hash and the time vectors stay
   // in global memory (one or two accesses per pair / copied by all lanes)
+  extern __shared__ __align__(16) unsigned char pb_smem[];
   __shared__ int s_top[PB_MAX_TOPK];
-  __shared__ int s_order[PB_MAX_BEAM];
-  __shared__ Hyp s_cur[PB_MAX_BEAM];
-  __shared__ Hyp s_nxt[PB_MAX_CAND];
-  __shared__ int s_chash[PB_HASH_CAND];
-  __shared__ int s_iter[PB_MAX_BEAM], s_unext[PB_MAX_BEAM], s_ubefore[128], s_scratch[PB_MAX_BEAM];
-  __shared__ unsigned long long s_uh[PB_MAX_BEAM];
+  Hyp* s_nxt = reinterpret_cast<Hyp*>(pb_smem);
+  Hyp* s_cur = s_nxt + p.cand_cap;
+  unsigned long long* s_uh = reinterpret_cast<unsigned long long*>(s_cur + p.second_beam);
+  int* s_order = reinterpret_cast<int*>(s_uh + p.second_beam);
+  int* s_iter = s_order + p.second_beam;
+  int* s_unext = s_iter + p.second_beam;
+  int* s_scratch = s_unext + p.second_beam;
+  int* s_ubefore = s_scratch + p.second_beam;
+  unsigned short* s_chash = reinterpret_cast<unsigned short*>(s_ubefore + PB_MAX_BUCKETS);
   const int u = blockIdx.x, lane = threadIdx.x;
   if (u >= p.N) return;
   const float* logp = p.logp + (size_t)u * p.T * p.C;
@@ -139,7 +147,8 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
   int* tpar = p.trie_parent + (size_t)u * p.trie_cap;
   int* ttok = p.trie_token + (size_t)u * p.trie_cap;
   int* thash = p.trie_hash + (size_t)u * p.trie_hash_cap;
-  int* chash = s_chash;
+  unsigned short* chash = s_chash;
+  const unsigned chmask = (unsigned)p.chash_cap - 1u;
   unsigned long long* th64 = p.trie_h64 + (size_t)u * p.trie_cap;
   int ntrie = 1;                                        // node 0 = empty prefix (lane 0's copy is the authoritative one)
   UMapOrder um;                                         // lane 0 only
@@ -151,9 +160,9 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
     s_iter[0] = 0;
   }
   for (int i = lane; i < p.trie_hash_cap; i += 32) thash[i] = -1;
-  for (int i = lane; i < PB_HASH_CAND; i += 32) chash[i] = -1;
+  for (int i = lane; i < p.chash_cap; i += 32) chash[i] = CH_EMPTY;
   const size_t tstride = (size_t)2 * p.max_len;          // per hypothesis: times_s | times_ns
-  int* tbuf[2] = {p.times + (size_t)u * 2 * PB_MAX_CAND * tstride, p.times + ((size_t)u * 2 + 1) * PB_MAX_CAND * tstride};
+  int* tbuf[2] = {p.times + (size_t)u * 2 * p.cand_cap * tstride, p.times + ((size_t)u * 2 + 1) * p.cand_cap * tstride};
 
   Hyp* cur = s_cur;
   Hyp* nxt = s_nxt;
@@ -193,16 +202,16 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
         int c_n[2] = {0, 0}, c_set[2] = {-1, -1}, ncp = 0;
         if (lane == 0) {
           auto find_or_add = [&](int node, int len, int last) -> int {
-            unsigned slot = mix((unsigned)node, 0x51u) & (PB_HASH_CAND - 1);
+            unsigned slot = mix((unsigned)node, 0x51u) & chmask;
             for (;;) {
-              const int j = chash[slot];
-              if (j < 0) break;
-              if (nxt[j].node == node) return j;
-              slot = (slot + 1) & (PB_HASH_CAND - 1);
+              const unsigned short j = chash[slot];
+              if (j == CH_EMPTY) break;
+              if (nxt[j].node == node) return (int)j;
+              slot = (slot + 1) & chmask;
             }
-            if (nn >= PB_MAX_CAND) { overflow = true; return nn - 1; }
+            if (nn >= p.cand_cap) { overflow = true; return nn - 1; }
             nxt[nn] = Hyp{node, len, last, PB_NEG, PB_NEG, PB_NEG, PB_NEG, PB_NEG};
-            chash[slot] = nn;
+            chash[slot] = (unsigned short)nn;
             return nn++;
           };
           auto child = [&](int node, int tok) -> int {
@@ -281,18 +290,19 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
     // 3. second beam: the best second_beam candidates by score, descending; the earlier candidate wins among equal scores
     const int keep = min(min(nn, p.second_beam), PB_MAX_BEAM);
     {
-      // candidate scores are recomputed per round from nxt (cheap); taken candidates are marked in a per-lane bitmask
-      // (lane l owns candidates l, l + 32, ...: at most PB_MAX_CAND / 32 = 22 of them)
-      unsigned taken = 0;
+      // the candidates' scores are computed once and parked in cur_token_prob (dead after the token passing of this frame and
+      // never read from a beam entry); a taken candidate is marked with -inf (scores are > -FLT_MAX).  Lane l owns l, l + 32, ...
+      for (int i = lane; i < nn; i += 32) nxt[i].cur_token_prob = hyp_score(nxt[i]);
+      __syncwarp();
       for (int r = 0; r < keep; ++r) {
         float bv = 0.f; int bi = -1;
-        for (int i = lane, q = 0; i < nn; i += 32, ++q) {
-          if ((taken >> q) & 1u) continue;
-          const float sc = hyp_score(nxt[i]);
+        for (int i = lane; i < nn; i += 32) {
+          const float sc = nxt[i].cur_token_prob;
+          if (sc == -INFINITY) continue;
           if (bi < 0 || sc > bv) { bv = sc; bi = i; }
         }
         warp_argmax(bv, bi);
-        if (bi >= 0 && (bi & 31) == lane) taken |= 1u << (bi >> 5);
+        if (bi >= 0 && (bi & 31) == lane) nxt[bi].cur_token_prob = -INFINITY;
         if (lane == 0) s_order[r] = bi;
       }
     }
@@ -304,7 +314,7 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
       int* dst = tc + (size_t)r * tstride;
       for (int i = lane; i < (int)tstride; i += 32) dst[i] = src[i];
     }
-    for (int i = lane; i < PB_HASH_CAND; i += 32) chash[i] = -1;
+    for (int i = lane; i < p.chash_cap; i += 32) chash[i] = CH_EMPTY;
     ncur = keep;
     __syncwarp();
     if (lane == 0) {                                     // cur_hyps_.clear(); cur_hyps_[prefix] = score in sorted order
@@ -362,12 +372,17 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
   int *d_lens, *d_tp, *d_tt, *d_th, *d_times, *d_ids, *d_len, *d_otimes, *d_n, *d_status;
   p.trie_hash_cap = 1024;
   while (p.trie_hash_cap < 2 * p.trie_cap) p.trie_hash_cap *= 2;
-  if (second_beam * (first_beam + 1) > PB_MAX_CAND) {
-    snprintf(g_perr, sizeof(g_perr), "second_beam * (first_beam + 1) must be <= %d", PB_MAX_CAND);
+  p.cand_cap = second_beam * (std::min(first_beam, C) + 1);
+  p.chash_cap = 256;
+  while (p.chash_cap < 2 * p.cand_cap && p.chash_cap < 8192) p.chash_cap *= 2;
+  while (p.chash_cap * 3 < p.cand_cap * 4) p.chash_cap *= 2;          // load factor <= 0.75 when the 2x table would not fit
+  const size_t smem = (size_t)p.cand_cap * sizeof(Hyp) + (size_t)second_beam * (sizeof(Hyp) + 8 + 4 * 4) + PB_MAX_BUCKETS * 4 + (size_t)p.chash_cap * 2;
+  if (p.cand_cap >= 0xffff || smem > (size_t)PB_SMEM_LIMIT) {
+    snprintf(g_perr, sizeof(g_perr), "second_beam %d x first_beam %d needs %zu bytes of shared memory per utterance (limit %d)", second_beam, first_beam, smem, PB_SMEM_LIMIT);
     return B2T_ERR_UNSUPPORTED;
   }
   const size_t nb = (size_t)N * second_beam;
-  const size_t times_elems = (size_t)N * 2 * PB_MAX_CAND * 2 * max_len;
+  const size_t times_elems = (size_t)N * 2 * p.cand_cap * 2 * max_len;
   // one cached device workspace per host thread, grown on demand (cudaMalloc / cudaFree per call cost more than the search)
   struct Ws { void* base = nullptr; size_t cap = 0; ~Ws() { /* released with the context */ } };
   static thread_local Ws ws;
@@ -403,7 +418,8 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   cudaDeviceSynchronize();
   const double t_k0 = now();
-  prefix_beam_kernel<<<N, 32>>>(p);
+  cudaFuncSetAttribute(prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM_LIMIT);
+  prefix_beam_kernel<<<N, 32, smem>>>(p);
   cudaError_t e = cudaDeviceSynchronize();
   if (timing) fprintf(stderr, "b2t prefix beam: N=%d T=%d beams %dx%d trie_cap %d: setup %.2f ms, kernel %.2f ms\n", N, T, first_beam, second_beam, p.trie_cap, t_k0 - t_begin, now() - t_k0);
   int rc = 0;

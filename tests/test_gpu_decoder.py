@@ -217,6 +217,29 @@ def test_prefix_beam_wide(LM):
             assert all(abs(a[1] - b[1]) < 1e-4 and abs(a[2] - b[2]) < 1e-4 for a, b in zip(ours[n], ref))
 
 
+@pytest.mark.parametrize("sb", [100, 500, 512])
+def test_prefix_beam_sweep_widths(LM, sb):
+    """BASELINE.json configs[4] sweeps the beam width to 500: second beams beyond the old limit of 64 (the emulated unordered_map
+    grows through 257 and 541 buckets), hypotheses / scores / Viterbi times against the oracle."""
+    rng = np.random.RandomState(40 + sb)
+    x = rng.randn(2, 60, 41).astype(np.float32) * 1.2
+    x[..., 0] += 1.5
+    lp = x - np.log(np.exp(x).sum(-1, keepdims=True))
+    ours = LM.ctc_prefix_beam_search(lp, first_beam_size=10, second_beam_size=sb)
+    for n in range(2):
+        ref = D.prefix_search(lp[n], 10, sb)
+        assert len(ours[n]) == len(ref) and len(ref) > 64
+        assert [r[0] for r in ours[n]] == [r[0] for r in ref]
+        assert all(abs(a[1] - b[1]) < 1e-4 and abs(a[2] - b[2]) < 1e-4 for a, b in zip(ours[n], ref))
+        assert [r[3] for r in ours[n]] == [r[3] for r in ref]
+
+
+def test_prefix_beam_rejects_what_does_not_fit(LM):
+    lp = np.log(np.full((1, 4, 41), 1.0 / 41, dtype=np.float32))
+    with pytest.raises(Exception, match="shared memory"):
+        LM.ctc_prefix_beam_search(lp, first_beam_size=40, second_beam_size=512)
+
+
 @pytest.mark.skipif(D.real_graph() is None, reason="the shipped 1-gram graph is staged under oracle/_ref/ by __graft_entry__.build()")
 @pytest.mark.parametrize("max_active,n_utt", [(7000, 2), (500, 5)])
 def test_shipped_1gram_graph_vs_oracle(LM, max_active, n_utt):
