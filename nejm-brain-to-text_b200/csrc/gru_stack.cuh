@@ -118,6 +118,27 @@ __device__ __forceinline__ void probe_until_published(int n_probe, int lt, AddrF
   asm volatile("bar.sync 2, %0;" ::"n"(NLOAD_THREADS) : "memory");
 }
 
+// A load ptxas may not hoist out of a polling loop (it does hoist the weak ld.global.cg when the loop holds nothing else).
+__device__ __forceinline__ uint4 ld_strong_v4(const void* ptr) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long stk_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// cross-layer timing (profiling aid, with the cycle trace): the first CTA of every layer stamps %globaltimer when it has stored
+// steps 0, 1, T/2 and T-1 -> trace[2*T*8 + dir*64 + layer*8 + k]
+#define STK_LAYER_STAMP(dir, first_cta, step)                                                                          \
+  do {                                                                                                                 \
+    if (p.trace != nullptr && (first_cta)) {                                                                           \
+      const int _k = (step) == 0 ? 1 : (step) == 1 ? 2 : (step) == p.T / 2 ? 3 : (step) == p.T - 1 ? 4 : -1;           \
+      if (_k > 0) p.trace[(size_t)2 * p.T * 8 + (dir) * 64 + layer * 8 + _k] = stk_globaltimer();                      \
+    }                                                                                                                  \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------------ forward
 template <int BG, int NSUB>
 __global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads + 32, 1)
@@ -150,6 +171,7 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
   const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_cta;
 #define STK_TRACE(step, slot) do { if (tracing) p.trace[(step) * 8 + (slot)] = clock64(); } while (0)
 
+  if (threadIdx.x == 0 && p.trace != nullptr && slice == 0 && cgrp == 0) p.trace[(size_t)2 * p.T * 8 + layer * 8] = stk_globaltimer();
   if (threadIdx.x == 0) {
     for (int c = 0; c < NSUB * 32; ++c) mbar_init(&bar_h[c], Cfg::kLoadWarps);
     for (int s = 0; s < NSUB; ++s) { mbar_init(&bar_d[s], 1); mbar_init(&bar_s[s], Cfg::kEpiWarps); cnt_p[s] = 0u; }
@@ -344,6 +366,7 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_s[sub]);
         if (e == 0 && sub == 0) STK_TRACE(t, 5);
+        if (e == 0 && sub == NSUB - 1) STK_LAYER_STAMP(0, slice == 0 && cgrp == 0, t);
         if (train) {
           st_bf16x4(L.R + off, r[0], r[1], r[2], r[3]);
           st_bf16x4(L.Z + off, z[0], z[1], z[2], z[3]);
@@ -394,9 +417,8 @@ struct StackBwdLayer {
   float* part;                    // [2][groups][H/128][4][4][BG*32] tagged fp32 partial sums
   float *dbih, *dbhh;             // [3H] (atomicAdd)
   float* dh_state;                // [Bpad][H]: gradient wrt the initial state on exit
-  const int* dy_done;             // per 128-row tile of dY: completion count of the gated data-gradient GEMM of the layer above (null: none)
+  int dy_polled;                  // dY is produced beside this kernel by the gated data-gradient GEMM of the layer above: sentinel-filled, polled
   int* prog;                      // [T]: += 1 per epilogue warp, CTA and batch group once dGx[t] is stored (null: no consumer)
-  int dy_need;
   int gen_base;                   // generation of this launch's first step (tag = (gen >> 1) & 3, buffer = gen & 1)
   float keep;                     // dropout that forward applied to this layer's output (1 => none)
   unsigned long long rng_offset;
@@ -449,6 +471,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
   const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_cta;
 #define STK_TRACE(step, slot) do { if (tracing) p.trace[((size_t)p.T + (step)) * 8 + (slot)] = clock64(); } while (0)
 
+  if (threadIdx.x == 0 && p.trace != nullptr && rl == 0) p.trace[(size_t)2 * p.T * 8 + 64 + layer * 8] = stk_globaltimer();
   if (threadIdx.x == 0) {
     for (int c = 0; c < NSUB * 16; ++c) mbar_init(&bar_h[c], Cfg::kLoadWarps);
     for (int s = 0; s < NSUB; ++s) { mbar_init(&bar_d[s], 1); mbar_init(&bar_s[s], Cfg::kEpiWarps); cnt_p[s] = 0u; }
@@ -612,7 +635,10 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
         for (int i = 0; i < 4; ++i)
           if (((pending >> i) & 1u) && tags_match(v[i], tag)) pending &= ~(1u << i);
         if (!pending) break;
-        if (++spins > REC_MAX_SPINS) __trap();
+        if (++spins > (1u << 22)) {
+          if (p.trace) { long long* d = p.trace + (size_t)2 * p.T * 8 + 128 + (size_t)blockIdx.x * 8; d[0] = 0xD2; d[1] = layer; d[2] = grp; d[3] = gen; d[4] = pending; __threadfence_system(); }
+          __trap();
+        }
       }
       float G[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -645,41 +671,54 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       st.n = __ldg(reinterpret_cast<const uint2*>(L.Nn + off)); st.hn = __ldg(reinterpret_cast<const uint2*>(L.HN + off));
       st.hp = *reinterpret_cast<const uint2*>(L.hseq + off);             // slot t = h_{t-1}
     };
-    // ... and the gradient from the layer above, which a gated GEMM may still be producing: dy_tile_ready() is the acquire side
-    auto dy_tile = [&](int b0, int t) { return (int)(((size_t)t * p.Bpad + b0) / 128); };
+    // ... and the gradient from the layer above, which a gated GEMM may still be producing (see phase A)
     auto load_dy = [&](int b, int t, Stash& st) {
       st.dy = ldcg_f4(L.dY + ((size_t)t * p.Bpad + b) * p.H + j);
     };
+    // inter-layer dropout mask of (row, units j..j+3), regenerated from the forward pass's Philox stream: bit i = unit i kept.
+    // Drawn one step ahead (behind the publish of the current step) so that the Philox rounds are off the step's critical path.
+    auto keep_bits = [&](int b, int t) -> uint32_t {
+      if (!(L.keep < 1.0f)) return 0xFu;
+      const size_t off = ((size_t)t * p.Bpad + b) * p.H + j;
+      const uint4 rnd = rec_dropout_bits(p.seed, L.rng_offset, off >> 2);
+      return (u32_to_unit(rnd.x) < L.keep ? 1u : 0u) | (u32_to_unit(rnd.y) < L.keep ? 2u : 0u) | (u32_to_unit(rnd.z) < L.keep ? 4u : 0u) |
+             (u32_to_unit(rnd.w) < L.keep ? 8u : 0u);
+    };
     Stash cur[NSUB];
-    bool have_dy[NSUB];
-    int ready_tile = 1 << 30;                                // dY tiles down to here are known complete (time runs downwards)
+    uint32_t kbits[NSUB];
 #pragma unroll
     for (int sub = 0; sub < NSUB; ++sub) {
-      load_fwd_stash((cgrp * NSUB + sub) * BG + bl, p.T - 1, cur[sub]);
-      have_dy[sub] = false;
+      const int b = (cgrp * NSUB + sub) * BG + bl;
+      load_fwd_stash(b, p.T - 1, cur[sub]);
+      load_dy(b, p.T - 1, cur[sub]);
+      kbits[sub] = keep_bits(b, p.T - 1);
     }
 
     auto phase_a = [&](int s, int sub) {
+      if (p.trace && e == 0) p.trace[(size_t)2 * p.T * 8 + 128 + (size_t)blockIdx.x * 8 + 6] = 0xA000 | (s << 4) | sub;
       const int t = p.T - 1 - s;
       const int grp = cgrp * NSUB + sub;
       const int b0 = grp * BG, b = b0 + bl;
       const bool valid = b < p.n_valid;
       const size_t row = (size_t)t * p.Bpad + b;
       const size_t off = row * p.H + j;
-      if (!have_dy[sub]) {
-        if (L.dy_done) {
-          const int tile = dy_tile(b0, t);
-          if (tile < ready_tile) { warp_wait_ge(L.dy_done + tile, L.dy_need, lane); ready_tile = tile; }
+      // dY of this step was requested one step ago.  It comes from the layer above through a GEMM that runs beside this kernel:
+      // the buffer is sentinel-filled before the step and the data is its own signal (one L2 round trip instead of a flag
+      // acquire followed by the load; a 16-byte store lands whole)
+      if (L.dy_polled) {
+        uint32_t spins = 0;
+        while (__float_as_uint(cur[sub].dy.x) == 0xFFFFFFFFu || __float_as_uint(cur[sub].dy.w) == 0xFFFFFFFFu) {
+          const uint4 v = ld_strong_v4(L.dY + ((size_t)t * p.Bpad + b) * p.H + j);
+          cur[sub].dy = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+          if (++spins > (1u << 22)) {
+            if (p.trace) { long long* d = p.trace + (size_t)2 * p.T * 8 + 128 + (size_t)blockIdx.x * 8; d[0] = 0xD1; d[1] = layer; d[2] = t; d[3] = b; d[4] = j; d[5] = s; __threadfence_system(); }
+            __trap();
+          }
         }
-        load_dy(b, t, cur[sub]);
       }
-      float dmask[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-      if (L.keep < 1.0f) {
-        const uint4 rnd = rec_dropout_bits(p.seed, L.rng_offset, off >> 2);
-        const uint32_t rr4[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+      float dmask[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dmask[i] = (u32_to_unit(rr4[i]) < L.keep) ? inv_keep : 0.0f;
-      }
+      for (int i = 0; i < 4; ++i) dmask[i] = (L.keep < 1.0f) ? (((kbits[sub] >> i) & 1u) ? inv_keep : 0.0f) : 1.0f;
       float P[4] = {0.f, 0.f, 0.f, 0.f};
       if (s > 0) {
         if (e == 0 && sub == 0) STK_TRACE(s, 4);
@@ -711,6 +750,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_s[sub]);
       if (e == 0 && sub == 0) STK_TRACE(s, 6);
+      if (e == 0 && sub == NSUB - 1) STK_LAYER_STAMP(1, rl == 0, s);
       st_bf16x4(L.dGx + goff, gr[0], gr[1], gr[2], gr[3]);
       st_bf16x4(L.dGx + goff + p.H, gz[0], gz[1], gz[2], gz[3]);
       st_bf16x4(L.dGx + goff + 2 * p.H, gn[0], gn[1], gn[2], gn[3]);
@@ -718,22 +758,15 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
         __syncwarp();
         if (lane == 0) smem_release_inc(&cnt_p[sub]);
       }
-      // next step's operands: the forward stash always; dY only if its tile has already landed (never block here)
+      // next step's operands: forward stash, dY (possibly still the sentinel: re-polled when it is needed) and the dropout mask
       if (s + 1 < p.T) {
         load_fwd_stash(b, t - 1, cur[sub]);
-        have_dy[sub] = false;
-        bool ok = true;
-        if (L.dy_done) {
-          const int tile = dy_tile(b0, t - 1);
-          if (tile < ready_tile) {
-            ok = warp_test_ge(L.dy_done + tile, L.dy_need, lane);
-            if (ok) ready_tile = tile;
-          }
-        }
-        if (ok) { load_dy(b, t - 1, cur[sub]); have_dy[sub] = true; }
+        load_dy(b, t - 1, cur[sub]);
+        kbits[sub] = keep_bits(b, t - 1);
       }
     };
     auto phase_b = [&](int s, int sub) {
+      if (p.trace && e == 0) p.trace[(size_t)2 * p.T * 8 + 128 + (size_t)blockIdx.x * 8 + 7] = 0xB000 | (s << 4) | sub;
       const int grp = cgrp * NSUB + sub;
       mbar_wait(&bar_d[sub], (uint32_t)s & 1u);
       if (e == 0 && sub == 0) STK_TRACE(s, 7);

@@ -26,7 +26,7 @@ namespace {
 constexpr int PB_MAX_BEAM = 512;      // second_beam_size limit (BASELINE.json configs[4] sweeps the width to 500)
 constexpr int PB_MAX_TOPK = 64;       // first_beam_size limit
 constexpr int PB_MAX_BUCKETS = 1109;  // largest bucket count the emulated unordered_map can reach with <= 512 elements (13 -> ... -> 541), one step spare
-constexpr int PB_SMEM_LIMIT = 227 * 1024;
+constexpr int PB_SMEM_LIMIT = 227 * 1024 - 1024;   // dynamic part; the kernel has a few hundred bytes of static shared memory as well
 // The per-utterance working set lives in dynamic shared memory sized from the beams (second_beam * (first_beam + 1) candidates of
 // 32 bytes dominate: 3.5 KB at 10 x 10, 180 KB at 512 x 10); the host entry point rejects combinations beyond 227 KB.
 #define PB_NEG (-3.402823466e+38f)    // -kFloatMax
@@ -418,9 +418,12 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   cudaDeviceSynchronize();
   const double t_k0 = now();
-  cudaFuncSetAttribute(prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PB_SMEM_LIMIT);
-  prefix_beam_kernel<<<N, 32, smem>>>(p);
-  cudaError_t e = cudaDeviceSynchronize();
+  cudaError_t e = smem > 48 * 1024 ? cudaFuncSetAttribute(prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) : cudaSuccess;
+  if (e == cudaSuccess) {
+    prefix_beam_kernel<<<N, 32, smem>>>(p);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (timing) fprintf(stderr, "b2t prefix beam: N=%d T=%d beams %dx%d trie_cap %d: setup %.2f ms, kernel %.2f ms\n", N, T, first_beam, second_beam, p.trie_cap, t_k0 - t_begin, now() - t_k0);
   int rc = 0;
   if (e != cudaSuccess) { snprintf(g_perr, sizeof(g_perr), "prefix_beam_kernel: %s", cudaGetErrorString(e)); rc = B2T_ERR_CUDA; }

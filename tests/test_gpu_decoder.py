@@ -229,9 +229,15 @@ def test_prefix_beam_sweep_widths(LM, sb):
     for n in range(2):
         ref = D.prefix_search(lp[n], 10, sb)
         assert len(ours[n]) == len(ref) and len(ref) > 64
-        assert [r[0] for r in ours[n]] == [r[0] for r in ref]
-        assert all(abs(a[1] - b[1]) < 1e-4 and abs(a[2] - b[2]) < 1e-4 for a, b in zip(ours[n], ref))
-        assert [r[3] for r in ours[n]] == [r[3] for r in ref]
+        # hypotheses with exactly equal scores come out in creation order here and in std::sort's (unstable) order in the
+        # reference: compare per hypothesis, and the order through the scores
+        so = {tuple(r[0]): r for r in ours[n]}
+        sr = {tuple(r[0]): r for r in ref}
+        assert set(so) == set(sr)
+        for k, r in sr.items():
+            assert so[k][1] == pytest.approx(r[1], abs=1e-4) and so[k][2] == pytest.approx(r[2], abs=1e-4) and so[k][3] == r[3], k
+        assert all(a[1] >= b[1] for a, b in zip(ours[n], ours[n][1:]))
+        assert [r[0] for r in ours[n][:20]] == [r[0] for r in ref[:20]] or len({round(r[1], 6) for r in ref[:21]}) < 21
 
 
 def test_prefix_beam_rejects_what_does_not_fit(LM):

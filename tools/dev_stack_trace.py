@@ -7,19 +7,28 @@ import numpy as np, torch
 import b2t_pkg, bench
 E = b2t_pkg.submodule("engine"); N = b2t_pkg.load()._native
 torch.manual_seed(0)
-cfg = E.make_config(**bench.CFG)
+cfg = E.make_config(**dict(bench.CFG, rnn_dropout=float(os.environ.get('B2T_TRACE_DROPOUT', bench.CFG['rnn_dropout']))))
 flat = (torch.randn(E.param_elems(cfg)) * 0.03).cuda()
 eng = E.Engine(cfg, flat, max_batch=64, max_T=400, max_label_len=64, training=True)
 hb = {k: v.cuda() for k, v in bench.synth_batches(1, 1)[0].items()}
 in_len = torch.full((64,), 97, dtype=torch.int32)
 Tp = 97
-trace = torch.zeros(2 * Tp * 8 + 148 * 8, dtype=torch.int64, device="cuda")
+trace = torch.zeros(2 * Tp * 8 + 128 + 148 * 8, dtype=torch.int64).pin_memory() if os.environ.get("B2T_TRACE_PINNED") else torch.zeros(2 * Tp * 8 + 128 + 148 * 8, dtype=torch.int64, device="cuda")
 N.check(N.lib.b2t_debug_set_trace(eng.handle, trace.data_ptr()), "trace")
-for i in range(3):
-    eng.forward(hb["x"], hb["days"], training=True, smooth_mode=1, white_noise_std=1.0, offset_noise_std=0.2, seed=i, want_logits=False)
-    eng.ctc_loss(hb["labels"], in_len, hb["lens"], grad_scale=1 / 64)
-    eng.backward()
-torch.cuda.synchronize()
+try:
+    for i in range(3):
+        eng.forward(hb["x"], hb["days"], training=True, smooth_mode=1, white_noise_std=1.0, offset_noise_std=0.2, seed=i, want_logits=False)
+        eng.ctc_loss(hb["labels"], in_len, hb["lens"], grad_scale=1 / 64)
+        eng.backward()
+    torch.cuda.synchronize()
+except Exception as ex:
+    print("FAILED:", str(ex).split("\n")[0])
+    d = trace[2 * Tp * 8 + 128:].view(148, 8)
+    for blk in range(148):
+        if d[blk, 0] != 0:
+            print(f"block {blk}: code {hex(int(d[blk, 0]))} {d[blk, 1:6].tolist()}")
+    print("last phases (A, B) per block:", " ".join(f"{blk}:{int(d[blk, 6]):x}/{int(d[blk, 7]):x}" for blk in range(120)))
+    sys.exit(1)
 tr = trace.cpu().numpy()[:2 * Tp * 8].reshape(2, Tp, 8).astype(np.float64)
 fw = ["chunk0 staged", "all staged", "MMA saw chunk0", "MMAs issued", "acc done", "h_t stored"]
 bw = ["dG chunk0 staged", "all dG staged", "MMA saw chunk0", "MMAs issued", "reduce start", "partials reduced", "dG published", "acc done"]
@@ -38,3 +47,12 @@ for a, b, nxt in ((6, 0, False), (0, 1, False), (0, 2, False), (2, 3, False), (3
     d = np.mean([t[s + 1, b] - t[s, a] if nxt else t[s, b] - t[s, a] for s in steps])
     print(f"  {bw[a]:>16s} -> {('next ' if nxt else '') + bw[b]:<22s}: {d:8.0f}")
 print("  per-step deltas (dG published), steps 0..96:", " ".join(f"{t[s+1,6]-t[s,6]:.0f}" for s in range(0, 96, 6)))
+
+# cross-layer timing: %globaltimer stamps of the first CTA of every layer (kernel start, steps 0 / 1 / T/2 / T-1 stored)
+tail = trace.cpu().numpy()[2 * Tp * 8:2 * Tp * 8 + 128].reshape(2, 8, 8).astype(np.float64)
+for d, name in ((0, "FWD"), (1, "BWD")):
+    t0 = min(tail[d, l, 0] for l in range(5))
+    print(name, "per layer (us after the first CTA's start): start, step0, step1, step T/2, step T-1")
+    order = range(5) if d == 0 else range(4, -1, -1)
+    for l in order:
+        print(f"  layer {l}: " + " ".join(f"{(tail[d, l, k] - t0) / 1e3:8.1f}" for k in range(5)))
