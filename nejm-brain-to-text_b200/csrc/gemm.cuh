@@ -221,22 +221,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       __syncwarp();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * GEMM_BN;
-      uint32_t va[32], vb[32];
-      tmem_ld32(tacc, va);
-#pragma unroll
-      for (int ci = 0; ci < GEMM_BN / 32; ++ci) {
-        const int c0 = ci * 32;
-        uint32_t (&v)[32] = (ci & 1) ? vb : va;
-        tmem_ld_wait32(v);
-        if (ci + 1 < GEMM_BN / 32) tmem_ld32(tacc + c0 + 32, (ci & 1) ? va : vb);   // next chunk in flight during this one's stores
-        if (c0 + 32 == GEMM_BN) {            // accumulator fully read: hand it back to the MMA issuer before the stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        }
+      // one 32-column chunk of the accumulator row block: bias, epilogue function, staging tile, coalesced stores
+      auto process_chunk = [&](const int c0, uint32_t (&v)[32]) {
         const int n0 = tn * GEMM_BN + c0;
         const int ncols = p.N - n0;          // columns of this 32-chunk that exist
-        if (ncols <= 0) continue;            // (warp-uniform)
+        if (ncols <= 0) return;              // (warp-uniform)
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -262,7 +251,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float y = f[4 * i4 + j];
-              y = y / (1.0f + fabsf(y));
+              y = __fdividef(y, 1.0f + fabsf(y));   // (2 ulp; the result is rounded to bf16)
               if (p.keep < 1.0f) y = (u32_to_unit(rr[j]) < p.keep) ? y * inv_keep : 0.0f;
               f[4 * i4 + j] = y;
             }
@@ -301,6 +290,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 store_one<OutT>(dst + k, w[k]);
               }
           }
+        }
+      };
+      if constexpr (EPI == EPI_DAY) {
+        // The softsign + Philox epilogue is ~1 400 instructions per chunk: unrolled over the chunks (and ping-pong buffered) the
+        // kernel grew to 150 KB of code and the epilogue warps stalled on instruction fetch (ncu: 30 % "no instruction").  One
+        // rolled loop over the chunks keeps the body resident.
+        uint32_t v[32];
+#pragma unroll 1
+        for (int c0 = 0; c0 < GEMM_BN; c0 += 32) {
+          tmem_ld32(tacc + c0, v);
+          tmem_ld_wait32(v);
+          if (c0 + 32 == GEMM_BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          process_chunk(c0, v);
+        }
+      } else {
+        uint32_t va[32], vb[32];
+        tmem_ld32(tacc, va);
+#pragma unroll
+        for (int ci = 0; ci < GEMM_BN / 32; ++ci) {
+          const int c0 = ci * 32;
+          uint32_t (&v)[32] = (ci & 1) ? vb : va;
+          tmem_ld_wait32(v);
+          if (ci + 1 < GEMM_BN / 32) tmem_ld32(tacc + c0 + 32, (ci & 1) ? va : vb);   // next chunk in flight during this one's stores
+          if (c0 + 32 == GEMM_BN) {            // accumulator fully read: hand it back to the MMA issuer before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          process_chunk(c0, v);
         }
       }
       if (p.done) {
