@@ -148,6 +148,8 @@ def run_ours(args):
     flat = model.flat_parameters.detach().clone().to(dev)
     del model
     eng = E.Engine(cfg, flat, max_batch=B, max_T=T, max_label_len=64, training=True)
+    if world > 1:
+        eng.reserve_comm_sms(int(os.environ.get("B2T_COMM_SMS", "16")))   # the backward tail leaves SMs to the bucketed all-reduce
     host = synth_batches(1234 + rank, N_ROT)
     for hb in host:
         for k in hb:
@@ -200,6 +202,8 @@ def run_ours(args):
         loss = eng.ctc_loss(d["labels"], in_len, d["lens"], grad_scale=gscale, max_target_len=45)
         eng.backward()
         if world > 1:
+            if os.environ.get("B2T_BENCH_COMM_SERIAL"):     # diagnostic: no overlap at all (collective issued after backward has drained)
+                torch.cuda.current_stream().synchronize()
             eng.all_reduce_grads()                          # the step's gradient all-reduce (gradients + day-touched flags), issued bucket by bucket behind backward
         eng.optimizer_step(lr, wd, 0.9, 0.999, 0.1, 10.0)
         if from_host:

@@ -128,6 +128,9 @@ int b2t_set_dlogits(b2t_engine* e, const float* dlogits, void* stream);
  * Gradients of day layers absent from the batch are left untouched (their "touched" flag stays 0). */
 int b2t_backward(b2t_engine* e, void* stream);
 
+/* Data parallel: leave n_sms SMs free during the tail of backward (weight-gradient and layer-0 data-gradient GEMMs otherwise hold
+ * every SM with one persistent CTA) so that the collective of the finished gradient buckets runs beside it.  0 = none (default). */
+int b2t_set_comm_sms(b2t_engine* e, int n_sms);
 /* Gradient buckets for data parallelism: contiguous ranges of the gradient buffer together with the point of b2t_backward after
  * which each is final, so that the caller's all-reduce of one bucket overlaps the rest of backward (the reference is single-GPU;
  * one all-reduce per step is the north-star's collective, here issued bucket by bucket).  After b2t_backward: bucket i in

@@ -65,6 +65,7 @@ def _load():
         "b2t_backward": (ci, [vp, vp]),
         "b2t_optimizer_step": (ci, [vp, C.POINTER(AdamWArgs), vp, vp]),
         "b2t_grad_buckets": (ci, [vp]),
+        "b2t_set_comm_sms": (ci, [vp, ci]),
         "b2t_grad_bucket": (ci, [vp, ci, C.POINTER(ll), C.POINTER(ll)]),
         "b2t_grad_bucket_wait": (ci, [vp, ci, vp]),
         "b2t_step_counters": (vp, [vp]),

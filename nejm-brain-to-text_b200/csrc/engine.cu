@@ -169,6 +169,7 @@ struct b2t_engine {
   bool plans_ok = false, use_unfold_copy = false;
   GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw;
   std::vector<GemmPlan> p_dwih, p_dwhh, p_dwih0;   // p_dwih0: layer-0 dW_ih per time chunk (accumulating)
+  int comm_sms = 0;                               // SMs the backward tail leaves to the collective (0 = none reserved)
   GemmPlan p_dwih_b, p_dwhh_b;                     // all layers' dW_ih (l >= 1) / dW_hh in one batched launch each (stack schedule)
   bool dw_batched = false;
   std::vector<std::vector<GemmPlan>> p_in, p_dx;     // [layer >= 1][chunk]
@@ -451,6 +452,9 @@ static int build_plans(b2t_engine* e) {
   e->poll_delay_b = env_int("B2T_POLL_DELAY_BWD", 300);
   const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp, M = e->M, K0 = e->K0, T = e->T_in;
   const bool tr = e->training != 0;
+  // Data parallel: the gradient all-reduce of the early buckets runs while the tail of backward (persistent GEMMs, one CTA per SM)
+  // still computes; NCCL's CTAs only get SMs the GEMMs leave free, so the tail GEMMs can be told to leave some (b2t_set_comm_sms)
+  const int tail_ctas = e->comm_sms > 0 ? std::max(num_sms() - e->comm_sms, 8) : 0;
   // ---- recurrence geometry: trials per CTA, concurrent launches, time chunks.  A tcgen05.mma costs the same for every
   //      N <= 64 (profiles/r1_mma_dispatch_microbench.md), so wider batch groups need fewer CTAs for the same MMA time.
   auto pick_bg = [&](const char* env) {
@@ -619,6 +623,7 @@ static int build_plans(b2t_engine* e) {
         } else {
           s.B = e->xu + (size_t)t0 * Bp * K0; s.ldb = K0;
         }
+        s.max_ctas = tail_ctas;
         if ((rc = gemm_plan_build(&e->p_dwih0[c], s))) return fail(B2T_ERR_CUDA, "dW_ih0 plan %d failed (%d)", c, rc);
       }
     } else {  // dW_ih = dGx^T X
@@ -655,6 +660,7 @@ static int build_plans(b2t_engine* e) {
           s.tm_reverse = 1; s.max_ctas = e->stk_gemm_ctas;   // (no completion counters: the consumer polls the sentinel-filled dY itself)
         }
       }
+      if (l == 0) s.max_ctas = tail_ctas;
       if ((rc = gemm_plan_build(&e->p_dx[l][c], s))) return fail(B2T_ERR_CUDA, "dX plan %d/%d failed (%d)", l, c, rc);
     }
   }
@@ -676,7 +682,7 @@ static int build_plans(b2t_engine* e) {
       GemmSpec s;
       s.a_mn = 1; s.b_mn = 1; s.epi = EPI_STORE; s.bn = 128;
       s.M = 3 * H; s.N = H; s.K = M; s.lda = 3 * H; s.ldb = H; s.ldc = H;
-      s.a_zstride = za; s.b_zstride = za;
+      s.a_zstride = za; s.b_zstride = za; s.max_ctas = tail_ctas;
       GemmSpec ih = s;
       ih.nz = L - 1; ih.A = e->lay[1].dGx; ih.B = e->lay[0].hdrop; ih.C = e->grads + seg_off(e, "gru.weight_ih_l1"); ih.c_zstride = zc_ih;
       GemmSpec hh = s;
@@ -692,6 +698,7 @@ static int build_plans(b2t_engine* e) {
     s.B = e->dpre; s.ldb = D; s.b_zstride = (long long)T * D; s.nzb = e->B;
     s.z_map = e->day_idx; s.zmap_b = 0;
     s.C = e->grads + seg_off(e, "day_weights.0"); s.ldc = D; s.c_zstride = (long long)D * D;
+    s.max_ctas = tail_ctas;
     if ((rc = gemm_plan_build(&e->p_daydw, s))) return fail(B2T_ERR_CUDA, "dW_day plan failed (%d)", rc);
   }
   return 0;
@@ -717,6 +724,12 @@ static int gauss_taps(float std, int size, float* taps16, int* ntaps) {
   for (int i = 0; i < 16; ++i) taps16[i] = 0.f;
   for (size_t i = 0; i < k.size(); ++i) taps16[16 - k.size() + i] = k[i] / s;
   *ntaps = (int)k.size();
+  return 0;
+}
+
+extern "C" int b2t_set_comm_sms(b2t_engine* e, int n_sms) {
+  if (!e || n_sms < 0 || n_sms >= num_sms()) return fail(B2T_ERR_ARG, "b2t_set_comm_sms: bad arguments");
+  if (e->comm_sms != n_sms) { e->comm_sms = n_sms; e->plans_ok = false; }
   return 0;
 }
 
@@ -1193,6 +1206,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     e->bucket_order.clear();
     { TlScope tl("dWih0", 7, bw); CK(gemm_run(e->p_dwih0[0], bw)); ++g_launches; }
     CK(cudaEventRecord(e->ev_bucket[1], bw)); e->bucket_order.push_back(1);
+    e->bucket_order.push_back(0);                               // day layers: final when the DX0 -> fold -> day-dW chain ends, about when dW_ih0 does
     if (e->dw_batched) {
       { TlScope tl("dWihB", 7, bw); CK(gemm_run(e->p_dwih_b, bw)); ++g_launches; }
       { TlScope tl("dWhhB", 7, bw); CK(gemm_run(e->p_dwhh_b, bw)); ++g_launches; }
@@ -1210,7 +1224,6 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       CK(cudaEventRecord(e->ev_bucket[2 + l], bw)); e->bucket_order.push_back(2 + l);    // (bias gradients were final when the recurrence ended)
     }
     CK(cudaEventRecord(e->ev_bucket[L + 2], bw)); e->bucket_order.push_back(L + 2);      // head (before the recurrence), h0 (all layers), touched flags
-    e->bucket_order.push_back(0);
     for (int i = MAX_LANES; i <= MAX_LANES + 1; ++i) {
       CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
       CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));

@@ -218,6 +218,10 @@ class Engine:
     def backward(self):
         N.check(N.lib.b2t_backward(self.handle, _stream()), "b2t_backward")
 
+    def reserve_comm_sms(self, n_sms: int):
+        """Data parallel: the tail of backward leaves n_sms SMs to the gradient all-reduce (b2t_set_comm_sms)."""
+        N.check(N.lib.b2t_set_comm_sms(self.handle, int(n_sms)), "b2t_set_comm_sms")
+
     def all_reduce_grads(self, group=None):
         """Data-parallel gradient exchange: SUM all-reduce of the flat gradient buffer (gradients + day-touched flags), issued
         bucket by bucket in the order backward finishes them, on a side stream, so that the collective of the early buckets
