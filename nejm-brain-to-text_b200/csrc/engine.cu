@@ -170,7 +170,8 @@ struct b2t_engine {
   GemmPlan p_day, p_head, p_dwout, p_dytop, p_daydw;
   std::vector<GemmPlan> p_dwih, p_dwhh, p_dwih0;   // p_dwih0: layer-0 dW_ih per time chunk (accumulating)
   int comm_sms = 0;                               // SMs the backward tail leaves to the collective (0 = none reserved)
-  GemmPlan p_dwih_b, p_dwhh_b;                     // all layers' dW_ih (l >= 1) / dW_hh in one batched launch each (stack schedule)
+  GemmPlan p_dwih_b, p_dwhh_b, p_dwih0_h[2];
+  bool dwih0_split = false;                     // all layers' dW_ih (l >= 1) / dW_hh in one batched launch each (stack schedule)
   bool dw_batched = false;
   std::vector<std::vector<GemmPlan>> p_in, p_dx;     // [layer >= 1][chunk]
   // side streams / events of the wave-front
@@ -374,17 +375,20 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
     if (pe != cudaSuccess) { fail(B2T_ERR_CUDA, "kernel preload failed: %s", cudaGetErrorString(pe)); b2t_engine_destroy(e); return nullptr; }
   }
   if (training) {
-    // buckets: 0 = day layers; 1 = layer-0 input weights; 2 + l = rest of layer l (layer 0: W_hh + biases); L + 2 = head, h0, touched flags
+    // buckets: 0 = day layers; 1 = layer-0 input weights, first half of the rows; 2 + l = rest of layer l (layer 0: W_hh + biases);
+    // L + 2 = head, h0, touched flags; L + 3 = layer-0 input weights, second half of the rows
     const long long n_grad = e->n_params + r64(e->cfg.n_days);
     auto off = [&](const std::string& n) { return seg_off(e, n); };
     e->bucket_range.push_back({0, off("gru.weight_ih_l0")});
-    e->bucket_range.push_back({off("gru.weight_ih_l0"), off("gru.weight_hh_l0") - off("gru.weight_ih_l0")});
+    const long long wih0_half = (long long)(3 * e->H / 2) * e->K0;   // rows [0, 3H/2) of W_ih0; the rest is bucket L + 3
+    e->bucket_range.push_back({off("gru.weight_ih_l0"), wih0_half});
     for (int l = 0; l < e->L; ++l) {
       const long long b = l == 0 ? off("gru.weight_hh_l0") : off("gru.weight_ih_l" + std::to_string(l));
       const long long en = l + 1 < e->L ? off("gru.weight_ih_l" + std::to_string(l + 1)) : off("out.weight");
       e->bucket_range.push_back({b, en - b});
     }
     e->bucket_range.push_back({off("out.weight"), n_grad - off("out.weight")});
+    e->bucket_range.push_back({off("gru.weight_ih_l0") + wih0_half, off("gru.weight_hh_l0") - off("gru.weight_ih_l0") - wih0_half});
     e->ev_bucket.assign(e->bucket_range.size(), nullptr);
     for (auto& ev : e->ev_bucket)
       if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { fail(B2T_ERR_CUDA, "event creation failed"); b2t_engine_destroy(e); return nullptr; }
@@ -448,6 +452,7 @@ extern "C" int b2t_refresh_weights(b2t_engine* e, void* stream) {
 
 // ------------------------------------------------------------------------------------ plans
 static int build_plans(b2t_engine* e) {
+  e->dwih0_split = false;
   e->poll_delay = env_int("B2T_POLL_DELAY", 700);
   e->poll_delay_b = env_int("B2T_POLL_DELAY_BWD", 300);
   const int D = e->D, H = e->H, L = e->L, Bp = e->Bpad, Tp = e->Tp, M = e->M, K0 = e->K0, T = e->T_in;
@@ -625,6 +630,16 @@ static int build_plans(b2t_engine* e) {
         }
         s.max_ctas = tail_ctas;
         if ((rc = gemm_plan_build(&e->p_dwih0[c], s))) return fail(B2T_ERR_CUDA, "dW_ih0 plan %d failed (%d)", c, rc);
+        if (nch == 1 && (3 * H / 2) % 128 == 0) {   // the same product as two row halves: each is a gradient bucket of its own, so the all-reduce of the first runs beside the GEMM of the second
+          e->dwih0_split = true;
+          for (int h = 0; h < 2; ++h) {
+            GemmSpec hs = s;
+            hs.M = 3 * H / 2;
+            hs.A = (const __nv_bfloat16*)s.A + (size_t)h * (3 * H / 2);
+            hs.C = (float*)s.C + (size_t)h * (3 * H / 2) * K0;
+            if ((rc = gemm_plan_build(&e->p_dwih0_h[h], hs))) { e->dwih0_split = false; break; }
+          }
+        }
       }
     } else {  // dW_ih = dGx^T X
       GemmSpec s;
@@ -1204,26 +1219,42 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       CK(cudaEventRecord(e->ev_bucket[0], bs));                 // day layers final
     }
     e->bucket_order.clear();
-    { TlScope tl("dWih0", 7, bw); CK(gemm_run(e->p_dwih0[0], bw)); ++g_launches; }
-    CK(cudaEventRecord(e->ev_bucket[1], bw)); e->bucket_order.push_back(1);
-    e->bucket_order.push_back(0);                               // day layers: final when the DX0 -> fold -> day-dW chain ends, about when dW_ih0 does
-    if (e->dw_batched) {
-      { TlScope tl("dWihB", 7, bw); CK(gemm_run(e->p_dwih_b, bw)); ++g_launches; }
-      { TlScope tl("dWhhB", 7, bw); CK(gemm_run(e->p_dwhh_b, bw)); ++g_launches; }
-    }
-    for (int l = L - 1; l >= 0; --l) {
-      const std::string sl = std::to_string(l);
-      if (!e->dw_batched) {
-        if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwih[l], bw)); ++g_launches; }
-        { TlScope tl(("dWhh" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwhh[l], bw)); ++g_launches; }
+    // Weight gradients.  Order = the order in which the gradient buckets become final, chosen so that the LAST one is small (its
+    // all-reduce cannot overlap anything): all upper-layer weights in two batched launches, then layer 0's input weights in two halves.
+    auto upper_layers = [&]() -> int {
+      if (e->dw_batched) {
+        { TlScope tl("dWihB", 7, bw); CK(gemm_run(e->p_dwih_b, bw)); ++g_launches; }
+        { TlScope tl("dWhhB", 7, bw); CK(gemm_run(e->p_dwhh_b, bw)); ++g_launches; }
       }
-      if (!e->states_given) {
-        reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bw>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
-        CK(LAUNCHED());
+      for (int l = L - 1; l >= 0; --l) {
+        const std::string sl = std::to_string(l);
+        if (!e->dw_batched) {
+          if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwih[l], bw)); ++g_launches; }
+          { TlScope tl(("dWhh" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwhh[l], bw)); ++g_launches; }
+        }
+        if (!e->states_given) {
+          reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bw>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
+          CK(LAUNCHED());
+        }
+        CK(cudaEventRecord(e->ev_bucket[2 + l], bw)); e->bucket_order.push_back(2 + l);    // (bias gradients were final when the recurrence ended)
       }
-      CK(cudaEventRecord(e->ev_bucket[2 + l], bw)); e->bucket_order.push_back(2 + l);    // (bias gradients were final when the recurrence ended)
+      CK(cudaEventRecord(e->ev_bucket[L + 2], bw)); e->bucket_order.push_back(L + 2);      // head (before the recurrence), h0 (all layers), touched flags
+      return 0;
+    };
+    if (e->dwih0_split && e->dw_batched && env_int("B2T_TAIL_SPLIT", 0)) {   // (measured on 2 GPUs: 3.77 ms against 3.74 ms for the plain order below -- the collective and the GEMMs share HBM, a finer overlap does not pay)
+      if (int rc = upper_layers()) return rc;
+      { TlScope tl("dWih0a", 7, bw); CK(gemm_run(e->p_dwih0_h[0], bw)); ++g_launches; }
+      CK(cudaEventRecord(e->ev_bucket[1], bw)); e->bucket_order.push_back(1);
+      e->bucket_order.push_back(0);                             // day layers: final when the DX0 -> fold -> day-dW chain ends
+      { TlScope tl("dWih0b", 7, bw); CK(gemm_run(e->p_dwih0_h[1], bw)); ++g_launches; }
+      CK(cudaEventRecord(e->ev_bucket[L + 3], bw)); e->bucket_order.push_back(L + 3);
+    } else {
+      { TlScope tl("dWih0", 7, bw); CK(gemm_run(e->p_dwih0[0], bw)); ++g_launches; }
+      CK(cudaEventRecord(e->ev_bucket[1], bw)); e->bucket_order.push_back(1);
+      CK(cudaEventRecord(e->ev_bucket[L + 3], bw)); e->bucket_order.push_back(L + 3);
+      e->bucket_order.push_back(0);
+      if (int rc = upper_layers()) return rc;
     }
-    CK(cudaEventRecord(e->ev_bucket[L + 2], bw)); e->bucket_order.push_back(L + 2);      // head (before the recurrence), h0 (all layers), touched flags
     for (int i = MAX_LANES; i <= MAX_LANES + 1; ++i) {
       CK(cudaEventRecord(e->ev_lane_end[i], e->lane[i]));
       CK(cudaStreamWaitEvent(st, e->ev_lane_end[i], 0));

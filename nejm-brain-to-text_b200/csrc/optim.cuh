@@ -78,15 +78,31 @@ clip_adamw_kernel(const AdamParams a) {
   const float step_size = lr / bc1;
   const long long base = sg.offset + cr.first;
   const int n = (int)((sg.size - cr.first) < OPT_CHUNK ? (sg.size - cr.first) : OPT_CHUNK);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const long long k = base + i;
-    const float g = a.g[k] * coef;
-    float p = a.p[k];
-    p *= 1.0f - lr * wd;
-    const float m = a.beta1 * a.m[k] + (1.0f - a.beta1) * g;
-    const float v = a.beta2 * a.v[k] + (1.0f - a.beta2) * g * g;
+  const float decay = 1.0f - lr * wd, omb1 = 1.0f - a.beta1, omb2 = 1.0f - a.beta2;
+  auto upd = [&](float g, float& p, float& m, float& v) {
+    g *= coef;
+    p *= decay;
+    m = a.beta1 * m + omb1 * g;
+    v = a.beta2 * v + omb2 * g * g;
     const float denom = sqrtf(v) / bc2s + a.eps;
     p -= step_size * (m / denom);
+  };
+  // 16-byte accesses (segment offsets are multiples of 64 elements, chunks of 4096): 4 loads + 3 stores of 16 B and one of 8 B per thread and pass
+  const int n4 = n >> 2;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const long long k = base + 4ll * i;
+    const float4 g4 = __ldcs(reinterpret_cast<const float4*>(a.g + k));          // gradients are dead after this pass
+    float4 p4 = *reinterpret_cast<const float4*>(a.p + k), m4 = *reinterpret_cast<const float4*>(a.m + k), v4 = *reinterpret_cast<const float4*>(a.v + k);
+    upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
+    *reinterpret_cast<float4*>(a.p + k) = p4;
+    *reinterpret_cast<float4*>(a.m + k) = m4;
+    *reinterpret_cast<float4*>(a.v + k) = v4;
+    st_bf16x4(a.shadow + k, p4.x, p4.y, p4.z, p4.w);
+  }
+  for (int i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+    const long long k = base + i;
+    float p = a.p[k], m = a.m[k], v = a.v[k];
+    upd(a.g[k], p, m, v);
     a.p[k] = p; a.m[k] = m; a.v[k] = v;
     a.shadow[k] = __float2bfloat16_rn(p);
   }

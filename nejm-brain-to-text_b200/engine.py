@@ -234,10 +234,22 @@ class Engine:
         off, cnt = C.c_longlong(), C.c_longlong()
         works = []
         with torch.cuda.stream(self._comm_stream):
+            pend = None                                  # [offset, count, bucket id, largest member] not yet issued
+            def flush():
+                if pend is not None:
+                    works.append(dist.all_reduce(self.grads[pend[0]:pend[0] + pend[1]], group=group, async_op=True))
             for i in range(n):
-                N.check(N.lib.b2t_grad_bucket(self.handle, i, C.byref(off), C.byref(cnt)), "b2t_grad_bucket")
+                k = N.check(N.lib.b2t_grad_bucket(self.handle, i, C.byref(off), C.byref(cnt)), "b2t_grad_bucket")
+                o, c = off.value, cnt.value
+                # neighbouring small buckets (the layers above layer 0's input weights and the head become final together when the
+                # weight gradients are batched) travel as one collective: each all-reduce costs ~25 us of latency on its own
+                merge = pend is not None and max(c, pend[3]) < (6 << 20) and (pend[0] + pend[1] == o or o + c == pend[0])
+                if not merge:
+                    flush()
+                    pend = None
                 N.check(N.lib.b2t_grad_bucket_wait(self.handle, i, self._comm_stream.cuda_stream), "b2t_grad_bucket_wait")
-                works.append(dist.all_reduce(self.grads[off.value:off.value + cnt.value], group=group, async_op=True))
+                pend = [min(pend[0], o), pend[1] + c, k, max(pend[3], c)] if merge else [o, c, k, c]
+            flush()
         for w in works:
             w.wait()                                     # current stream waits for the collective
 
