@@ -138,6 +138,7 @@ constexpr int MAX_LANES = 5;   // concurrent recurrence launches (side streams)
 
 struct LayerBuf {
   __nv_bfloat16 *hseq, *hdrop, *R, *Z, *Nn, *HN, *dGx, *dGh;
+  unsigned char* kmask;         // keep bits of hdrop, one byte per 4 units (training)
   float *gx, *dY, *part, *h_state, *dh_state;
   int gen = 0;                                       // backward partial-exchange generation (mod 8), advanced per launch
 };
@@ -251,6 +252,7 @@ static size_t carve(b2t_engine* e, void* ws, size_t cap, bool dry) {
     b.hseq = c.take<__nv_bfloat16>((M + Bp) * H);
     __nv_bfloat16* hd = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;   // reserved for every layer so that the per-layer blocks have one stride (batched dW GEMMs)
     b.hdrop = (l < L - 1) ? hd : nullptr;
+    b.kmask = tr ? c.take<unsigned char>(M * H / 4) : nullptr;
     b.R = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
     b.Z = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
     b.Nn = tr ? c.take<__nv_bfloat16>(M * H) : nullptr;
@@ -945,6 +947,7 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
       y.hdrop = save ? e->lay[l].hdrop : nullptr;
       y.R = save ? e->lay[l].R : nullptr; y.Z = save ? e->lay[l].Z : nullptr; y.Nn = save ? e->lay[l].Nn : nullptr; y.HN = save ? e->lay[l].HN : nullptr;
       y.keep = keep_rnn; y.rng_offset = (unsigned long long)(l + 1) << 40;
+      y.kmask = (save && y.hdrop) ? e->lay[l].kmask : nullptr;
       if (!save && e->lay[l].hdrop) { y.hdrop = e->lay[l].hdrop; y.keep = 1.0f; }   // eval through a training engine: the next layer reads hdrop
       y.gx_done = l > 0 ? e->ctr + (size_t)(1 * L + l) * e->ctr_stride : nullptr;
       y.gx_need = 4 * e->p_in[l][0].p.tiles_n;
@@ -1191,6 +1194,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
       y.prog = l > 0 ? e->ctr + (size_t)(2 * L + l) * e->ctr_stride : nullptr;
       y.gen_base = e->lay[l].gen; e->lay[l].gen = (e->lay[l].gen + Tp) & 7;
       y.keep = (l < L - 1) ? keep_rnn : 1.0f;
+      y.kmask = (l < L - 1 && env_int("B2T_BWD_KMASK", 1)) ? e->lay[l].kmask : nullptr;
       y.rng_offset = (unsigned long long)(l + 1) << 40;
     }
     { TlScope tl("SRB", 0, rs); CK(launch_stack_bwd(e->stk_BG, e->stk_NSUB, sp, e->stk_grid, rs)); }

@@ -41,6 +41,7 @@ struct StackFwdLayer {
   int gx_need;                    // value gx_done[tile] reaches when the tile is complete
   float keep;                     // dropout keep probability of hdrop
   unsigned long long rng_offset;
+  unsigned char* kmask;           // [T][Bpad][H/4] keep bits of hdrop (bit i = unit 4k+i kept), re-read by the backward kernel (nullable)
 };
 
 struct StackFwdParams {
@@ -378,8 +379,14 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
           if (L.keep < 1.0f) {
             const uint4 rnd = rec_dropout_bits(p.seed, L.rng_offset, off >> 2);
             const uint32_t rr4[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+            uint32_t kb = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] = (u32_to_unit(rr4[i]) < L.keep) ? d[i] * inv_keep : 0.0f;
+            for (int i = 0; i < 4; ++i) {
+              const bool kept = u32_to_unit(rr4[i]) < L.keep;
+              d[i] = kept ? d[i] * inv_keep : 0.0f;
+              kb |= (kept ? 1u : 0u) << i;
+            }
+            if (L.kmask) L.kmask[off >> 2] = (unsigned char)kb;   // backward re-reads the mask instead of re-drawing it (the Philox rounds sat on its critical path)
           }
           st_bf16x4(L.hdrop + off, d[0], d[1], d[2], d[3]);
         }
@@ -422,6 +429,7 @@ struct StackBwdLayer {
   int gen_base;                   // generation of this launch's first step (tag = (gen >> 1) & 3, buffer = gen & 1)
   float keep;                     // dropout that forward applied to this layer's output (1 => none)
   unsigned long long rng_offset;
+  const unsigned char* kmask;     // keep bits written by the forward stack kernel (null: regenerate them from the Philox stream)
 };
 
 struct StackBwdParams {
@@ -680,6 +688,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
     auto keep_bits = [&](int b, int t) -> uint32_t {
       if (!(L.keep < 1.0f)) return 0xFu;
       const size_t off = ((size_t)t * p.Bpad + b) * p.H + j;
+      if (L.kmask) return (uint32_t)__ldg(L.kmask + (off >> 2));
       const uint4 rnd = rec_dropout_bits(p.seed, L.rng_offset, off >> 2);
       return (u32_to_unit(rnd.x) < L.keep ? 1u : 0u) | (u32_to_unit(rnd.y) < L.keep ? 2u : 0u) | (u32_to_unit(rnd.z) < L.keep ? 4u : 0u) |
              (u32_to_unit(rnd.w) < L.keep ? 8u : 0u);
