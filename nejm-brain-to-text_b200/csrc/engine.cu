@@ -371,6 +371,7 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
     if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_fwd_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<16, 1>::fwd_smem_bytes(e->H)));
     if (pe == cudaSuccess && e->H % 256 == 0) {
       pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::bwd_smem_bytes(e->H)));
+      if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::bwd_smem_bytes(e->H)));
       if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 1>::bwd_smem_bytes(e->H)));
       if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<16, 1>::bwd_smem_bytes(e->H)));
     }
@@ -812,21 +813,23 @@ static cudaError_t launch_stack_fwd_t(const StackFwdParams& p, int grid, cudaStr
   ++g_launches;
   return cudaLaunchCooperativeKernel((const void*)gru_stack_fwd_kernel<BG, NSUB>, dim3(grid), dim3(StackCfg<BG, NSUB>::kThreads), args, smem, st);
 }
-template <int BG, int NSUB>
+template <int BG, int NSUB, int ESETS = 1>
 static cudaError_t launch_stack_bwd_t(const StackBwdParams& p, int grid, cudaStream_t st) {
   const size_t smem = std::max(REC_SMEM_BYTES, StackCfg<BG, NSUB>::bwd_smem_bytes(p.H));
-  cudaError_t err = cudaFuncSetAttribute(gru_stack_bwd_kernel<BG, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = cudaFuncSetAttribute(gru_stack_bwd_kernel<BG, NSUB, ESETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_stack_bwd_kernel<BG, NSUB>, dim3(grid), dim3(StackCfg<BG, NSUB>::kThreads), args, smem, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_stack_bwd_kernel<BG, NSUB, ESETS>, dim3(grid), dim3(StackCfg<BG, NSUB>::bwd_threads(ESETS)), args, smem, st);
 }
 static cudaError_t launch_stack_fwd(int BG, int NSUB, const StackFwdParams& p, int grid, cudaStream_t st) {
   if (BG == 32) return NSUB == 2 ? launch_stack_fwd_t<32, 2>(p, grid, st) : launch_stack_fwd_t<32, 1>(p, grid, st);
   return NSUB == 1 ? launch_stack_fwd_t<16, 1>(p, grid, st) : cudaErrorInvalidValue;   // 16-trial groups only arise for an odd group count
 }
 static cudaError_t launch_stack_bwd(int BG, int NSUB, const StackBwdParams& p, int grid, cudaStream_t st) {
-  if (BG == 32) return NSUB == 2 ? launch_stack_bwd_t<32, 2>(p, grid, st) : launch_stack_bwd_t<32, 1>(p, grid, st);
+  static const int esets = env_int("B2T_BWD_ESETS", 2);   // one set of epilogue warps per batch group (see gru_stack.cuh)
+  if (BG == 32 && NSUB == 2) return esets == 2 ? launch_stack_bwd_t<32, 2, 2>(p, grid, st) : launch_stack_bwd_t<32, 2>(p, grid, st);
+  if (BG == 32) return launch_stack_bwd_t<32, 1>(p, grid, st);
   return NSUB == 1 ? launch_stack_bwd_t<16, 1>(p, grid, st) : cudaErrorInvalidValue;
 }
 
@@ -1199,6 +1202,8 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     }
     { TlScope tl("SRB", 0, rs); CK(launch_stack_bwd(e->stk_BG, e->stk_NSUB, sp, e->stk_grid, rs)); }
     CK(cudaEventRecord(e->ev_r[0], rs));
+    // (nothing else may be queued behind the recurrence on its stream before the gated GEMMs below are launched: streams share
+    //  hardware queues, and work stuck behind the recurrence would hold back the GEMMs the recurrence is waiting for)
     for (int l = L - 1; l >= 1; --l) {
       cudaStream_t gs = e->gstream[l];
       CK(cudaStreamWaitEvent(gs, e->ev_top, 0));
@@ -1208,6 +1213,12 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     }
     CK(cudaStreamWaitEvent(bs, e->ev_r[0], 0));
     CK(cudaStreamWaitEvent(bw, e->ev_r[0], 0));
+    if (!e->states_given) {   // gradient of the learned initial state: five tiny kernels, first on the weight-gradient stream so that its end is a GEMM
+      for (int l = 0; l < L; ++l) {
+        reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bw>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
+        CK(LAUNCHED());
+      }
+    }
     // chain on the first bulk stream: layer-0 data gradient -> patch fold -> day layer; everything else on the second one
     { TlScope tl("DX0", 8, bs); CK(gemm_run(e->p_dx[0][0], bs)); ++g_launches; }
     static const int dx0_first = env_int("B2T_TAIL_DX0_FIRST", 0);
@@ -1235,10 +1246,6 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
         if (!e->dw_batched) {
           if (l > 0) { TlScope tl(("dWih" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwih[l], bw)); ++g_launches; }
           { TlScope tl(("dWhh" + sl).c_str(), 7, bw); CK(gemm_run(e->p_dwhh[l], bw)); ++g_launches; }
-        }
-        if (!e->states_given) {
-          reduce_dh0_kernel<<<(H + 127) / 128, 128, 0, bw>>>(e->lay[l].dh_state, e->B, H, e->grads + seg_off(e, "h0"));
-          CK(LAUNCHED());
         }
         CK(cudaEventRecord(e->ev_bucket[2 + l], bw)); e->bucket_order.push_back(2 + l);    // (bias gradients were final when the recurrence ended)
       }

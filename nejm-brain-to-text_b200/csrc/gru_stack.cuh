@@ -56,6 +56,7 @@ struct StackFwdParams {
 template <int BG, int NSUB> struct StackCfg {
   using Base = RecCfg<BG>;
   static constexpr int kThreads = Base::kFwdThreads + 32;      // + one warp whose lane 0 publishes the layer's progress
+  static constexpr int bwd_threads(int esets) { return kThreads + (esets - 1) * Base::kEpiThreads; }
   static constexpr size_t fwd_smem_bytes(int H) {
     return (size_t)NSUB * ((size_t)2 * (H / 64) * BG * 128 + (size_t)3 * 32 * Base::kXPitch * 4) + (size_t)(NSUB * 32 + 3 * NSUB) * 8 + 64 + 1024;
   }
@@ -441,14 +442,20 @@ struct StackBwdParams {
   StackBwdLayer lay[STACK_MAX_LAYERS];
 };
 
-template <int BG, int NSUB>
-__global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads + 32, 1)
+// ESETS = 2 (with NSUB = 2): each batch group gets its own set of epilogue warps.  With one set the four phases of a step --
+// A(s,0) B(s-1,1) B(s,0) A(s,1) -- queue up behind each other on the same warps and the step is bound by their sum (measured:
+// "accumulator done -> partials reduced" 9 000 cycles of which most is waiting for the warps, not for the peers).
+template <int BG, int NSUB, int ESETS = 1>
+__global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads + 32 + (ESETS - 1) * RecCfg<BG>::kEpiThreads, 1)
 gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
+  static_assert(ESETS == 1 || (ESETS == 2 && NSUB == 2), "one epilogue set, or one per batch group");
   using Cfg = RecCfg<BG>;
   constexpr int CHUNK_BYTES = BG * 128;
   constexpr int A_CHUNK = 128 * 128;
   constexpr int UNITS = BG * 8;
-  constexpr int NTHREADS = Cfg::kFwdThreads + 32;
+  constexpr int NTHREADS = Cfg::kFwdThreads + 32 + (ESETS - 1) * Cfg::kEpiThreads;
+  constexpr int EPI_WARPS_ALL = ESETS * Cfg::kEpiWarps;     // warps 2 .. 2 + EPI_WARPS_ALL - 1
+  constexpr int NSL = ESETS == 2 ? 1 : NSUB;                // batch groups whose state one epilogue thread carries
   constexpr uint32_t TMEM_COLS = NSUB * BG < 32 ? 32 : NSUB * BG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -474,8 +481,8 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
   const int NG = p.n_cgroups * NSUB;                       // batch groups of the layer
   const StackBwdLayer& L = p.lay[layer];
   const int j0 = mb * 128 + kq * REC_US;
-  const bool is_signaller = warp == Cfg::kFwdThreads / 32;
-  const bool is_loader = warp == 0 || (warp >= 2 + Cfg::kEpiWarps && !is_signaller);
+  const bool is_signaller = warp == NTHREADS / 32 - 1;
+  const bool is_loader = warp == 0 || (warp >= 2 + EPI_WARPS_ALL && !is_signaller);
   const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_cta;
 #define STK_TRACE(step, slot) do { if (tracing) p.trace[((size_t)p.T + (step)) * 8 + (slot)] = clock64(); } while (0)
 
@@ -515,7 +522,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
 
   // Steps are indexed s = 0..T-1 for t = T-1-s.
   if (is_loader) {
-    const int lw = warp == 0 ? 0 : warp - (1 + Cfg::kEpiWarps);
+    const int lw = warp == 0 ? 0 : warp - (1 + EPI_WARPS_ALL);
     const int lt = lw * 32 + lane;
     constexpr int UPT = Cfg::kUnitsPerThread;
     constexpr int PC = UPT == 1 ? 9 : 5;
@@ -580,6 +587,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
           }
           __threadfence();
           red_release_add(L.prog + (p.T - 1 - s), 1);
+          if (p.trace) p.trace[(size_t)2 * p.T * 8 + 128 + (size_t)blockIdx.x * 8 + 5] = 0xC000 | (s << 4) | sub;
         }
       }
     }
@@ -611,20 +619,22 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
     // ---------------- epilogue.  Per (step, group): phase A = reduce partials of the previous step, gate math, publish dG_t;
     // phase B = drain the accumulator of the group's MMA into the four partial blocks.  The phases of the two groups are
     // interleaved A(s,0) B(s-1,1) B(s,0) A(s,1).
-    const int e = threadIdx.x - 64;
+    const int eset = (warp - 2) / Cfg::kEpiWarps;          // 0 when there is one set
+    const int e = threadIdx.x - 64 - eset * Cfg::kEpiThreads;
     const int ew = e >> 5;
     const int q = warp & 3;
     const int chalf = ew >> 2;
     const int bl = e >> 3, u0 = (e & 7) * 4;
     const int j = j0 + u0;
     const float inv_keep = 1.0f / L.keep;
-    float carry[NSUB][4];
+    auto SI = [](int sub) { return ESETS == 2 ? 0 : sub; };   // slot of a group's state in this thread's arrays
+    float carry[NSL][4];
     float accx[3][4], acch[4];                             // bias-gradient sums: both groups add into the same units
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       accx[0][i] = accx[1][i] = accx[2][i] = 0.f; acch[i] = 0.f;
 #pragma unroll
-      for (int sub = 0; sub < NSUB; ++sub) carry[sub][i] = 0.f;
+      for (int sub = 0; sub < NSL; ++sub) carry[sub][i] = 0.f;
     }
 
     auto block_of = [&](int grp, int gen, int dest, int src) {
@@ -693,14 +703,14 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       return (u32_to_unit(rnd.x) < L.keep ? 1u : 0u) | (u32_to_unit(rnd.y) < L.keep ? 2u : 0u) | (u32_to_unit(rnd.z) < L.keep ? 4u : 0u) |
              (u32_to_unit(rnd.w) < L.keep ? 8u : 0u);
     };
-    Stash cur[NSUB];
-    uint32_t kbits[NSUB];
+    Stash cur[NSL];
+    uint32_t kbits[NSL];
 #pragma unroll
-    for (int sub = 0; sub < NSUB; ++sub) {
-      const int b = (cgrp * NSUB + sub) * BG + bl;
-      load_fwd_stash(b, p.T - 1, cur[sub]);
-      load_dy(b, p.T - 1, cur[sub]);
-      kbits[sub] = keep_bits(b, p.T - 1);
+    for (int si = 0; si < NSL; ++si) {
+      const int b = (cgrp * NSUB + (ESETS == 2 ? eset : si)) * BG + bl;
+      load_fwd_stash(b, p.T - 1, cur[si]);
+      load_dy(b, p.T - 1, cur[si]);
+      kbits[si] = keep_bits(b, p.T - 1);
     }
 
     auto phase_a = [&](int s, int sub) {
@@ -716,9 +726,9 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       // acquire followed by the load; a 16-byte store lands whole)
       if (L.dy_polled) {
         uint32_t spins = 0;
-        while (__float_as_uint(cur[sub].dy.x) == 0xFFFFFFFFu || __float_as_uint(cur[sub].dy.w) == 0xFFFFFFFFu) {
+        while (__float_as_uint(cur[SI(sub)].dy.x) == 0xFFFFFFFFu || __float_as_uint(cur[SI(sub)].dy.w) == 0xFFFFFFFFu) {
           const uint4 v = ld_strong_v4(L.dY + ((size_t)t * p.Bpad + b) * p.H + j);
-          cur[sub].dy = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+          cur[SI(sub)].dy = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
           if (++spins > (1u << 22)) {
             if (p.trace) { long long* d = p.trace + (size_t)2 * p.T * 8 + 128 + (size_t)blockIdx.x * 8; d[0] = 0xD1; d[1] = layer; d[2] = t; d[3] = b; d[4] = j; d[5] = s; __threadfence_system(); }
             __trap();
@@ -727,7 +737,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       }
       float dmask[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dmask[i] = (L.keep < 1.0f) ? (((kbits[sub] >> i) & 1u) ? inv_keep : 0.0f) : 1.0f;
+      for (int i = 0; i < 4; ++i) dmask[i] = (L.keep < 1.0f) ? (((kbits[SI(sub)] >> i) & 1u) ? inv_keep : 0.0f) : 1.0f;
       float P[4] = {0.f, 0.f, 0.f, 0.f};
       if (s > 0) {
         if (e == 0 && sub == 0) STK_TRACE(s, 4);
@@ -735,12 +745,12 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
         if (e == 0 && sub == 0) STK_TRACE(s, 5);
       }
       float r[4], z[4], n[4], hn[4], hp[4];
-      unpack(cur[sub].r, r); unpack(cur[sub].z, z); unpack(cur[sub].n, n); unpack(cur[sub].hn, hn); unpack(cur[sub].hp, hp);
-      const float dy[4] = {cur[sub].dy.x * dmask[0], cur[sub].dy.y * dmask[1], cur[sub].dy.z * dmask[2], cur[sub].dy.w * dmask[3]};
+      unpack(cur[SI(sub)].r, r); unpack(cur[SI(sub)].z, z); unpack(cur[SI(sub)].n, n); unpack(cur[SI(sub)].hn, hn); unpack(cur[SI(sub)].hp, hp);
+      const float dy[4] = {cur[SI(sub)].dy.x * dmask[0], cur[SI(sub)].dy.y * dmask[1], cur[SI(sub)].dy.z * dmask[2], cur[SI(sub)].dy.w * dmask[3]};
       float gr[4], gz[4], gn[4], gnh[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float dh = s > 0 ? carry[sub][i] + P[i] + dy[i] : dy[i];
+        const float dh = s > 0 ? carry[SI(sub)][i] + P[i] + dy[i] : dy[i];
         const float d = valid ? dh : 0.0f;
         const float dn = d * (1.0f - z[i]);
         const float dz = d * (hp[i] - n[i]);
@@ -748,7 +758,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
         gz[i] = dz * z[i] * (1.0f - z[i]);
         gr[i] = gn[i] * hn[i] * r[i] * (1.0f - r[i]);
         gnh[i] = gn[i] * r[i];
-        carry[sub][i] = d * z[i];
+        carry[SI(sub)][i] = d * z[i];
         accx[0][i] += gr[i]; accx[1][i] += gz[i]; accx[2][i] += gn[i]; acch[i] += gnh[i];
       }
       // publish dGh_t: the data is the signal (polled by the loaders of the group's CTAs)
@@ -769,9 +779,9 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       }
       // next step's operands: forward stash, dY (possibly still the sentinel: re-polled when it is needed) and the dropout mask
       if (s + 1 < p.T) {
-        load_fwd_stash(b, t - 1, cur[sub]);
-        load_dy(b, t - 1, cur[sub]);
-        kbits[sub] = keep_bits(b, t - 1);
+        load_fwd_stash(b, t - 1, cur[SI(sub)]);
+        load_dy(b, t - 1, cur[SI(sub)]);
+        kbits[SI(sub)] = keep_bits(b, t - 1);
       }
     };
     auto phase_b = [&](int s, int sub) {
@@ -796,6 +806,9 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       if constexpr (NSUB == 1) {
         phase_a(s, 0);
         phase_b(s, 0);
+      } else if constexpr (ESETS == 2) {
+        phase_a(s, eset);
+        phase_b(s, eset);
       } else {
         // In the steady state the two groups run half a period apart: A(s,0) and B(s-1,1) are due together, then B(s,0) and A(s,1).
         // (A phase right behind the B phase it depends on -- B(s-1,1) A(s,1) -- would stall for a full L2 hand-over.)
@@ -805,10 +818,11 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
         phase_a(s, 1);
       }
     }
-    if constexpr (NSUB == 2) phase_b(p.T - 1, 1);
+    if constexpr (NSUB == 2 && ESETS == 1) phase_b(p.T - 1, 1);
     // recurrent gradient wrt the initial state: dh_{-1} = dh_0 * z_0 + dGh_0 W_hh
 #pragma unroll
-    for (int sub = 0; sub < NSUB; ++sub) {
+    for (int si = 0; si < NSL; ++si) {
+      const int sub = ESETS == 2 ? eset : si;
       const int grp = cgrp * NSUB + sub;
       const int b = grp * BG + bl;
       const bool valid = b < p.n_valid;
@@ -816,7 +830,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       reduce_partials(grp, L.gen_base + p.T - 1, P);
       float o[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = valid ? carry[sub][i] + P[i] : 0.0f;
+      for (int i = 0; i < 4; ++i) o[i] = valid ? carry[si][i] + P[i] : 0.0f;
       *reinterpret_cast<float4*>(L.dh_state + (size_t)b * p.H + j) = make_float4(o[0], o[1], o[2], o[3]);
     }
 #pragma unroll

@@ -27,6 +27,7 @@ except Exception as ex:
     for blk in range(148):
         if d[blk, 0] != 0:
             print(f"block {blk}: code {hex(int(d[blk, 0]))} {d[blk, 1:6].tolist()}")
+    print("signaller progress per block:", " ".join(f"{blk}:{int(d[blk, 5]):x}" for blk in range(120)))
     print("last phases (A, B) per block:", " ".join(f"{blk}:{int(d[blk, 6]):x}/{int(d[blk, 7]):x}" for blk in range(120)))
     sys.exit(1)
 tr = trace.cpu().numpy()[:2 * Tp * 8].reshape(2, Tp, 8).astype(np.float64)
