@@ -369,6 +369,7 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
     if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_fwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::fwd_smem_bytes(e->H)));
     if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_fwd_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 1>::fwd_smem_bytes(e->H)));
     if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_fwd_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<16, 1>::fwd_smem_bytes(e->H)));
+    if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_fwd_kernel<32, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::fwd_smem_bytes(e->H)));
     if (pe == cudaSuccess && e->H % 256 == 0) {
       pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::bwd_smem_bytes(e->H)));
       if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::bwd_smem_bytes(e->H)));
@@ -804,14 +805,14 @@ static cudaError_t launch_rec_bwd(int BG, int nsub, const RecBwdParams& p, int g
   return BG == 64 ? launch_rec_bwd_t<64, 1>(p, grid, st) : BG == 32 ? launch_rec_bwd_t<32, 1>(p, grid, st) : launch_rec_bwd_t<16, 1>(p, grid, st);
 }
 
-template <int BG, int NSUB>
+template <int BG, int NSUB, int LSETS = 1>
 static cudaError_t launch_stack_fwd_t(const StackFwdParams& p, int grid, cudaStream_t st) {
   const size_t smem = std::max(REC_SMEM_BYTES, StackCfg<BG, NSUB>::fwd_smem_bytes(p.H));
-  cudaError_t err = cudaFuncSetAttribute(gru_stack_fwd_kernel<BG, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = cudaFuncSetAttribute(gru_stack_fwd_kernel<BG, NSUB, LSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_stack_fwd_kernel<BG, NSUB>, dim3(grid), dim3(StackCfg<BG, NSUB>::kThreads), args, smem, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_stack_fwd_kernel<BG, NSUB, LSETS>, dim3(grid), dim3(StackCfg<BG, NSUB>::fwd_threads(LSETS)), args, smem, st);
 }
 template <int BG, int NSUB, int ESETS = 1>
 static cudaError_t launch_stack_bwd_t(const StackBwdParams& p, int grid, cudaStream_t st) {
@@ -823,7 +824,9 @@ static cudaError_t launch_stack_bwd_t(const StackBwdParams& p, int grid, cudaStr
   return cudaLaunchCooperativeKernel((const void*)gru_stack_bwd_kernel<BG, NSUB, ESETS>, dim3(grid), dim3(StackCfg<BG, NSUB>::bwd_threads(ESETS)), args, smem, st);
 }
 static cudaError_t launch_stack_fwd(int BG, int NSUB, const StackFwdParams& p, int grid, cudaStream_t st) {
-  if (BG == 32) return NSUB == 2 ? launch_stack_fwd_t<32, 2>(p, grid, st) : launch_stack_fwd_t<32, 1>(p, grid, st);
+  static const int lsets = env_int("B2T_FWD_LSETS", 2);   // one set of loader warps per batch group (see gru_stack.cuh)
+  if (BG == 32 && NSUB == 2) return lsets == 2 ? launch_stack_fwd_t<32, 2, 2>(p, grid, st) : launch_stack_fwd_t<32, 2>(p, grid, st);
+  if (BG == 32) return launch_stack_fwd_t<32, 1>(p, grid, st);
   return NSUB == 1 ? launch_stack_fwd_t<16, 1>(p, grid, st) : cudaErrorInvalidValue;   // 16-trial groups only arise for an odd group count
 }
 static cudaError_t launch_stack_bwd(int BG, int NSUB, const StackBwdParams& p, int grid, cudaStream_t st) {

@@ -57,6 +57,7 @@ template <int BG, int NSUB> struct StackCfg {
   using Base = RecCfg<BG>;
   static constexpr int kThreads = Base::kFwdThreads + 32;      // + one warp whose lane 0 publishes the layer's progress
   static constexpr int bwd_threads(int esets) { return kThreads + (esets - 1) * Base::kEpiThreads; }
+  static constexpr int fwd_threads(int lsets) { return kThreads + (lsets - 1) * Base::kLoadThreads; }
   static constexpr size_t fwd_smem_bytes(int H) {
     return (size_t)NSUB * ((size_t)2 * (H / 64) * BG * 128 + (size_t)3 * 32 * Base::kXPitch * 4) + (size_t)(NSUB * 32 + 3 * NSUB) * 8 + 64 + 1024;
   }
@@ -108,7 +109,7 @@ __device__ __forceinline__ float4 ldcg_f4(const float* p) {
 // poll one 16-byte unit per (producer CTA, producer epilogue warp[, gate]) -- a few KB per round -- and only when every probe
 // has been seen (named barrier over the loader warps) do they stage the operand, which still checks every word.
 template <int NLOAD_THREADS, typename AddrF>
-__device__ __forceinline__ void probe_until_published(int n_probe, int lt, AddrF addr) {
+__device__ __forceinline__ void probe_until_published(int n_probe, int lt, AddrF addr, int bar_id = 2) {
   for (int i = lt; i < n_probe; i += NLOAD_THREADS) {
     const uint8_t* a = addr(i);
     uint32_t spins = 0;
@@ -117,7 +118,7 @@ __device__ __forceinline__ void probe_until_published(int n_probe, int lt, AddrF
       if (++spins > REC_MAX_SPINS) __trap();
     }
   }
-  asm volatile("bar.sync 2, %0;" ::"n"(NLOAD_THREADS) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NLOAD_THREADS) : "memory");
 }
 
 // A load ptxas may not hoist out of a polling loop (it does hoist the weak ld.global.cg when the loop holds nothing else).
@@ -142,10 +143,15 @@ __device__ __forceinline__ long long stk_globaltimer() {
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int BG, int NSUB>
-__global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads + 32, 1)
+// LSETS = 2 (with NSUB = 2): each batch group gets its own set of loader warps, so the staging of one group's h_{t-1} no longer
+// waits behind the staging of the other group's (measured with one set: "h_t stored -> next chunk staged" 5 300 cycles, of
+// which 2 800 are the other group's staging).
+template <int BG, int NSUB, int LSETS = 1>
+__global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads + 32 + (LSETS - 1) * RecCfg<BG>::kLoadThreads, 1)
 gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
+  static_assert(LSETS == 1 || (LSETS == 2 && NSUB == 2), "one loader set, or one per batch group");
   using Cfg = RecCfg<BG>;
+  constexpr int NTHREADS = Cfg::kFwdThreads + 32 + (LSETS - 1) * Cfg::kLoadThreads;
   constexpr int XP = Cfg::kXPitch;
   constexpr int CHUNK_BYTES = BG * 128;
   constexpr int UNITS = BG * 8;
@@ -168,8 +174,10 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
   const StackFwdLayer& L = p.lay[layer];
   const int j0 = slice * REC_US;
   const int a_cols = p.H / 2;
-  const bool is_signaller = warp == Cfg::kFwdThreads / 32;
+  const bool is_signaller = warp == NTHREADS / 32 - 1;
   const bool is_loader = warp == 0 || (warp >= 2 + Cfg::kEpiWarps && !is_signaller);
+  // loader set 0 = warp 0 + the kLoadWarps - 1 warps behind the epilogue warps; set 1 (LSETS == 2) = the kLoadWarps warps after those
+  const int lset = (LSETS == 2 && warp >= 2 + Cfg::kEpiWarps + Cfg::kLoadWarps - 1) ? 1 : 0;
   const bool tracing = p.trace != nullptr && (int)blockIdx.x == p.trace_cta;
 #define STK_TRACE(step, slot) do { if (tracing) p.trace[(step) * 8 + (slot)] = clock64(); } while (0)
 
@@ -208,7 +216,7 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
 
   if (is_loader) {
     // ---------------- loaders: for every (t, group) pair in order, poll h_{t-1} of the group out of hseq and stage it
-    const int lw = warp == 0 ? 0 : warp - (1 + Cfg::kEpiWarps);
+    const int lw = warp == 0 ? 0 : (lset == 1 ? warp - (2 + Cfg::kEpiWarps + Cfg::kLoadWarps - 1) : warp - (1 + Cfg::kEpiWarps));
     const int lt = lw * 32 + lane;
     constexpr int UPT = Cfg::kUnitsPerThread;
     constexpr int ROWS_PER_PASS = Cfg::kLoadThreads / 8;
@@ -221,6 +229,7 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
       const int buf = t & 1;
 #pragma unroll
       for (int sub = 0; sub < NSUB; ++sub) {
+        if (LSETS == 2 && sub != lset) continue;              // this set serves one batch group
         const int b0 = (cgrp * NSUB + sub) * BG;
         if (t > 0) {
           mbar_wait(&bar_s[sub], (uint32_t)(t - 1) & 1u);     // this CTA has stored its own slice of h_{t-1}: the peers do so about now
@@ -233,7 +242,7 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
           const __nv_bfloat16* hrow = L.hseq + ((size_t)t * p.Bpad + b0) * p.H;
           probe_until_published<Cfg::kLoadThreads>(p.n_slices * Cfg::kEpiWarps, lt, [&](int i) {
             return reinterpret_cast<const uint8_t*>(hrow + (size_t)(4 * (i % Cfg::kEpiWarps)) * p.H + (i / Cfg::kEpiWarps) * REC_US);
-          });
+          }, 2 + lset);
         }
         const uint8_t* g = reinterpret_cast<const uint8_t*>(L.hseq + ((size_t)t * p.Bpad + b0 + row) * p.H) + seg * 16;   // slot t = h_{t-1}
         uint8_t* sdst = sH + sub * SH_SUB + (size_t)buf * KC * CHUNK_BYTES + soff;
