@@ -172,6 +172,8 @@ struct b2t_engine {
   std::vector<GemmPlan> p_dwih, p_dwhh, p_dwih0;   // p_dwih0: layer-0 dW_ih per time chunk (accumulating)
   int comm_sms = 0;                               // SMs the backward tail leaves to the collective (0 = none reserved)
   GemmPlan p_dwih_b, p_dwhh_b, p_dwih0_h[2];
+  CUtensorMap tm_hseq[STACK_MAX_LAYERS], tm_dgh[STACK_MAX_LAYERS];   // operand views for the TMA staging of the stack kernels
+  bool stk_tma = false;
   bool dwih0_split = false;                     // all layers' dW_ih (l >= 1) / dW_hh in one batched launch each (stack schedule)
   bool dw_batched = false;
   std::vector<std::vector<GemmPlan>> p_in, p_dx;     // [layer >= 1][chunk]
@@ -709,6 +711,25 @@ static int build_plans(b2t_engine* e) {
       if (gemm_plan_build(&e->p_dwih_b, ih) == 0 && gemm_plan_build(&e->p_dwhh_b, hh) == 0) e->dw_batched = true;
     }
   }
+  e->stk_tma = false;
+  // Opt-in (B2T_STACK_TMA=1): after the probe the forward loaders fetch h_{t-1} with TMA tensor loads and verify it in shared memory.
+  // Measured slower (3.07 vs 3.00 ms per step): the MMA chain can only start when the whole operand has been verified, while the
+  // polled path hands it over chunk by chunk.
+  if (e->stack && env_int("B2T_STACK_TMA", 0) != 0) {
+    bool ok = true;
+    for (int l = 0; l < L && ok; ++l) {
+      const uint64_t rows = (uint64_t)(Tp + 1) * Bp;
+      uint64_t dims[4] = {(uint64_t)H, rows, 1, 1}, str[3] = {(uint64_t)H, (uint64_t)H * rows, (uint64_t)H * rows};
+      uint32_t box[4] = {64, (uint32_t)e->stk_BG, 1, 1};
+      ok = make_tmap_bf16_4d(&e->tm_hseq[l], e->lay[l].hseq, dims, str, box) == 0;
+      if (ok && tr) {
+        const uint64_t rg = (uint64_t)Tp * Bp;
+        uint64_t d2[4] = {(uint64_t)3 * H, rg, 1, 1}, s2[3] = {(uint64_t)3 * H, (uint64_t)3 * H * rg, (uint64_t)3 * H * rg};
+        ok = make_tmap_bf16_4d(&e->tm_dgh[l], e->lay[l].dGh, d2, s2, box) == 0;
+      }
+    }
+    e->stk_tma = ok;
+  }
   {  // dW_day[day_b] += xs[b]^T dpre[b]
     GemmSpec s;
     s.a_mn = 1; s.b_mn = 1; s.epi = EPI_ATOMIC;
@@ -945,6 +966,8 @@ extern "C" int b2t_forward(b2t_engine* e, const b2t_forward_args* a, void* strea
     memset(&sp, 0, sizeof(sp));
     sp.H = H; sp.Bpad = Bp; sp.T = Tp; sp.n_slices = H / 32; sp.n_layers = L; sp.n_cgroups = e->stk_ncg;
     sp.poll_delay = env_int("B2T_STACK_POLL_DELAY", 0); sp.seed = a->seed; sp.trace = e->trace; sp.trace_cta = env_int("B2T_TRACE_CTA_FWD", 0);
+    sp.use_tma = e->stk_tma ? 1 : 0;
+    for (int l = 0; l < L; ++l) sp.tm_h[l] = e->tm_hseq[l];
     for (int l = 0; l < L; ++l) {
       const std::string sl = std::to_string(l);
       StackFwdLayer& y = sp.lay[l];

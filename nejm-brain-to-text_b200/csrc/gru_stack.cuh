@@ -50,7 +50,9 @@ struct StackFwdParams {
   int trace_cta;                  // CTA whose group 0 writes the cycle trace
   unsigned long long seed;
   long long* trace;
+  int use_tma;                    // stage h_{t-1} with TMA tensor loads (after the probe) and verify it in shared memory, instead of polled 16-byte loads
   StackFwdLayer lay[STACK_MAX_LAYERS];
+  CUtensorMap tm_h[STACK_MAX_LAYERS];   // hseq of every layer as [(T+1)*Bpad rows][H], box {64, BG}, SWIZZLE_128B
 };
 
 template <int BG, int NSUB> struct StackCfg {
@@ -59,7 +61,7 @@ template <int BG, int NSUB> struct StackCfg {
   static constexpr int bwd_threads(int esets) { return kThreads + (esets - 1) * Base::kEpiThreads; }
   static constexpr int fwd_threads(int lsets) { return kThreads + (lsets - 1) * Base::kLoadThreads; }
   static constexpr size_t fwd_smem_bytes(int H) {
-    return (size_t)NSUB * ((size_t)2 * (H / 64) * BG * 128 + (size_t)3 * 32 * Base::kXPitch * 4) + (size_t)(NSUB * 32 + 3 * NSUB) * 8 + 64 + 1024;
+    return (size_t)NSUB * ((size_t)2 * (H / 64) * BG * 128 + (size_t)3 * 32 * Base::kXPitch * 4) + (size_t)(NSUB * 32 + 4 * NSUB) * 8 + 64 + 1024;
   }
   static constexpr size_t bwd_smem_bytes(int H) {
     return (size_t)(3 * H / 4 / 64) * (128 * 128 + (size_t)NSUB * BG * 128) + (size_t)(NSUB * 16 + 3 * NSUB) * 8 + 64 + 1024;
@@ -164,7 +166,8 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
   uint64_t* bar_h = reinterpret_cast<uint64_t*>(sX + NSUB * 3 * 32 * XP);   // [NSUB][2][16]
   uint64_t* bar_d = bar_h + NSUB * 32;                      // [NSUB]
   uint64_t* bar_s = bar_d + NSUB;                           // [NSUB]
-  uint32_t* cnt_p = reinterpret_cast<uint32_t*>(bar_s + NSUB);   // [NSUB] epilogue warps that have stored a step's outputs (monotonic)
+  uint64_t* bar_t = bar_s + NSUB;                           // [NSUB] TMA staging of a group's operand
+  uint32_t* cnt_p = reinterpret_cast<uint32_t*>(bar_t + NSUB);   // [NSUB] epilogue warps that have stored a step's outputs (monotonic)
   uint32_t* tmem_slot = cnt_p + 2 * NSUB;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,7 +187,7 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
   if (threadIdx.x == 0 && p.trace != nullptr && slice == 0 && cgrp == 0) p.trace[(size_t)2 * p.T * 8 + layer * 8] = stk_globaltimer();
   if (threadIdx.x == 0) {
     for (int c = 0; c < NSUB * 32; ++c) mbar_init(&bar_h[c], Cfg::kLoadWarps);
-    for (int s = 0; s < NSUB; ++s) { mbar_init(&bar_d[s], 1); mbar_init(&bar_s[s], Cfg::kEpiWarps); cnt_p[s] = 0u; }
+    for (int s = 0; s < NSUB; ++s) { mbar_init(&bar_d[s], 1); mbar_init(&bar_s[s], Cfg::kEpiWarps); mbar_init(&bar_t[s], 1); cnt_p[s] = 0u; }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<REC_TMEM_COLS>(tmem_slot);
@@ -247,6 +250,27 @@ gru_stack_fwd_kernel(const __grid_constant__ StackFwdParams p) {
         const uint8_t* g = reinterpret_cast<const uint8_t*>(L.hseq + ((size_t)t * p.Bpad + b0 + row) * p.H) + seg * 16;   // slot t = h_{t-1}
         uint8_t* sdst = sH + sub * SH_SUB + (size_t)buf * KC * CHUNK_BYTES + soff;
         uint64_t* bars_sub = &bar_h[(sub * 2 + buf) * 16];
+        if (p.use_tma && UPT == 1) {
+          // The probe has seen every producer warp's store of this step; fetch the operand with KC tensor loads (they land in the
+          // swizzled layout the MMA reads) and verify it in shared memory: a word that is still the sentinel -- a store of the
+          // same instruction that became visible later than the probed one -- sends this warp through the polled path below.
+          if (lt == 0) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");   // the producers' generic-proxy stores -> async-proxy reads
+            mbar_arrive_expect_tx(&bar_t[sub], (uint32_t)(KC * CHUNK_BYTES));
+            uint8_t* dst0 = sH + sub * SH_SUB + (size_t)buf * KC * CHUNK_BYTES;
+            for (int c = 0; c < KC; ++c) tma_load_2d(dst0 + (size_t)c * CHUNK_BYTES, &p.tm_h[layer], &bar_t[sub], c * 64, t * p.Bpad + b0);
+          }
+          mbar_wait(&bar_t[sub], (uint32_t)t & 1u);
+          bool ok = true;
+          if (active)
+            for (int c = 0; c < KC; ++c) ok = ok && !has_sentinel(*reinterpret_cast<const uint4*>(sdst + (size_t)c * CHUNK_BYTES));
+          if (__all_sync(0xffffffffu, ok)) {
+            for (int c = 0; c < KC; ++c)
+              if (lane == 0) mbar_arrive(&bars_sub[c]);
+            if (lt == 0 && sub == 0) { STK_TRACE(t, 0); STK_TRACE(t, 1); }
+            continue;
+          }
+        }
 #pragma unroll
         for (int gi = 0; gi < (16 + PG - 1) / PG; ++gi) {    // chunk groups unrolled at compile time (a run-time loop around the poll registers spills)
           const int c0 = gi * PG;
