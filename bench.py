@@ -149,7 +149,7 @@ def run_ours(args):
     del model
     eng = E.Engine(cfg, flat, max_batch=B, max_T=T, max_label_len=64, training=True)
     if world > 1:
-        eng.reserve_comm_sms(int(os.environ.get("B2T_COMM_SMS", "16")))   # the backward tail leaves SMs to the bucketed all-reduce
+        eng.reserve_comm_sms(int(os.environ.get("B2T_COMM_SMS", "0")))   # (only useful with B2T_DP_BUCKETS=bucketed: SMs the backward tail leaves to the overlapping collectives)
     host = synth_batches(1234 + rank, N_ROT)
     for hb in host:
         for k in hb:

@@ -474,7 +474,7 @@ class BrainToTextDecoder_Trainer:
         self.model.fused_updates = True
         seed = int(self._aug_rng.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(self._aug_rng.randint(0, 2 ** 31 - 1))
         if self.world_size > 1:
-            eng.reserve_comm_sms(int(os.environ.get("B2T_COMM_SMS", "16")))   # the backward tail leaves SMs to the bucketed all-reduce
+            eng.reserve_comm_sms(int(os.environ.get("B2T_COMM_SMS", "0")))   # (only useful with B2T_DP_BUCKETS=bucketed: SMs the backward tail leaves to the overlapping collectives)
         eng.forward(features, day_indicies, training=True, smooth_mode=1 if ta['smooth_data'] else 0,
                     smooth_std=float(ta['smooth_kernel_std']), smooth_size=int(ta['smooth_kernel_size']), cut=cut,
                     white_noise_std=float(ta['white_noise_std']), offset_noise_std=float(ta['constant_offset_std']), seed=seed,
