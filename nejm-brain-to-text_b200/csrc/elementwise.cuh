@@ -273,9 +273,14 @@ __global__ void scatter_dlogits_kernel(const float* __restrict__ in, int T, int 
 __global__ void colsum_kernel(const float* __restrict__ in, size_t rows, int ld, int C, float* __restrict__ out) {
   const int c = threadIdx.x;
   if (c >= C) return;
-  float s = 0.f;
-  for (size_t r = blockIdx.x; r < rows; r += gridDim.x) s += in[r * ld + c];
-  atomicAdd(out + c, s);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent loads in flight (the column walk is latency-bound)
+  for (size_t r = (size_t)blockIdx.x * 4; r < rows; r += (size_t)gridDim.x * 4) {
+    s0 += in[r * ld + c];
+    if (r + 1 < rows) s1 += in[(r + 1) * ld + c];
+    if (r + 2 < rows) s2 += in[(r + 2) * ld + c];
+    if (r + 3 < rows) s3 += in[(r + 3) * ld + c];
+  }
+  atomicAdd(out + c, (s0 + s1) + (s2 + s3));
 }
 
 // ---------------------------------------------------------------------------------------------

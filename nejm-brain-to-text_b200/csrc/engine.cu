@@ -1196,13 +1196,20 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     }
   }
 
-  // head
-  colsum_kernel<<<64, 64, 0, st>>>(e->dlog32, (size_t)e->M, LDL, e->C, e->grads + seg_off(e, "out.bias"));
-  CK(LAUNCHED());
-  { TlScope tl("dWout", 9, st); CK(gemm_run(e->p_dwout, st)); ++g_launches; }
+  // head.  Only dY of the top layer is on the way to the backward recurrence; in the stack schedule the head's own gradients
+  // (out.bias column sums, dW_out: six tiles) are issued behind it and run beside the recurrence's first steps.
+  auto head_grads = [&]() -> int {
+    colsum_kernel<<<256, 64, 0, st>>>(e->dlog32, (size_t)e->M, LDL, e->C, e->grads + seg_off(e, "out.bias"));
+    CK(LAUNCHED());
+    { TlScope tl("dWout", 9, st); CK(gemm_run(e->p_dwout, st)); ++g_launches; }
+    return 0;
+  };
+  if (!e->stack) { if (int rc = head_grads()) return rc; }
   { TlScope tl("dYtop", 9, st); CK(gemm_run(e->p_dytop, st)); ++g_launches; }
   CK(cudaEventRecord(e->ev_top, st));
   if (e->stack) {
+    if (int rc = head_grads()) return rc;
+    CK(cudaEventRecord(e->ev_dx0, st));                      // (head gradients final: awaited before the head bucket's event below)
     // ---- whole-stack schedule: ONE persistent backward recurrence for all layers; the data-gradient GEMMs dY_{l-1} = dGx_l W_ih_l
     //      follow it as gated GEMMs (time descending) on the free SMs; weight gradients, layer-0 data gradient, fold and day layer after it
     cudaStream_t rs = e->lane[0], bs = e->lane[MAX_LANES], bw = e->lane[MAX_LANES + 1];
@@ -1247,8 +1254,6 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
     }
     // chain on the first bulk stream: layer-0 data gradient -> patch fold -> day layer; everything else on the second one
     { TlScope tl("DX0", 8, bs); CK(gemm_run(e->p_dx[0][0], bs)); ++g_launches; }
-    static const int dx0_first = env_int("B2T_TAIL_DX0_FIRST", 0);
-    if (dx0_first) { CK(cudaEventRecord(e->ev_dx0, bs)); CK(cudaStreamWaitEvent(bw, e->ev_dx0, 0)); }   // the fold -> day-layer chain hangs off DX0: let it own the chip first
     {
       FoldParams fp;
       fp.dxu = e->dxu; fp.xd = e->xd; fp.dpre = e->dpre; fp.dbias_day = e->grads + seg_off(e, "day_biases.0"); fp.bias_pitch = (int)r64(D);
@@ -1275,7 +1280,8 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
         }
         CK(cudaEventRecord(e->ev_bucket[2 + l], bw)); e->bucket_order.push_back(2 + l);    // (bias gradients were final when the recurrence ended)
       }
-      CK(cudaEventRecord(e->ev_bucket[L + 2], bw)); e->bucket_order.push_back(L + 2);      // head (before the recurrence), h0 (all layers), touched flags
+      CK(cudaStreamWaitEvent(bw, e->ev_dx0, 0));                                           // head gradients (issued beside the recurrence)
+      CK(cudaEventRecord(e->ev_bucket[L + 2], bw)); e->bucket_order.push_back(L + 2);      // head, h0 (all layers), touched flags
       return 0;
     };
     if (e->dwih0_split && e->dw_batched && env_int("B2T_TAIL_SPLIT", 0)) {   // (measured on 2 GPUs: 3.77 ms against 3.74 ms for the plain order below -- the collective and the GEMMs share HBM, a finer overlap does not pay)
