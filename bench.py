@@ -362,6 +362,10 @@ def run_ours(args):
             "achieved": dom["tflops"] if dom else whole, "frac": (dom["tflops"] if dom else whole) / peak_tf,
             "dominant_kernel": dom["name"] if dom else None,
             "traffic": None,
+            "traffic_note": "per-kernel DRAM bytes cannot be captured for the shipped schedule (ncu's kernel replay serialises launches, the stack "
+                            "kernels and their gated GEMMs wait for each other); profiles/r2_ncu_stack_and_step.md holds an app-range capture of the "
+                            "whole step (1.94 GB read + 2.21 GB written per step) and a --set full capture of the same kernels with one layer "
+                            "(gru_stack_bwd_kernel: 174 MB read + 114 MB written per 247-step launch)",
             "note": "achieved = algorithmic FLOPs of one launch of the kernel with the largest time share / its average launch duration "
                     "(CUDA events on its own stream, live in this run); the launch occupies a share of the SMs, the peak is the whole chip's",
             "whole_step": {"achieved": whole, "frac": whole / peak_tf,
