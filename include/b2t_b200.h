@@ -234,8 +234,8 @@ int b2t_decoder_decode_batch(b2t_decoder* d, const float* logits, const int* len
 int b2t_decoder_stats(b2t_decoder* d, int slot, int* frames, long long* tokens, long long* links, double* kernel_ms);
 int b2t_decoder_tokens_per_frame(b2t_decoder* d, int slot, int* out, int cap);
 
-/* LM-free CTC prefix beam search (ctc_prefix_beam_search.cc:44-136), one warp per utterance; first_beam <= 64, second_beam <= 512, and the
- * working set second_beam * (first_beam + 1) * 32 B (+ tables) must fit the 227 KB of shared memory (512 x 10 does; B2T_ERR_UNSUPPORTED otherwise).
+/* LM-free CTC prefix beam search (ctc_prefix_beam_search.cc:44-136), one warp per utterance; first_beam <= 64, second_beam <= 512.  The
+ * per-frame candidates (second_beam * (first_beam + 1) * 32 B) live in shared memory when they fit its 227 KB (512 x 10 does), else in global memory (slower).
  * Hypotheses are walked in the iteration order of the reference's unordered_map (libstdc++), on which its Viterbi times depend.
  * logp: host [N][T][C] log-probabilities; lens: host [N].  Outputs (host, best first): ids [N][second_beam][max_len],
  * len / score / viterbi [N][second_beam], times [N][second_beam][max_len], n_hyp [N]. */

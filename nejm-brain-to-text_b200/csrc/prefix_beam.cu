@@ -37,6 +37,7 @@ struct PbParams {
   const int* lens;     // [N]
   int N, T, C, blank, first_beam, second_beam, max_len;
   int cand_cap, chash_cap;                             // candidates per frame; candidate hash size (power of two)
+  struct Hyp* nxt_g; unsigned short* chash_g;          // [N][cand_cap] / [N][chash_cap] in global memory when the candidates do not fit shared memory (else null)
   // per-utterance scratch
   int* trie_parent; int* trie_token; int trie_cap;     // [N][trie_cap]
   int* trie_hash; int trie_hash_cap;                   // [N][trie_hash_cap] (power of two) -> trie node or -1
@@ -131,16 +132,18 @@ __global__ void __launch_bounds__(32) prefix_beam_kernel(const PbParams p) {
   // in global memory (one or two accesses per pair / copied by all lanes)
   extern __shared__ __align__(16) unsigned char pb_smem[];
   __shared__ int s_top[PB_MAX_TOPK];
-  Hyp* s_nxt = reinterpret_cast<Hyp*>(pb_smem);
-  Hyp* s_cur = s_nxt + p.cand_cap;
+  const int u = blockIdx.x, lane = threadIdx.x;
+  // (wide first beams: second_beam x (first_beam + 1) candidates of 32 B exceed shared memory; they then live in global memory and the
+  //  serial walk pays L2 latency per access -- a functional path for the sweep's corner, not a fast one)
+  Hyp* s_nxt = p.nxt_g ? p.nxt_g + (size_t)u * p.cand_cap : reinterpret_cast<Hyp*>(pb_smem);
+  Hyp* s_cur = p.nxt_g ? reinterpret_cast<Hyp*>(pb_smem) : s_nxt + p.cand_cap;
   unsigned long long* s_uh = reinterpret_cast<unsigned long long*>(s_cur + p.second_beam);
   int* s_order = reinterpret_cast<int*>(s_uh + p.second_beam);
   int* s_iter = s_order + p.second_beam;
   int* s_unext = s_iter + p.second_beam;
   int* s_scratch = s_unext + p.second_beam;
   int* s_ubefore = s_scratch + p.second_beam;
-  unsigned short* s_chash = reinterpret_cast<unsigned short*>(s_ubefore + PB_MAX_BUCKETS);
-  const int u = blockIdx.x, lane = threadIdx.x;
+  unsigned short* s_chash = p.chash_g ? p.chash_g + (size_t)u * p.chash_cap : reinterpret_cast<unsigned short*>(s_ubefore + PB_MAX_BUCKETS);
   if (u >= p.N) return;
   const float* logp = p.logp + (size_t)u * p.T * p.C;
   const int Tn = min(max(p.lens[u], 0), p.T);
@@ -376,9 +379,15 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
   p.chash_cap = 256;
   while (p.chash_cap < 2 * p.cand_cap && p.chash_cap < 8192) p.chash_cap *= 2;
   while (p.chash_cap * 3 < p.cand_cap * 4) p.chash_cap *= 2;          // load factor <= 0.75 when the 2x table would not fit
-  const size_t smem = (size_t)p.cand_cap * sizeof(Hyp) + (size_t)second_beam * (sizeof(Hyp) + 8 + 4 * 4) + PB_MAX_BUCKETS * 4 + (size_t)p.chash_cap * 2;
-  if (p.cand_cap >= 0xffff || smem > (size_t)PB_SMEM_LIMIT) {
-    snprintf(g_perr, sizeof(g_perr), "second_beam %d x first_beam %d needs %zu bytes of shared memory per utterance (limit %d)", second_beam, first_beam, smem, PB_SMEM_LIMIT);
+  const size_t smem_small = (size_t)second_beam * (sizeof(Hyp) + 8 + 4 * 4) + PB_MAX_BUCKETS * 4;
+  size_t smem = (size_t)p.cand_cap * sizeof(Hyp) + smem_small + (size_t)p.chash_cap * 2;
+  const bool cand_in_global = smem > (size_t)PB_SMEM_LIMIT;            // wide first beam x wide second beam
+  if (cand_in_global) {
+    smem = smem_small;
+    while (p.chash_cap < 2 * p.cand_cap) p.chash_cap *= 2;
+  }
+  if (p.cand_cap >= 0xffff) {
+    snprintf(g_perr, sizeof(g_perr), "second_beam %d x (first_beam %d + 1) candidates per frame exceed the 65534 the candidate hash can index", second_beam, first_beam);
     return B2T_ERR_UNSUPPORTED;
   }
   const size_t nb = (size_t)N * second_beam;
@@ -391,7 +400,8 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
   const size_t o_logp = carve((size_t)N * T * C * 4 + 4), o_lens = carve((size_t)N * 4), o_tp = carve((size_t)N * p.trie_cap * 4),
                o_tt = carve((size_t)N * p.trie_cap * 4), o_th = carve((size_t)N * p.trie_hash_cap * 4), o_h64 = carve((size_t)N * p.trie_cap * 8), o_times = carve(times_elems * 4),
                o_ids = carve(nb * max_len * 4), o_len = carve(nb * 4), o_score = carve(nb * 4), o_vit = carve(nb * 4),
-               o_otimes = carve(nb * max_len * 4), o_n = carve((size_t)N * 4), o_status = carve((size_t)N * 4);
+               o_otimes = carve(nb * max_len * 4), o_n = carve((size_t)N * 4), o_status = carve((size_t)N * 4),
+               o_nxt = carve(cand_in_global ? (size_t)N * p.cand_cap * sizeof(Hyp) : 0), o_ch = carve(cand_in_global ? (size_t)N * p.chash_cap * 2 : 0);
   bool ok = true;
   if (off > ws.cap) {
     if (ws.base) cudaFree(ws.base);
@@ -413,6 +423,8 @@ int b2t_prefix_beam_search(const float* logp, const int* lens, int N, int T, int
   cudaMemset(d_status, 0, N * 4); cudaMemset(d_ids, 0, nb * max_len * 4); cudaMemset(d_otimes, 0, nb * max_len * 4);
   cudaMemset(d_len, 0, nb * 4); cudaMemset(d_score, 0, nb * 4); cudaMemset(d_vit, 0, nb * 4);
   p.logp = d_logp; p.lens = d_lens; p.trie_parent = d_tp; p.trie_token = d_tt; p.trie_hash = d_th; p.trie_h64 = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws.base) + o_h64); p.times = d_times;
+  p.nxt_g = cand_in_global ? reinterpret_cast<Hyp*>(reinterpret_cast<uint8_t*>(ws.base) + o_nxt) : nullptr;
+  p.chash_g = cand_in_global ? reinterpret_cast<unsigned short*>(reinterpret_cast<uint8_t*>(ws.base) + o_ch) : nullptr;
   p.out_ids = d_ids; p.out_len = d_len; p.out_score = d_score; p.out_viterbi = d_vit; p.out_times = d_otimes; p.out_n = d_n; p.status = d_status;
   static const bool timing = getenv("B2T_DECODER_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };

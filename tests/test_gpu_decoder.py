@@ -240,10 +240,29 @@ def test_prefix_beam_sweep_widths(LM, sb):
         assert [r[0] for r in ours[n][:20]] == [r[0] for r in ref[:20]] or len({round(r[1], 6) for r in ref[:21]}) < 21
 
 
-def test_prefix_beam_rejects_what_does_not_fit(LM):
+def test_prefix_beam_width_500_full_first_beam(LM):
+    """"for prefix search first_beam = min(41, w), second_beam = w".  At w = 500 the 21 000 candidates of a
+    frame exceed shared memory and live in global memory; same hypotheses, scores and times as the oracle."""
+    rng = np.random.RandomState(77)
+    x = rng.randn(1, 14, 41).astype(np.float32) * 1.2
+    x[..., 0] += 1.0
+    lp = x - np.log(np.exp(x).sum(-1, keepdims=True))
+    ours = LM.ctc_prefix_beam_search(lp, first_beam_size=41, second_beam_size=500)[0]
+    ref = D.prefix_search(lp[0], 41, 500)
+    assert len(ours) == len(ref) == 500
+    so = {tuple(r[0]): r for r in ours}
+    sr = {tuple(r[0]): r for r in ref}
+    worst = min(r[1] for r in ref)
+    cut = lambda d: {k for k, v in d.items() if v[1] > worst + 1e-4}          # (ties with the last kept hypothesis may differ)
+    assert cut(so) == cut(sr)
+    for k in cut(sr):
+        assert so[k][1] == pytest.approx(sr[k][1], abs=1e-4) and so[k][2] == pytest.approx(sr[k][2], abs=1e-4) and so[k][3] == sr[k][3], k
+
+
+def test_prefix_beam_rejects_beams_beyond_the_caps(LM):
     lp = np.log(np.full((1, 4, 41), 1.0 / 41, dtype=np.float32))
-    with pytest.raises(Exception, match="shared memory"):
-        LM.ctc_prefix_beam_search(lp, first_beam_size=40, second_beam_size=512)
+    with pytest.raises(Exception, match="beam sizes"):
+        LM.ctc_prefix_beam_search(lp, first_beam_size=10, second_beam_size=513)
 
 
 @pytest.mark.skipif(D.real_graph() is None, reason="the shipped 1-gram graph is staged under oracle/_ref/ by __graft_entry__.build()")
