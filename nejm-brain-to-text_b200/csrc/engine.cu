@@ -375,6 +375,7 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
     if (pe == cudaSuccess && e->H % 256 == 0) {
       pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::bwd_smem_bytes(e->H)));
       if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::bwd_smem_bytes(e->H)));
+      if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 2>::bwd_smem_bytes(e->H)));
       if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<32, 1>::bwd_smem_bytes(e->H)));
       if (pe == cudaSuccess) pe = cudaFuncSetAttribute(gru_stack_bwd_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(REC_SMEM_BYTES, StackCfg<16, 1>::bwd_smem_bytes(e->H)));
     }
@@ -835,14 +836,14 @@ static cudaError_t launch_stack_fwd_t(const StackFwdParams& p, int grid, cudaStr
   ++g_launches;
   return cudaLaunchCooperativeKernel((const void*)gru_stack_fwd_kernel<BG, NSUB, LSETS>, dim3(grid), dim3(StackCfg<BG, NSUB>::fwd_threads(LSETS)), args, smem, st);
 }
-template <int BG, int NSUB, int ESETS = 1>
+template <int BG, int NSUB, int ESETS = 1, int LSPLIT = 0>
 static cudaError_t launch_stack_bwd_t(const StackBwdParams& p, int grid, cudaStream_t st) {
   const size_t smem = std::max(REC_SMEM_BYTES, StackCfg<BG, NSUB>::bwd_smem_bytes(p.H));
-  cudaError_t err = cudaFuncSetAttribute(gru_stack_bwd_kernel<BG, NSUB, ESETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = cudaFuncSetAttribute(gru_stack_bwd_kernel<BG, NSUB, ESETS, LSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   void* args[1] = {(void*)&p};
   ++g_launches;
-  return cudaLaunchCooperativeKernel((const void*)gru_stack_bwd_kernel<BG, NSUB, ESETS>, dim3(grid), dim3(StackCfg<BG, NSUB>::bwd_threads(ESETS)), args, smem, st);
+  return cudaLaunchCooperativeKernel((const void*)gru_stack_bwd_kernel<BG, NSUB, ESETS, LSPLIT>, dim3(grid), dim3(StackCfg<BG, NSUB>::bwd_threads(ESETS)), args, smem, st);
 }
 static cudaError_t launch_stack_fwd(int BG, int NSUB, const StackFwdParams& p, int grid, cudaStream_t st) {
   static const int lsets = env_int("B2T_FWD_LSETS", 2);   // one set of loader warps per batch group (see gru_stack.cuh)
@@ -852,6 +853,8 @@ static cudaError_t launch_stack_fwd(int BG, int NSUB, const StackFwdParams& p, i
 }
 static cudaError_t launch_stack_bwd(int BG, int NSUB, const StackBwdParams& p, int grid, cudaStream_t st) {
   static const int esets = env_int("B2T_BWD_ESETS", 2);   // one set of epilogue warps per batch group (see gru_stack.cuh)
+  static const int lsplit = env_int("B2T_BWD_LSPLIT", 0);   // the loader warps as two half sets, one per batch group: measured slower (3.26 vs 2.94 ms per step: half the loaders stage a group twice as slowly), opt-in
+  if (BG == 32 && NSUB == 2 && esets == 2 && lsplit) return launch_stack_bwd_t<32, 2, 2, 1>(p, grid, st);
   if (BG == 32 && NSUB == 2) return esets == 2 ? launch_stack_bwd_t<32, 2, 2>(p, grid, st) : launch_stack_bwd_t<32, 2>(p, grid, st);
   if (BG == 32) return launch_stack_bwd_t<32, 1>(p, grid, st);
   return NSUB == 1 ? launch_stack_bwd_t<16, 1>(p, grid, st) : cudaErrorInvalidValue;

@@ -478,10 +478,15 @@ struct StackBwdParams {
 // ESETS = 2 (with NSUB = 2): each batch group gets its own set of epilogue warps.  With one set the four phases of a step --
 // A(s,0) B(s-1,1) B(s,0) A(s,1) -- queue up behind each other on the same warps and the step is bound by their sum (measured:
 // "accumulator done -> partials reduced" 9 000 cycles of which most is waiting for the warps, not for the peers).
-template <int BG, int NSUB, int ESETS = 1>
+// LSPLIT = 1 (with NSUB = 2): the 8 loader warps work as two sets of 4, one per batch group (two 16-byte units per thread and chunk),
+// so that a group's dG is staged the moment it is published instead of behind the other group's staging.
+template <int BG, int NSUB, int ESETS = 1, int LSPLIT = 0>
 __global__ void __launch_bounds__(RecCfg<BG>::kFwdThreads + 32 + (ESETS - 1) * RecCfg<BG>::kEpiThreads, 1)
 gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
   static_assert(ESETS == 1 || (ESETS == 2 && NSUB == 2), "one epilogue set, or one per batch group");
+  static_assert(LSPLIT == 0 || (NSUB == 2 && BG == 32), "split loader sets are written for two groups of 32 trials");
+  constexpr int LOAD_WARPS = LSPLIT ? RecCfg<BG>::kLoadWarps / 2 : RecCfg<BG>::kLoadWarps;   // per set
+  constexpr int LOAD_THREADS = 32 * LOAD_WARPS;
   using Cfg = RecCfg<BG>;
   constexpr int CHUNK_BYTES = BG * 128;
   constexpr int A_CHUNK = 128 * 128;
@@ -521,7 +526,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
 
   if (threadIdx.x == 0 && p.trace != nullptr && rl == 0) p.trace[(size_t)2 * p.T * 8 + 64 + layer * 8] = stk_globaltimer();
   if (threadIdx.x == 0) {
-    for (int c = 0; c < NSUB * 16; ++c) mbar_init(&bar_h[c], Cfg::kLoadWarps);
+    for (int c = 0; c < NSUB * 16; ++c) mbar_init(&bar_h[c], LOAD_WARPS);
     for (int s = 0; s < NSUB; ++s) { mbar_init(&bar_d[s], 1); mbar_init(&bar_s[s], Cfg::kEpiWarps); cnt_p[s] = 0u; }
     fence_mbar_init();
   }
@@ -555,11 +560,13 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
 
   // Steps are indexed s = 0..T-1 for t = T-1-s.
   if (is_loader) {
-    const int lw = warp == 0 ? 0 : warp - (1 + EPI_WARPS_ALL);
+    const int lw_all = warp == 0 ? 0 : warp - (1 + EPI_WARPS_ALL);          // 0 .. kLoadWarps - 1
+    const int lset = LSPLIT ? lw_all / LOAD_WARPS : 0;
+    const int lw = LSPLIT ? lw_all % LOAD_WARPS : lw_all;
     const int lt = lw * 32 + lane;
-    constexpr int UPT = Cfg::kUnitsPerThread;
+    constexpr int UPT = (UNITS + LOAD_THREADS - 1) / LOAD_THREADS;
     constexpr int PC = UPT == 1 ? 9 : 5;
-    constexpr int ROWS_PER_PASS = Cfg::kLoadThreads / 8;
+    constexpr int ROWS_PER_PASS = LOAD_THREADS / 8;
     const bool active = lt < UNITS / UPT;
     const int row = lt >> 3, seg = lt & 7;
     const uint32_t soff = row * 128 + ((seg ^ (row & 7)) << 4);
@@ -568,6 +575,7 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
       const int t = p.T - 1 - s;
 #pragma unroll
       for (int sub = 0; sub < NSUB; ++sub) {
+        if (LSPLIT && sub != lset) continue;                   // this set serves one batch group
         const int b0 = (cgrp * NSUB + sub) * BG;
         // start when this CTA's own epilogue has published dG_t of the group (also orders the staging after MMA(s-1, group),
         // which read the same single buffer: dG of step s is published only after the accumulator of step s-1 was drained)
@@ -579,10 +587,10 @@ gru_stack_bwd_kernel(const __grid_constant__ StackBwdParams p) {
         {   // probe (producer CTA of this contraction quarter, its epilogue warp, gate)
           const __nv_bfloat16* grow = L.dGh + ((size_t)t * p.Bpad + b0) * 3 * p.H + kq * KQ;
           const int npc = KQ / REC_US;
-          probe_until_published<Cfg::kLoadThreads>(npc * Cfg::kEpiWarps * 3, lt, [&](int i) {
+          probe_until_published<LOAD_THREADS>(npc * Cfg::kEpiWarps * 3, lt, [&](int i) {
             const int gate = i % 3, w = (i / 3) % Cfg::kEpiWarps, pc = i / (3 * Cfg::kEpiWarps);
             return reinterpret_cast<const uint8_t*>(grow + (size_t)(4 * w) * 3 * p.H + (size_t)gate * p.H + pc * REC_US);
-          });
+          }, 2 + lset);
         }
         const uint8_t* g = reinterpret_cast<const uint8_t*>(L.dGh + ((size_t)t * p.Bpad + b0 + row) * 3 * p.H + kq * KQ) + seg * 16;
         auto chunk_addr = [&](int cc) {
