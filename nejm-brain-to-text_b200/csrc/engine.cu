@@ -179,7 +179,7 @@ struct b2t_engine {
   std::vector<std::vector<GemmPlan>> p_in, p_dx;     // [layer >= 1][chunk]
   // side streams / events of the wave-front
   cudaStream_t lane[MAX_LANES + 2] = {};   // [MAX_LANES] = bulk stream (layer-0 projections / data gradients), [MAX_LANES + 1] = second bulk stream (weight gradients)
-  cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 2] = {}, ev_top = nullptr, ev_init = nullptr, ev_dx0 = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_lane_end[MAX_LANES + 2] = {}, ev_top = nullptr, ev_init = nullptr, ev_head = nullptr;
   std::vector<cudaEvent_t> ev_r, ev_dx;              // [layer * MAX_CHUNKS + chunk]
   cudaEvent_t ev_g0[MAX_CHUNKS] = {};                // layer-0 input projection chunks (issued ahead on the bulk stream)
   // state of the last forward
@@ -316,7 +316,7 @@ extern "C" void b2t_engine_destroy(b2t_engine* e) {
   }
   if (e->ev_start) cudaEventDestroy(e->ev_start);
   if (e->ev_top) cudaEventDestroy(e->ev_top);
-  if (e->ev_dx0) cudaEventDestroy(e->ev_dx0);
+  if (e->ev_head) cudaEventDestroy(e->ev_head);
   if (e->ev_init) cudaEventDestroy(e->ev_init);
   for (cudaEvent_t ev : e->ev_r) if (ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : e->ev_dx) if (ev) cudaEventDestroy(ev);
@@ -347,7 +347,7 @@ extern "C" b2t_engine* b2t_engine_create(const b2t_config* cfg, int max_batch, i
   e->touched = grads ? grads + e->n_params : nullptr;
   bool ok = cudaEventCreateWithFlags(&e->ev_start, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_top, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&e->ev_dx0, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_head, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_init, cudaEventDisableTiming) == cudaSuccess;
   // recurrence lanes outrank the bulk stream: when SMs free up, the latency-critical cooperative launches are placed first
   int prio_lo = 0, prio_hi = 0;
@@ -1212,7 +1212,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
   CK(cudaEventRecord(e->ev_top, st));
   if (e->stack) {
     if (int rc = head_grads()) return rc;
-    CK(cudaEventRecord(e->ev_dx0, st));                      // (head gradients final: awaited before the head bucket's event below)
+    CK(cudaEventRecord(e->ev_head, st));                      // (head gradients final: awaited before the head bucket's event below)
     // ---- whole-stack schedule: ONE persistent backward recurrence for all layers; the data-gradient GEMMs dY_{l-1} = dGx_l W_ih_l
     //      follow it as gated GEMMs (time descending) on the free SMs; weight gradients, layer-0 data gradient, fold and day layer after it
     cudaStream_t rs = e->lane[0], bs = e->lane[MAX_LANES], bw = e->lane[MAX_LANES + 1];
@@ -1283,7 +1283,7 @@ extern "C" int b2t_backward(b2t_engine* e, void* stream) {
         }
         CK(cudaEventRecord(e->ev_bucket[2 + l], bw)); e->bucket_order.push_back(2 + l);    // (bias gradients were final when the recurrence ended)
       }
-      CK(cudaStreamWaitEvent(bw, e->ev_dx0, 0));                                           // head gradients (issued beside the recurrence)
+      CK(cudaStreamWaitEvent(bw, e->ev_head, 0));                                           // head gradients (issued beside the recurrence)
       CK(cudaEventRecord(e->ev_bucket[L + 2], bw)); e->bucket_order.push_back(L + 2);      // head, h0 (all layers), touched flags
       return 0;
     };
