@@ -23,6 +23,7 @@
 // The irregular once-per-sentence work (final-cost pruning, best path, n-best) runs on the host from the
 // token/link pools.
 #include <math.h>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -780,6 +781,7 @@ struct b2t_decoder {
   std::vector<Slot> slots;
   cudaStream_t stream = nullptr;
   double last_kernel_ms = 0.0;
+  std::atomic<float> nbest_margin_hint{1.0f};   // cost margin that sufficed for the last n-best extraction (collect_nbest starts there)
   void *lm_old = nullptr, *lm_new = nullptr;   // LmAcceptor*: the LM the graph was built from / the rescoring LM (DecodeResource lm_fst_path, rescore_lm_fst_path)
 };
 
@@ -1059,7 +1061,11 @@ void collect_nbest(b2t_decoder* d, const Lattice& L, const std::vector<float>& e
       v.resize(cap);
     }
   };
-  for (float margin = std::min(1.0f, full);; margin = std::min(margin * 2.0f, full)) {
+  // (the first margin is the one that sufficed for the previous utterances of this decoder, so that the usual case is one pass)
+  const float hint = d->nbest_margin_hint.load(std::memory_order_relaxed);
+  int passes = 0;
+  for (float margin = std::min(std::max(hint, 1.0f), full);; margin = std::min(margin * 2.0f, full)) {
+    ++passes;
     const float limit = beta[0] + margin + 1e-4f;
     WordTrie trie;
     std::vector<std::vector<Hyp>> hyps(nt);
@@ -1095,6 +1101,7 @@ void collect_nbest(b2t_decoder* d, const Lattice& L, const std::vector<float>& e
     const bool complete = margin >= full || ((int)finals.size() >= K && finals[K - 1].g + finals[K - 1].a <= beta[0] + margin);
     if (!complete) continue;
     for (size_t i = 0; i < finals.size() && (int)i < K; ++i) out->push_back(NbOut{trie.words(finals[i].seq), finals[i].g, finals[i].a});
+    d->nbest_margin_hint.store(passes == 1 ? std::max(1.0f, margin * 0.8f) : margin, std::memory_order_relaxed);
     break;
   }
 }
