@@ -514,7 +514,8 @@ static int build_plans(b2t_engine* e) {
     // for each other while running (the persistent recurrence and its gated GEMMs): under them the stack schedule is off unless
     // B2T_STACK=1 forces it (single-layer models have no cross-kernel dependency and can be profiled with it).
     static const bool serialising_tool = getenv("NV_NSIGHT_INJECTION_PORT_BASE") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ||
-                                         getenv("NV_SANITIZER_INJECTION_PORT_BASE");
+                                         getenv("NV_SANITIZER_INJECTION_PORT_BASE") ||
+                                         (getenv("CUDA_LAUNCH_BLOCKING") && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);   // blocking launches serialise as well
     bool ok = env_int("B2T_STACK", serialising_tool ? 0 : 1) != 0 && L <= STACK_MAX_LAYERS && grid + std::max(L - 1, 0) <= num_sms() && smem_f <= 227 * 1024 &&
               128 % bg == 0 && (nsub * bg) <= 128 && (128 % (nsub * bg) == 0);
     if (tr) ok = ok && (H % 256 == 0);          // backward uses the two-dimensional decomposition (H/128 x 4 CTAs per batch group)
